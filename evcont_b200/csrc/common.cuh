@@ -1,0 +1,63 @@
+// Internal helpers shared by the translation units of libevcont_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "evcont_b200.h"
+
+struct evc_ctx {
+  int device;
+  cudaStream_t stream;
+  int sm_count;
+  size_t smem_optin;
+  double last_trdm_flops;
+};
+
+void evc_set_error(const char* fmt, ...);
+
+#define EVC_CHECK_CUDA(expr)                                                        \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      evc_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,              \
+                    cudaGetErrorString(_e));                                        \
+      return -2;                                                                    \
+    }                                                                               \
+  } while (0)
+
+#define EVC_REQUIRE(cond, ...)                                                      \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      evc_set_error(__VA_ARGS__);                                                   \
+      return -1;                                                                    \
+    }                                                                               \
+  } while (0)
+
+#define EVC_CHECK_LAUNCH() EVC_CHECK_CUDA(cudaGetLastError())
+
+static inline size_t evc_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller-provided workspace
+struct evc_arena {
+  char* base;
+  size_t size;
+  size_t used;
+  evc_arena(void* p, size_t n) : base(static_cast<char*>(p)), size(n), used(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = evc_align_up(count * sizeof(T), 256);
+    if (used + bytes > size) return nullptr;
+    T* r = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return r;
+  }
+};
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}

@@ -1,0 +1,424 @@
+// K1+K2: transition 1-/2-RDMs between FCI vectors, fused t1 gather + FP64 DMMA.
+//
+// Replaces cisolver.trans_rdm12(cibra, ciket, norb, nelec) at
+// evcont/FCI_EVCont.py:117-127 (PySCF FCIrdm12_drv / FCItdm12kern_sf + reorder_rdm,
+// SURVEY.md Appendix A).  Definitions:
+//   t1_v[K, p*n+q] = <K|E_pq|v>                                   (gathered)
+//   C[x, y] = sum_K braT[x, K] ketT[y, K]                          (DMMA)
+//     braT[(p,q)] = t1_bra[:, (q,p)], braT[n^2] = bra        (index swap folded
+//     ketT[(r,s)] = t1_ket[:, (r,s)], ketT[n^2] = ket         into the gather)
+//   => C[(p,q),(r,s)] = <bra|E_pq E_rs|ket>, C[n^2,(r,s)] = <bra|E_rs|ket>,
+//      C[n^2,n^2] = <bra|ket>.
+// Only macro-blocks on/below the diagonal of C are computed; the rest follows
+// from [E_pq, E_rs] = d_qr E_ps - d_ps E_rq in the finalize kernel, which also
+// applies PySCF's reorder (dm2[p,q,r,s] = C[pq,rs] - d_qr <bra|p^+ s|ket>) and the
+// dm1 transpose.
+//
+// Work decomposition: CTA = (pair, slice of alpha strings).  For each alpha string
+// Ia of the slice and each tile of Bt beta strings the CTA builds the two
+// [W x Bt] tiles in shared memory (K contiguous, row pitch Bp = Bt with
+// Bt % 8 == 4 so that both the scatter and the DMMA fragment loads are
+// conflict-free), then every warp multiplies its macro-blocks (16x16 outputs
+// = 2x2 DMMA tiles) with accumulators in registers.  Partial sums per CTA go to
+// the workspace and are reduced in slice order => deterministic.
+#include "common.cuh"
+
+namespace {
+
+struct TrdmParams {
+  int norb;
+  int n2;          // norb*norb
+  int W;           // padded number of columns (n2+1 rounded up to 16)
+  int64_t na, nb;
+  const double* civecs;
+  int64_t vec_stride;
+  const int32_t* pairs;
+  int nsplit;
+  const uint64_t* link_a;  // string-major [na][nlink_a]
+  int nlink_a;
+  const uint64_t* link_b;  // link-major   [nlink_b][nb]
+  int nlink_b;
+  int Bt;           // beta tile width, Bt % 8 == 4
+  int ntile;        // ceil(nb / Bt)
+  double* partial;  // [npairs][nsplit][T][256]
+  int T;            // number of lower-triangular macro-blocks
+  unsigned char blk_start[16];
+  unsigned char blk_count[16];
+};
+
+__device__ __forceinline__ void unpack_link(uint64_t rec, int& addr, int& a, int& i, double& sgn) {
+  addr = static_cast<int>(rec & 0xffffffffu);
+  a = static_cast<int>((rec >> 32) & 0xff);
+  i = static_cast<int>((rec >> 40) & 0xff);
+  sgn = static_cast<double>(static_cast<signed char>((rec >> 48) & 0xff));
+}
+
+// Build the two [W x Bp] tiles (bra: E_pq stored in column (q,p); ket: column
+// (p,q)) for alpha string Ia and beta strings [b0, b0+Bt).  Three phases separated
+// by block barriers: zero + stage c[Ia,:]; alpha links (pure stores, every
+// (column, x) is written by exactly one link); beta links (read-modify-write,
+// again one link per (column, x)).
+__device__ __forceinline__ void alpha_phase(const TrdmParams& P, const double* __restrict__ c,
+                                            const uint64_t* __restrict__ la, int b0, int width,
+                                            bool swap, double* __restrict__ tile,
+                                            const double* __restrict__ crow, int nthreads) {
+  const int tid = threadIdx.x;
+  const int n = P.norb, Bp = P.Bt;
+  const int nb = static_cast<int>(P.nb);
+  const bool vec2 = ((nb & 1) == 0) && ((b0 & 1) == 0);
+  if (vec2) {
+    const int half = (width + 1) >> 1;
+    const int tot = P.nlink_a * half;
+    for (int k = tid; k < tot; k += nthreads) {
+      const int l = k / half, x = (k - l * half) * 2;
+      int Ja, a, i; double sg;
+      unpack_link(__ldg(la + l), Ja, a, i, sg);
+      const int col = swap ? (a * n + i) : (i * n + a);
+      const double* src = c + static_cast<int64_t>(Ja) * P.nb + b0 + x;
+      if (x + 1 < width) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(src));
+        *reinterpret_cast<double2*>(tile + col * Bp + x) = make_double2(sg * v.x, sg * v.y);
+      } else {
+        tile[col * Bp + x] = sg * __ldg(src);
+      }
+    }
+  } else {
+    const int tot = P.nlink_a * width;
+    for (int k = tid; k < tot; k += nthreads) {
+      const int l = k / width, x = k - l * width;
+      int Ja, a, i; double sg;
+      unpack_link(__ldg(la + l), Ja, a, i, sg);
+      const int col = swap ? (a * n + i) : (i * n + a);
+      tile[col * Bp + x] = sg * __ldg(c + static_cast<int64_t>(Ja) * P.nb + b0 + x);
+    }
+  }
+  // identity column: the CI coefficients themselves
+  for (int x = tid; x < width; x += nthreads) tile[P.n2 * Bp + x] = crow[b0 + x];
+}
+
+__device__ __forceinline__ void build_tiles(const TrdmParams& P, const double* __restrict__ cbra,
+                                            const double* __restrict__ cket, int64_t Ia, int b0,
+                                            double* __restrict__ braT, double* __restrict__ ketT,
+                                            double* __restrict__ crow_bra,
+                                            double* __restrict__ crow_ket, int nthreads) {
+  const int tid = threadIdx.x;
+  const int n = P.norb, Bp = P.Bt;
+  const int nb = static_cast<int>(P.nb);
+  {
+    // braT and ketT are contiguous: one vectorised zero fill
+    double2* t2 = reinterpret_cast<double2*>(braT);
+    const int tot = P.W * Bp;
+    for (int k = tid; k < tot; k += nthreads) t2[k] = make_double2(0.0, 0.0);
+    if (b0 == 0) {  // c[Ia, :] rows change only with Ia
+      const double* sb = cbra + Ia * P.nb;
+      const double* sk = cket + Ia * P.nb;
+      for (int k = tid; k < nb; k += nthreads) {
+        crow_bra[k] = __ldg(sb + k);
+        crow_ket[k] = __ldg(sk + k);
+      }
+    }
+  }
+  __syncthreads();
+  const int width = min(P.Bt, nb - b0);
+  const uint64_t* la = P.link_a + Ia * P.nlink_a;
+  alpha_phase(P, cbra, la, b0, width, true, braT, crow_bra, nthreads);
+  alpha_phase(P, cket, la, b0, width, false, ketT, crow_ket, nthreads);
+  __syncthreads();
+  {
+    const int tot = P.nlink_b * width;
+    for (int k = tid; k < tot; k += nthreads) {
+      const int l = k / width, x = k - l * width;
+      int Jb, a, i; double sg;
+      unpack_link(__ldg(P.link_b + static_cast<int64_t>(l) * P.nb + b0 + x), Jb, a, i, sg);
+      braT[(a * n + i) * Bp + x] += sg * crow_bra[Jb];
+      ketT[(i * n + a) * Bp + x] += sg * crow_ket[Jb];
+    }
+  }
+}
+
+template <int NWARPS, int MAXBLK>
+__global__ void __launch_bounds__(NWARPS * 32)
+trdm_fused_kernel(const __grid_constant__ TrdmParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nthreads = NWARPS * 32;
+  const int Bp = P.Bt;
+  const int nbpad = (static_cast<int>(P.nb) + 1) & ~1;
+  double* braT = reinterpret_cast<double*>(smem_raw);
+  double* ketT = braT + P.W * Bp;
+  double* crow_bra = ketT + P.W * Bp;
+  double* crow_ket = crow_bra + nbpad;
+
+  const int item = blockIdx.x;
+  const int pair = item / P.nsplit;
+  const int split = item - pair * P.nsplit;
+  const int ibra = P.pairs[2 * pair], iket = P.pairs[2 * pair + 1];
+  const double* cbra = P.civecs + ibra * P.vec_stride;
+  const double* cket = P.civecs + iket * P.vec_stride;
+  const int64_t ia_lo = P.na * split / P.nsplit;
+  const int64_t ia_hi = P.na * (split + 1) / P.nsplit;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tg = lane & 3;
+  const int my_start = P.blk_start[warp], my_count = P.blk_count[warp];
+
+  // macro-block coordinates of this warp's slots
+  int xoff[MAXBLK], yoff[MAXBLK];
+#pragma unroll
+  for (int s = 0; s < MAXBLK; ++s) {
+    int t = my_start + (s < my_count ? s : 0);
+    int r = 0;
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    const int cc = t - r * (r + 1) / 2;
+    xoff[s] = (r * 16 + g) * Bp + tg;
+    yoff[s] = (cc * 16 + g) * Bp + tg;
+  }
+  double acc[MAXBLK][4][2];
+#pragma unroll
+  for (int s = 0; s < MAXBLK; ++s)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[s][q][0] = acc[s][q][1] = 0.0;
+
+  for (int64_t Ia = ia_lo; Ia < ia_hi; ++Ia) {
+    for (int tile = 0; tile < P.ntile; ++tile) {
+      const int b0 = tile * P.Bt;
+      __syncthreads();  // previous MMA phase done with the tiles
+      build_tiles(P, cbra, cket, Ia, b0, braT, ketT, crow_bra, crow_ket, nthreads);
+      __syncthreads();
+#pragma unroll 1
+      for (int k0 = 0; k0 < P.Bt; k0 += 4) {
+#pragma unroll
+        for (int s = 0; s < MAXBLK; ++s) {
+          if (s < my_count) {
+            const double a0 = braT[xoff[s] + k0];
+            const double a1 = braT[xoff[s] + 8 * Bp + k0];
+            const double b0v = ketT[yoff[s] + k0];
+            const double b1v = ketT[yoff[s] + 8 * Bp + k0];
+            dmma8x8x4(acc[s][0][0], acc[s][0][1], a0, b0v);
+            dmma8x8x4(acc[s][1][0], acc[s][1][1], a0, b1v);
+            dmma8x8x4(acc[s][2][0], acc[s][2][1], a1, b0v);
+            dmma8x8x4(acc[s][3][0], acc[s][3][1], a1, b1v);
+          }
+        }
+      }
+    }
+  }
+  // write partial sums: [item][t][tile(2x2)][8x8 row-major]
+  double* out = P.partial + static_cast<int64_t>(item) * P.T * 256;
+#pragma unroll
+  for (int s = 0; s < MAXBLK; ++s) {
+    if (s < my_count) {
+      double* blk = out + (my_start + s) * 256;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<double2*>(blk + q * 64)[lane] = make_double2(acc[s][q][0], acc[s][q][1]);
+    }
+  }
+}
+
+// One CTA per pair: ordered reduction over the alpha slices, triangular fill,
+// PySCF reorder, dm1 transpose.
+__global__ void trdm_finalize_kernel(int norb, int T, int nsplit, const double* __restrict__ partial,
+                                     double* __restrict__ ovlp, double* __restrict__ dm1,
+                                     double* __restrict__ dm2) {
+  extern __shared__ double r1[];  // rdm1_C[(p,q)] = <bra|p^+ q|ket>
+  const int pair = blockIdx.x;
+  const int n = norb, n2 = n * n;
+  const double* base = partial + static_cast<int64_t>(pair) * nsplit * T * 256;
+  const int64_t item_stride = static_cast<int64_t>(T) * 256;
+  auto fetch = [&](int x, int y) -> double {  // requires blk(x) >= blk(y)
+    const int bx = x >> 4, by = y >> 4;
+    const int off = (bx * (bx + 1) / 2 + by) * 256 + ((((x >> 3) & 1) << 1) | ((y >> 3) & 1)) * 64 +
+                    (x & 7) * 8 + (y & 7);
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += base[k * item_stride + off];
+    return s;
+  };
+  for (int y = threadIdx.x; y <= n2; y += blockDim.x) {
+    const double v = fetch(n2, y);
+    if (y < n2) r1[y] = v; else ovlp[pair] = v;
+  }
+  __syncthreads();
+  double* d1 = dm1 + static_cast<int64_t>(pair) * n2;
+  for (int k = threadIdx.x; k < n2; k += blockDim.x) {
+    const int p = k / n, q = k - p * n;
+    d1[k] = r1[q * n + p];  // dm1[p,q] = <bra|q^+ p|ket>
+  }
+  double* d2 = dm2 + static_cast<int64_t>(pair) * n2 * n2;
+  const int64_t tot = static_cast<int64_t>(n2) * n2;
+  for (int64_t k = threadIdx.x; k < tot; k += blockDim.x) {
+    const int x = static_cast<int>(k / n2), y = static_cast<int>(k - static_cast<int64_t>(x) * n2);
+    const int p = x / n, q = x - p * n, r = y / n, s = y - r * n;
+    double v;
+    if ((x >> 4) >= (y >> 4)) {
+      v = fetch(x, y);
+    } else {
+      // E_pq E_rs = E_rs E_pq + d_qr E_ps - d_ps E_rq
+      v = fetch(y, x);
+      if (q == r) v += r1[p * n + s];
+      if (p == s) v -= r1[r * n + q];
+    }
+    if (q == r) v -= r1[p * n + s];  // reorder: p^+ q r^+ s = d_qr p^+ s + p^+ r^+ s q
+    d2[k] = v;
+  }
+}
+
+struct TrdmPlan {
+  int W, nblk, T, nwarps, maxblk, Bt, ntile, nsplit, occupancy;
+  size_t smem;
+};
+
+int plan_trdm(int norb, int64_t na, int64_t nb, int npairs, int sm_count, TrdmPlan* pl) {
+  const int n2 = norb * norb;
+  pl->W = (n2 + 1 + 15) / 16 * 16;
+  pl->nblk = pl->W / 16;
+  pl->T = pl->nblk * (pl->nblk + 1) / 2;
+  if (pl->nblk > 11) return -1;
+  pl->nwarps = pl->nblk >= 9 ? 16 : 8;
+  const int per_smsp = (pl->T + 3) / 4;
+  const int warps_per_smsp = pl->nwarps / 4;
+  pl->maxblk = (per_smsp + warps_per_smsp - 1) / warps_per_smsp;
+  // beta tile: Bt % 8 == 4; prefer two CTAs per SM, little padding waste.
+  const size_t smem_cap = 227 * 1024;
+  const int nbpad = (static_cast<int>(nb) + 1) & ~1;
+  const size_t crow_bytes = 2 * static_cast<size_t>(nbpad) * 8;
+  const int want_occ = pl->nwarps == 8 ? 2 : 1;
+  const size_t budget = smem_cap / want_occ - 1024;  // 1 KB reserved per CTA
+  int best = -1;
+  double best_cost = 1e300;
+  for (int bt = 12; bt <= 100; bt += 8) {
+    const size_t bytes = 2 * static_cast<size_t>(pl->W) * bt * 8 + crow_bytes;
+    if (bytes > budget) break;
+    const int nt = static_cast<int>((nb + bt - 1) / bt);
+    // cost model: padded MMA work + a fixed per-tile overhead worth ~8 columns
+    const double cost = static_cast<double>(nt) * (bt + 8);
+    if (cost < best_cost) { best_cost = cost; best = bt; }
+  }
+  if (best < 0) {
+    // fall back to one CTA per SM
+    for (int bt = 12; bt <= 100; bt += 8) {
+      const size_t bytes = 2 * static_cast<size_t>(pl->W) * bt * 8 + crow_bytes;
+      if (bytes > smem_cap - 1024) break;
+      const int nt = static_cast<int>((nb + bt - 1) / bt);
+      const double cost = static_cast<double>(nt) * (bt + 8);
+      if (cost < best_cost) { best_cost = cost; best = bt; }
+    }
+  }
+  if (best < 0) return -2;
+  pl->Bt = best;
+  pl->ntile = static_cast<int>((nb + best - 1) / best);
+  pl->smem = 2 * static_cast<size_t>(pl->W) * best * 8 + crow_bytes;
+  pl->occupancy = static_cast<int>(smem_cap / (pl->smem + 1024));
+  if (pl->occupancy > want_occ) pl->occupancy = want_occ;
+  if (pl->occupancy < 1) pl->occupancy = 1;
+  // alpha slices: aim for >= 6 waves of CTAs, at least 2 alpha strings per slice
+  const int64_t resident = static_cast<int64_t>(sm_count) * pl->occupancy;
+  int64_t s = (6 * resident + npairs - 1) / npairs;
+  if (s > na / 2) s = na / 2;
+  if (s < 1) s = 1;
+  if (s > 4096) s = 4096;
+  pl->nsplit = static_cast<int>(s);
+  return 0;
+}
+
+void assign_blocks(const TrdmPlan& pl, TrdmParams* P) {
+  // spread the T macro-blocks evenly over the 4 SM sub-partitions (warp % 4),
+  // then over the warps of each sub-partition; contiguous ranges per warp.
+  int per_smsp[4];
+  for (int q = 0; q < 4; ++q) per_smsp[q] = pl.T / 4 + (q < pl.T % 4 ? 1 : 0);
+  const int wps = pl.nwarps / 4;
+  int count[16] = {0};
+  for (int q = 0; q < 4; ++q)
+    for (int j = 0; j < wps; ++j) count[j * 4 + q] = per_smsp[q] / wps + (j < per_smsp[q] % wps ? 1 : 0);
+  int start = 0;
+  for (int w = 0; w < 16; ++w) {
+    P->blk_start[w] = static_cast<unsigned char>(w < pl.nwarps ? start : 0);
+    P->blk_count[w] = static_cast<unsigned char>(w < pl.nwarps ? count[w] : 0);
+    if (w < pl.nwarps) start += count[w];
+  }
+}
+
+template <int NWARPS, int MAXBLK>
+int launch_fused(const TrdmParams& P, const TrdmPlan& pl, int nitems, cudaStream_t stream) {
+  auto kern = trdm_fused_kernel<NWARPS, MAXBLK>;
+  EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(pl.smem)));
+  kern<<<nitems, NWARPS * 32, pl.smem, stream>>>(P);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int evc_trans_rdm12_workspace_bytes(int norb, int64_t na, int64_t nb, int npairs, int sm_count,
+                                    size_t* bytes) {
+  EVC_REQUIRE(bytes != nullptr, "evc_trans_rdm12_workspace_bytes: bytes is NULL");
+  EVC_REQUIRE(norb >= 1 && norb <= 13, "evc_trans_rdm12: norb=%d unsupported (1..13)", norb);
+  EVC_REQUIRE(npairs >= 1 && na >= 1 && nb >= 1, "evc_trans_rdm12: empty problem");
+  TrdmPlan pl;
+  EVC_REQUIRE(plan_trdm(norb, na, nb, npairs, sm_count > 0 ? sm_count : 148, &pl) == 0,
+              "evc_trans_rdm12: no launch plan for norb=%d nb=%lld", norb, (long long)nb);
+  *bytes = static_cast<size_t>(npairs) * pl.nsplit * pl.T * 256 * sizeof(double);
+  return 0;
+}
+
+int evc_trans_rdm12_batch(evc_ctx* ctx, int norb, int64_t na, int64_t nb, const double* civecs,
+                          int64_t vec_stride, int nvec, const int32_t* pairs, int npairs,
+                          const uint64_t* link_a, int nlink_a, const uint64_t* link_b, int nlink_b,
+                          double* ovlp, double* dm1, double* dm2, void* workspace,
+                          size_t workspace_bytes) {
+  EVC_REQUIRE(ctx != nullptr, "evc_trans_rdm12_batch: ctx is NULL");
+  EVC_REQUIRE(norb >= 1 && norb <= 13, "evc_trans_rdm12_batch: norb=%d unsupported (1..13)", norb);
+  EVC_REQUIRE(civecs && pairs && link_a && link_b && ovlp && dm1 && dm2 && workspace,
+              "evc_trans_rdm12_batch: NULL pointer argument");
+  EVC_REQUIRE(npairs >= 1 && nvec >= 1 && na >= 1 && nb >= 1, "evc_trans_rdm12_batch: empty problem");
+  EVC_REQUIRE(vec_stride >= na * nb, "evc_trans_rdm12_batch: vec_stride %lld < na*nb", (long long)vec_stride);
+  EVC_REQUIRE((reinterpret_cast<uintptr_t>(civecs) & 15) == 0 && (vec_stride & 1) == 0,
+              "evc_trans_rdm12_batch: civecs must be 16-byte aligned with an even stride");
+  TrdmPlan pl;
+  EVC_REQUIRE(plan_trdm(norb, na, nb, npairs, ctx->sm_count, &pl) == 0,
+              "evc_trans_rdm12_batch: no launch plan for norb=%d nb=%lld", norb, (long long)nb);
+  const size_t need = static_cast<size_t>(npairs) * pl.nsplit * pl.T * 256 * sizeof(double);
+  EVC_REQUIRE(workspace_bytes >= need, "evc_trans_rdm12_batch: workspace %zu < %zu bytes", workspace_bytes, need);
+  EVC_REQUIRE(pl.smem <= ctx->smem_optin, "evc_trans_rdm12_batch: needs %zu B shared memory, device allows %zu",
+              pl.smem, ctx->smem_optin);
+
+  TrdmParams P;
+  P.norb = norb; P.n2 = norb * norb; P.W = pl.W; P.na = na; P.nb = nb;
+  P.civecs = civecs; P.vec_stride = vec_stride; P.pairs = pairs; P.nsplit = pl.nsplit;
+  P.link_a = link_a; P.nlink_a = nlink_a; P.link_b = link_b; P.nlink_b = nlink_b;
+  P.Bt = pl.Bt; P.ntile = pl.ntile; P.partial = static_cast<double*>(workspace); P.T = pl.T;
+  assign_blocks(pl, &P);
+  const int nitems = npairs * pl.nsplit;
+  int rc = -1;
+  if (pl.nwarps == 8) {
+    switch (pl.maxblk) {
+      case 1: rc = launch_fused<8, 1>(P, pl, nitems, ctx->stream); break;
+      case 2: rc = launch_fused<8, 2>(P, pl, nitems, ctx->stream); break;
+      case 3: rc = launch_fused<8, 3>(P, pl, nitems, ctx->stream); break;
+      case 4: rc = launch_fused<8, 4>(P, pl, nitems, ctx->stream); break;
+      case 5: rc = launch_fused<8, 5>(P, pl, nitems, ctx->stream); break;
+      default: break;
+    }
+  } else {
+    switch (pl.maxblk) {
+      case 3: rc = launch_fused<16, 3>(P, pl, nitems, ctx->stream); break;
+      case 4: rc = launch_fused<16, 4>(P, pl, nitems, ctx->stream); break;
+      case 5: rc = launch_fused<16, 5>(P, pl, nitems, ctx->stream); break;
+      default: break;
+    }
+  }
+  EVC_REQUIRE(rc != -1, "evc_trans_rdm12_batch: no kernel instance for nwarps=%d maxblk=%d", pl.nwarps, pl.maxblk);
+  if (rc != 0) return rc;
+  trdm_finalize_kernel<<<npairs, 256, P.n2 * sizeof(double), ctx->stream>>>(
+      norb, pl.T, pl.nsplit, P.partial, ovlp, dm1, dm2);
+  EVC_CHECK_LAUNCH();
+  ctx->last_trdm_flops = static_cast<double>(npairs) * static_cast<double>(na) * pl.ntile * pl.Bt *
+                         static_cast<double>(pl.T) * 256.0 * 2.0;
+  return 0;
+}
+
+double evc_trans_rdm12_last_issued_flops(const evc_ctx* ctx) { return ctx ? ctx->last_trdm_flops : 0.0; }
+
+}  // extern "C"

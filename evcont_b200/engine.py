@@ -1,0 +1,328 @@
+"""Device engine: thin object layer over the C ABI.
+
+PyTorch is used only for what the C ABI leaves to the caller: device buffers
+(``torch.empty(..., device=...)`` + ``data_ptr()``), the current CUDA stream and
+(in ``evcont_b200.distributed``) the NCCL process group.  All arithmetic runs in
+``libevcont_b200.so``.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AoBundle, check
+
+LAYOUT_FULL, LAYOUT_TRIL, LAYOUT_FULL_EXCH, LAYOUT_TRIL_EXCH = 6, 5, 3, 2
+
+_engines = {}
+_engines_lock = threading.Lock()
+
+
+def get_engine(device=None):
+    """The per-device :class:`Engine` singleton (``device``: int, str or torch.device)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "evcont_b200 needs a CUDA device (B200, sm_100a): torch.cuda.is_available() is "
+            "False and there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError(f"evcont_b200 runs on CUDA devices only, not {dev}")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _engines_lock:
+        if idx not in _engines:
+            _engines[idx] = Engine(idx)
+        return _engines[idx]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Engine:
+    """One ``evc_ctx`` bound to one GPU, plus caches (link tables, workspace)."""
+
+    def __init__(self, device_index):
+        self.lib = _lib.lib()
+        self.device = torch.device("cuda", device_index)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.evc_ctx_create(device_index, None, C.byref(handle)))
+        self._ctx = handle
+        self.sm_count = self.lib.evc_ctx_sm_count(handle)
+        self._links = {}
+        self._ws = None
+
+    # -- plumbing ------------------------------------------------------------
+    def _bind_stream(self):
+        stream = torch.cuda.current_stream(self.device)
+        check(self.lib.evc_ctx_set_stream(self._ctx, C.c_void_p(stream.cuda_stream)))
+
+    def workspace(self, nbytes):
+        """A reusable scratch buffer of at least ``nbytes`` (grown geometrically)."""
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8,
+                                   device=self.device)
+        return self._ws
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def to_device(self, a, dtype=torch.float64):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
+
+    # -- K0 --------------------------------------------------------------------
+    def link_tables(self, norb, nocc):
+        """(nstr, nlink, string-major packed table, link-major packed table) on device."""
+        key = (norb, nocc)
+        if key not in self._links:
+            from . import cistring
+            tab = cistring.gen_linkstr_index(range(norb), nocc)
+            nstr, nlink = tab.shape[0], tab.shape[1]
+            sm = np.empty(nstr * nlink, dtype=np.uint64)
+            lm = np.empty(nstr * nlink, dtype=np.uint64)
+            check(self.lib.evc_linkindex_pack_host(nstr, nlink, tab.ctypes.data, 0, sm.ctypes.data))
+            check(self.lib.evc_linkindex_pack_host(nstr, nlink, tab.ctypes.data, 1, lm.ctypes.data))
+            self._links[key] = (nstr, nlink,
+                                torch.from_numpy(sm.view(np.int64)).to(self.device),
+                                torch.from_numpy(lm.view(np.int64)).to(self.device))
+        return self._links[key]
+
+    # -- K1 + K2 -----------------------------------------------------------------
+    def trans_rdm12_batch(self, civecs, pairs, norb, nelec):
+        """Transition RDMs for ``pairs`` [(bra, ket), ...] among ``civecs`` (nvec, na, nb).
+
+        Returns device tensors ``(ovlp[np], dm1[np,n,n], dm2[np,n,n,n,n])``.
+        """
+        neleca, nelecb = nelec
+        na, nlink_a, la_sm, _ = self.link_tables(norb, neleca)
+        nb, nlink_b, _, lb_lm = self.link_tables(norb, nelecb)
+        civecs = self.to_device(civecs).reshape(-1, na * nb)
+        nvec = civecs.shape[0]
+        stride = na * nb + ((na * nb) & 1)
+        if stride != na * nb:  # keep every vector 16-byte aligned
+            padded = self.empty(nvec, stride)
+            padded[:, : na * nb] = civecs
+            padded[:, na * nb:] = 0
+            civecs = padded
+        pairs_h = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        if pairs_h.min() < 0 or pairs_h.max() >= nvec:
+            raise IndexError("pair index out of range")
+        npairs = pairs_h.shape[0]
+        pairs_d = torch.from_numpy(pairs_h).to(self.device)
+        n = norb
+        ovlp = self.empty(npairs)
+        dm1 = self.empty(npairs, n, n)
+        dm2 = self.empty(npairs, n, n, n, n)
+        nbytes = C.c_size_t()
+        check(self.lib.evc_trans_rdm12_workspace_bytes(n, na, nb, npairs, self.sm_count,
+                                                       C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        check(self.lib.evc_trans_rdm12_batch(
+            self._ctx, n, na, nb, _ptr(civecs), stride, nvec, _ptr(pairs_d), npairs,
+            _ptr(la_sm), nlink_a, _ptr(lb_lm), nlink_b, _ptr(ovlp), _ptr(dm1), _ptr(dm2),
+            _ptr(ws), ws.numel()))
+        return ovlp, dm1, dm2
+
+    def trans_rdm12_issued_flops(self):
+        return self.lib.evc_trans_rdm12_last_issued_flops(self._ctx)
+
+    # -- K3 ------------------------------------------------------------------------
+    def loewdin(self, s_ao):
+        """Batched Loewdin: ``s_ao`` (G, n, n) device -> (X, evals, evecs)."""
+        G, n = s_ao.shape[0], s_ao.shape[-1]
+        x, evals, evecs = self.empty(G, n, n), self.empty(G, n), self.empty(G, n, n)
+        self._bind_stream()
+        check(self.lib.evc_loewdin(self._ctx, G, n, _ptr(s_ao), _ptr(x), _ptr(evals), _ptr(evecs)))
+        return x, evals, evecs
+
+    def loewdin_grad(self, evals, evecs, dS):
+        """``dS`` (G, nder, n, n) -> dX (G, nder, n, n)."""
+        G, nder, n = dS.shape[0], dS.shape[1], dS.shape[-1]
+        dX = self.empty(G, nder, n, n)
+        self._bind_stream()
+        check(self.lib.evc_loewdin_grad(self._ctx, G, n, nder, _ptr(evals), _ptr(evecs), _ptr(dS),
+                                        _ptr(dX)))
+        return dX
+
+    # -- K4 --------------------------------------------------------------------------
+    def ao2oao(self, hcore, eri, c, transpose_c=False, want_t3=False):
+        """``h1 = C^T h C`` and the four-index transform, batched (G, ...)."""
+        G, n = c.shape[0], c.shape[-1]
+        h1 = self.empty(G, n, n) if hcore is not None else None
+        h2 = self.empty(G, n, n, n, n) if eri is not None else None
+        t3 = self.empty(G, n, n, n, n) if (want_t3 and eri is not None) else None
+        ws = self.workspace(2 * (G * n ** 4 * 8 + 256))
+        self._bind_stream()
+        check(self.lib.evc_ao2oao(self._ctx, G, n, _ptr(hcore), _ptr(eri), _ptr(c),
+                                  1 if transpose_c else 0, _ptr(h1), _ptr(h2), _ptr(t3),
+                                  _ptr(ws), ws.numel()))
+        return h1, h2, t3
+
+    # -- K5 ---------------------------------------------------------------------------
+    def subspace_H(self, stack, h1, h2):
+        G = h1.shape[0]
+        H = self.empty(G, stack.ntrain, stack.ntrain)
+        nbytes = C.c_size_t()
+        check(self.lib.evc_subspace_workspace_bytes(stack.layout, stack.ntrain, stack.norb, G,
+                                                    C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        check(self.lib.evc_subspace_H(self._ctx, stack.layout, stack.ntrain, stack.norb,
+                                      _ptr(stack.one_rdm), _ptr(stack.two_rdm), G, _ptr(h1),
+                                      _ptr(h2), _ptr(H), _ptr(ws), ws.numel()))
+        return H
+
+    # -- K6 ----------------------------------------------------------------------------
+    def geneig_prepare(self, S):
+        N = S.shape[0]
+        linv = self.empty(N, N)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._bind_stream()
+        check(self.lib.evc_geneig_prepare(self._ctx, N, _ptr(S), _ptr(linv), _ptr(info)))
+        k = int(info.item())
+        if k != 0:
+            raise np.linalg.LinAlgError(
+                f"The leading minor of order {k} of the subspace overlap S is not positive "
+                "definite; the generalized eigenproblem cannot be solved (as scipy.linalg.eigh)")
+        return linv
+
+    def geneig(self, H, linv, nroots=1):
+        G, N = H.shape[0], H.shape[-1]
+        E, Cv = self.empty(G, nroots), self.empty(G, nroots, N)
+        self._bind_stream()
+        check(self.lib.evc_geneig(self._ctx, G, N, _ptr(H), _ptr(linv), nroots, _ptr(E), _ptr(Cv)))
+        return E, Cv
+
+    # -- K7 ------------------------------------------------------------------------------
+    def predict_rdm(self, stack, cvec):
+        """``cvec`` (G, N) -> gamma (G, n, n), Gamma (G, n, n, n, n)."""
+        G, n = cvec.shape[0], stack.norb
+        gamma, Gamma = self.empty(G, n, n), self.empty(G, n, n, n, n)
+        nbytes = C.c_size_t()
+        check(self.lib.evc_predict_workspace_bytes(stack.layout, stack.ntrain, n, G, C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        check(self.lib.evc_predict_rdm(self._ctx, stack.layout, stack.ntrain, n, _ptr(stack.one_rdm),
+                                       _ptr(stack.two_rdm), G, _ptr(cvec), cvec.stride(0),
+                                       _ptr(gamma), _ptr(Gamma), _ptr(ws), ws.numel()))
+        return gamma, Gamma
+
+    # -- K8 --------------------------------------------------------------------------------
+    def grad_elec(self, aoslices, evals, evecs, x, hcore, t3, gamma, Gamma, ipovlp, hcore_deriv,
+                  eri_ip1):
+        G, n, natm = x.shape[0], x.shape[-1], aoslices.shape[0]
+        grad = self.empty(G, natm, 3)
+        nbytes = C.c_size_t()
+        check(self.lib.evc_grad_workspace_bytes(n, natm, G, C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        check(self.lib.evc_grad_elec(self._ctx, G, n, natm, _ptr(aoslices), _ptr(evals), _ptr(evecs),
+                                     _ptr(x), _ptr(hcore), _ptr(t3), _ptr(gamma), _ptr(Gamma),
+                                     _ptr(ipovlp), _ptr(hcore_deriv), _ptr(eri_ip1), _ptr(grad),
+                                     _ptr(ws), ws.numel()))
+        return grad
+
+    # -- fused step ------------------------------------------------------------------------
+    def energy_with_grad(self, stack, ao, want_rdms=False, out=None):
+        """One prediction step for a batch of geometries resident on the device.
+
+        ``ao``: :class:`DeviceAO`.  Returns ``(E[G], grad[G,natm,3], gamma, Gamma, cvec)``
+        (gamma/Gamma are ``None`` unless ``want_rdms``).
+        """
+        G, n, natm, N = ao.nbatch, ao.nao, ao.natm, stack.ntrain
+        if n != stack.norb:
+            raise ValueError(f"mol.nao={n} does not match the stack's norb={stack.norb}")
+        if out is None:
+            E, grad, cvec = self.empty(G), self.empty(G, natm, 3), self.empty(G, N)
+        else:
+            E, grad, cvec = out
+        gamma = self.empty(G, n, n) if want_rdms else None
+        Gamma = self.empty(G, n, n, n, n) if want_rdms else None
+        nbytes = C.c_size_t()
+        check(self.lib.evc_energy_with_grad_workspace_bytes(stack.layout, N, n, natm, G,
+                                                            C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        bundle = ao.bundle()
+        check(self.lib.evc_energy_with_grad(
+            self._ctx, stack.layout, N, n, natm, _ptr(stack.one_rdm), _ptr(stack.two_rdm),
+            _ptr(stack.linv), G, C.byref(bundle), _ptr(E), _ptr(grad), _ptr(gamma), _ptr(Gamma),
+            _ptr(cvec), _ptr(ws), ws.numel()))
+        return E, grad, gamma, Gamma, cvec
+
+
+class DeviceStack:
+    """The t-RDM stack resident in HBM, in one of the reference's four layouts.
+
+    ``overlap (N,N)``, ``one_rdm (N,N,n,n)`` and ``two_rdm`` as accepted by
+    evcont/ab_initio_eigenvector_continuation.py:12-90 (dispatch on ``two_rdm.ndim``:
+    6 / 5 / 3 / 2).  The Cholesky factor of ``overlap`` is computed once here
+    because S does not depend on the geometry.
+    """
+
+    def __init__(self, overlap, one_rdm, two_rdm, engine=None, norb=None):
+        self.engine = engine or get_engine()
+        eng = self.engine
+        ndim = two_rdm.ndim
+        if ndim not in (6, 5, 3, 2):
+            raise AssertionError("two_RDM must have 2, 3, 5 or 6 dimensions")
+        self.layout = ndim
+        self.ntrain = int(overlap.shape[0])
+        self.norb = int(one_rdm.shape[-1]) if norb is None else int(norb)
+        self.overlap = eng.to_device(overlap)
+        self.one_rdm = eng.to_device(one_rdm).reshape(self.ntrain * self.ntrain, -1)
+        npairs = self.ntrain ** 2 if ndim in (6, 3) else self.ntrain * (self.ntrain + 1) // 2
+        self.two_rdm = eng.to_device(two_rdm).reshape(npairs, -1)
+        n2 = self.norb ** 2
+        expect = n2 * n2 if ndim in (6, 5) else n2 * (n2 + 1) // 2
+        if self.two_rdm.shape[1] != expect or self.one_rdm.shape[1] != n2:
+            raise ValueError("t-RDM stack shapes are inconsistent with norb/ntrain")
+        self.linv = eng.geneig_prepare(self.overlap)
+
+    @property
+    def nbytes(self):
+        return self.two_rdm.numel() * 8 + self.one_rdm.numel() * 8
+
+
+class DeviceAO:
+    """AO arrays of a batch of geometries on the device (the ``evc_ao_bundle``)."""
+
+    FIELDS = ("ovlp", "hcore", "eri", "ipovlp", "hcore_deriv", "eri_ip1", "e_nuc", "grad_nuc")
+
+    def __init__(self, engine, nbatch, nao, natm, aoslices):
+        self.engine, self.nbatch, self.nao, self.natm = engine, nbatch, nao, natm
+        n = nao
+        shapes = dict(ovlp=(nbatch, n, n), hcore=(nbatch, n, n), eri=(nbatch, n, n, n, n),
+                      ipovlp=(nbatch, 3, n, n), hcore_deriv=(nbatch, natm, 3, n, n),
+                      eri_ip1=(nbatch, 3, n, n, n, n), e_nuc=(nbatch,), grad_nuc=(nbatch, natm, 3))
+        self.shapes = shapes
+        for k, shp in shapes.items():
+            setattr(self, k, engine.empty(*shp))
+        self.aoslices = torch.from_numpy(
+            np.ascontiguousarray(aoslices, dtype=np.int32).reshape(natm, 2)).to(engine.device)
+
+    @classmethod
+    def from_bundles(cls, engine, bundles):
+        """Upload a list of host ``ao_bundle`` dicts (evcont_b200.mol.ao_bundle)."""
+        b0 = bundles[0]
+        self = cls(engine, len(bundles), b0["nao"], b0["natm"], b0["aoslices"])
+        for k in cls.FIELDS:
+            host = np.stack([np.asarray(b[k], dtype=np.float64) for b in bundles])
+            getattr(self, k).copy_(torch.from_numpy(host.reshape(self.shapes[k])))
+        return self
+
+    def nbytes(self):
+        return sum(getattr(self, k).numel() * 8 for k in self.FIELDS)
+
+    def bundle(self):
+        b = AoBundle()
+        for k in self.FIELDS:
+            setattr(b, k, getattr(self, k).data_ptr())
+        b.aoslices = self.aoslices.data_ptr()
+        return b

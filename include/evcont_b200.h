@@ -1,0 +1,214 @@
+/*
+ * evcont_b200.h -- C ABI of libevcont_b200.so, the B200 (sm_100a) engine behind
+ * evcont's FCI eigenvector-continuation path.
+ *
+ * The reference (BoothGroup/evcont) has no FFI of its own: its extension points
+ * are duck-typed Python objects.  Each entry point below
+ * names the reference interface (file:line under the reference tree) whose
+ * arithmetic it replaces; the Python package `evcont_b200` binds them with
+ * ctypes and mirrors the reference's function names on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; evc_last_error() gives
+ *     the thread-local message of the last failure.
+ *   - all array arguments are DEVICE pointers owned by the caller (torch tensors
+ *     on the Python side) unless the parameter name ends in `_host`.
+ *   - no hidden device allocation: scratch space is passed in as
+ *     (workspace, workspace_bytes); `*_workspace_bytes()` tells how much.
+ *   - all work is enqueued on the ctx stream and is asynchronous; the caller
+ *     synchronises.  One ctx per GPU/thread; calls on one ctx are not re-entrant.
+ *   - all floating point data is IEEE double, C order (row-major).
+ *   - "batch" always means independent geometries (MD replicas / scan points).
+ */
+#ifndef EVCONT_B200_H
+#define EVCONT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVC_ABI_VERSION 1
+
+typedef struct evc_ctx evc_ctx;
+
+/* layouts of the two-body t-RDM stack, named after the `two_RDM.ndim` dispatch of
+ * evcont/ab_initio_eigenvector_continuation.py:41-71 */
+enum {
+  EVC_LAYOUT_FULL = 6,      /* (N, N, n, n, n, n)                        */
+  EVC_LAYOUT_TRIL = 5,      /* (N(N+1)/2, n, n, n, n), np.tril_indices   */
+  EVC_LAYOUT_FULL_EXCH = 3, /* (N, N, n^2(n^2+1)/2)                      */
+  EVC_LAYOUT_TRIL_EXCH = 2  /* (N(N+1)/2, n^2(n^2+1)/2)                  */
+};
+
+/* ---- library / context ------------------------------------------------- */
+int evc_abi_version(void);
+const char *evc_last_error(void);
+/* stream: a cudaStream_t (NULL = legacy default stream). */
+int evc_ctx_create(int device, void *stream, evc_ctx **out);
+int evc_ctx_destroy(evc_ctx *ctx);
+int evc_ctx_set_stream(evc_ctx *ctx, void *stream);
+int evc_ctx_sm_count(const evc_ctx *ctx);
+
+/* ---- K0: occupation strings and link tables (host, bit-exact) ---------
+ * Replaces pyscf.fci.cistring.make_strings / str2addr / gen_linkstr_index, which
+ * the reference reaches (and rebuilds on every call) through
+ * cisolver.trans_rdm12 at evcont/FCI_EVCont.py:121.  Layout: SURVEY.md App. A.2. */
+int64_t evc_num_strings(int norb, int nocc);
+int evc_num_links(int norb, int nocc); /* nocc + nocc*(norb-nocc) */
+int evc_make_strings_host(int norb, int nocc, int64_t *strings_host);
+int64_t evc_str2addr(int norb, int nocc, int64_t string);
+int64_t evc_addr2str(int norb, int nocc, int64_t addr);
+/* out_host: int32 [nstr][nlink][4] = (cre a, des i, addr of a^+ i|str>, sign) */
+int evc_linkindex_build_host(int norb, int nocc, int32_t *out_host);
+/* pack the int32 table into the 8-byte device records the kernels read:
+ * bits 0..31 target address, 32..39 a, 40..47 i, 48..55 sign (as int8).
+ * link_major == 0: packed[str][link] (alpha role: one string per CTA);
+ * link_major != 0: packed[link][str] (beta role: coalesced over strings). */
+int evc_linkindex_pack_host(int64_t nstr, int nlink, const int32_t *tab_host,
+                            int link_major, uint64_t *packed_host);
+
+/* ---- K1+K2: transition 1-/2-RDMs --------------------------------------
+ * Replaces cisolver.trans_rdm12(cibra, ciket, norb, nelec) as called at
+ * evcont/FCI_EVCont.py:117-127 (PySCF: make_rdm12_spin1('FCItdm12kern_sf') +
+ * reorder_rdm).  Conventions: dm1[p,q] = <bra|q^+ p|ket>,
+ * dm2[p,q,r,s] = <bra|p^+ r^+ s q|ket>, spin-summed; ovlp = <bra|ket>.
+ *
+ * civecs: nvec vectors of shape (na, nb), vector v at civecs + v*vec_stride.
+ * pairs : int32 [npairs][2] = (bra index, ket index), DEVICE pointer.
+ * Outputs: ovlp[npairs], dm1[npairs][n][n], dm2[npairs][n][n][n][n].
+ * The fused kernel gathers t1[K,(pq)] = <K|E_pq|v> for bra and ket through the
+ * packed alpha/beta link tables into shared memory and contracts
+ * t1_bra^T t1_ket on the FP64 tensor cores (DMMA); split-K partial sums are
+ * reduced in a fixed order, so results are run-to-run bit-identical.
+ * norb <= 13 in this version. */
+int evc_trans_rdm12_workspace_bytes(int norb, int64_t na, int64_t nb, int npairs,
+                                    int sm_count, size_t *bytes);
+int evc_trans_rdm12_batch(evc_ctx *ctx, int norb, int64_t na, int64_t nb,
+                          const double *civecs, int64_t vec_stride, int nvec,
+                          const int32_t *pairs, int npairs,
+                          const uint64_t *link_a /* string-major */, int nlink_a,
+                          const uint64_t *link_b /* link-major */, int nlink_b,
+                          double *ovlp, double *dm1, double *dm2,
+                          void *workspace, size_t workspace_bytes);
+/* issued DMMA flop count of the last evc_trans_rdm12_batch call on this ctx
+ * (for tensor-pipe utilisation; the algorithmic count is 2 n^4 ndet per pair) */
+double evc_trans_rdm12_last_issued_flops(const evc_ctx *ctx);
+
+/* ---- K3: Loewdin orthogonalisation -------------------------------------
+ * Replaces get_loewdin_trafo (evcont/electron_integral_utils.py:6-18):
+ * S = V diag(s) V^T (batched Jacobi), X = V diag(s>1e-15 ? s^-1/2 : 0) V^T.
+ * s_ao, x, evecs: [nbatch][n][n]; evals: [nbatch][n] ascending; n <= 32.
+ * evecs[b][i][k] = component i of eigenvector k (numpy eigh convention). */
+int evc_loewdin(evc_ctx *ctx, int nbatch, int n, const double *s_ao, double *x,
+                double *evals, double *evecs);
+/* Replaces loewdin_trafo_grad + the einsum of get_derivative_ao_mo_trafo
+ * (evcont/ab_initio_gradients_loewdin.py:41-134):
+ * dX_xi = V (G o (V^T dS_xi V)) V^T with the exact divided differences
+ * G_pq = -1/(sqrt(s_p) sqrt(s_q) (sqrt(s_p)+sqrt(s_q))).
+ * dS, dX: [nbatch][nder][n][n]. */
+int evc_loewdin_grad(evc_ctx *ctx, int nbatch, int n, int nder, const double *evals,
+                     const double *evecs, const double *dS, double *dX);
+
+/* ---- K4: AO -> orthogonal-basis integral transform ----------------------
+ * Replaces get_integrals / the inline copy in get_energy_with_grad
+ * (evcont/electron_integral_utils.py:122-138, ab_initio_gradients_loewdin.py:338-339;
+ * PySCF ao2mo.kernel + restore(1)):  h1 = C^T hcore C,
+ * h2[abcd] = sum (ij|kl) C_ia C_jb C_kc C_ld, four chained FP64 DMMA GEMM passes.
+ * hcore, c, h1: [nbatch][n][n]; eri, h2: [nbatch][n^4]; t3 (optional, may be
+ * NULL): [nbatch][n^4] receives the three-quarter transform
+ * t3[l,a,b,c] = sum_ijk (ij|kl) C_ia C_jb C_kc needed by the gradient.
+ * workspace: 2*nbatch*n^4 doubles.  `transpose_c` != 0 uses C^T (the
+ * trafo[a,i] convention of transform_integrals, electron_integral_utils.py:21-35). */
+int evc_ao2oao(evc_ctx *ctx, int nbatch, int n, const double *hcore, const double *eri,
+               const double *c, int transpose_c, double *h1, double *h2, double *t3,
+               void *workspace, size_t workspace_bytes);
+
+/* ---- K5: subspace Hamiltonian from the stack ----------------------------
+ * Replaces the H assembly of approximate_ground_state / approximate_multistate
+ * (evcont/ab_initio_eigenvector_continuation.py:38-71) for all four layouts.
+ * one_rdm: [N][N][n][n]; two_rdm: per `layout`; h1: [nbatch][n][n];
+ * h2: [nbatch][n^4]; H: [nbatch][N][N] (lower triangle is what the eigensolver
+ * reads; for the TRIL layouts the strict upper triangle holds the one-body part
+ * only, exactly like the reference).
+ * workspace: evc_subspace_workspace_bytes(). */
+int evc_subspace_workspace_bytes(int layout, int ntrain, int n, int nbatch, size_t *bytes);
+int evc_subspace_H(evc_ctx *ctx, int layout, int ntrain, int n, const double *one_rdm,
+                   const double *two_rdm, int nbatch, const double *h1, const double *h2,
+                   double *H, void *workspace, size_t workspace_bytes);
+
+/* ---- K6: generalized symmetric-definite eigenproblem H c = E S c ----------
+ * Replaces scipy.linalg.eigh(H, S) + root selection
+ * (evcont/ab_initio_eigenvector_continuation.py:75-88, 157-173).
+ * evc_geneig_prepare: S = L L^T once per stack (S does not depend on geometry);
+ * writes Linv [N][N] (L^-1, lower) and info (device int: 0 ok, k>0 = leading
+ * minor k not positive definite -- the caller raises like LAPACK does).
+ * evc_geneig: per geometry A = L^-1 H L^-T (lower triangle of H), batched
+ * two-sided Jacobi, c = L^-T y; returns the nroots lowest:
+ * E: [nbatch][nroots], C: [nbatch][nroots][N] with c^T S c = 1. N <= 112. */
+int evc_geneig_prepare(evc_ctx *ctx, int ntrain, const double *S, double *Linv, int *info);
+int evc_geneig(evc_ctx *ctx, int nbatch, int ntrain, const double *H, const double *Linv,
+               int nroots, double *E, double *C);
+
+/* ---- K7: predicted RDMs (c (x) c) . stack ---------------------------------
+ * Replaces evcont/ab_initio_gradients_loewdin.py:343-361.
+ * C: [nbatch][c_stride] (first N entries = ground-state vector);
+ * gamma: [nbatch][n][n]; Gamma: [nbatch][n^4] (exchange symmetry restored). */
+int evc_predict_workspace_bytes(int layout, int ntrain, int n, int nbatch, size_t *bytes);
+int evc_predict_rdm(evc_ctx *ctx, int layout, int ntrain, int n, const double *one_rdm,
+                    const double *two_rdm, int nbatch, const double *C, int64_t c_stride,
+                    double *gamma, double *Gamma, void *workspace, size_t workspace_bytes);
+
+/* ---- K8: electronic gradient in the Loewdin basis -------------------------
+ * Replaces get_grad_elec_OAO and its callees
+ * (evcont/ab_initio_gradients_loewdin.py:13-305) in the adjoint form of
+ * no dX/dR tensor is formed.
+ * Inputs per geometry: evals/evecs/x from evc_loewdin, hcore [n][n], t3 from
+ * evc_ao2oao, gamma/Gamma from evc_predict_rdm, ipovlp [3][n][n] (int1e_ipovlp),
+ * hcore_deriv [natm][3][n][n] (hcore_generator per atom), eri_ip1 [3][n^4]
+ * (int2e_ip1), aoslices int32 [natm][2] (shared by the batch).
+ * Output grad_elec [nbatch][natm][3].  workspace: evc_grad_workspace_bytes().
+ * Requires the 8-fold symmetric AO ERIs libcint produces (t3 is reused as the
+ * three-quarter transform through (ij|kl) = (lk|ji)). */
+int evc_grad_workspace_bytes(int n, int natm, int nbatch, size_t *bytes);
+int evc_grad_elec(evc_ctx *ctx, int nbatch, int n, int natm, const int32_t *aoslices,
+                  const double *evals, const double *evecs, const double *x,
+                  const double *hcore, const double *t3, const double *gamma,
+                  const double *Gamma, const double *ipovlp, const double *hcore_deriv,
+                  const double *eri_ip1, double *grad_elec, void *workspace,
+                  size_t workspace_bytes);
+
+/* ---- fused prediction step -------------------------------------------------
+ * Replaces get_energy_with_grad(mol, one_RDM, two_RDM, S)
+ * (evcont/ab_initio_gradients_loewdin.py:308-379) for a batch of geometries whose
+ * AO arrays are resident on the device: K3 -> K4 -> K5 -> K6 -> K7 -> K8 on the
+ * ctx stream with no host round trip (CUDA-graph capturable).
+ * e_nuc [nbatch] and grad_nuc [nbatch][natm][3] are added to the outputs.
+ * E: [nbatch]; grad: [nbatch][natm][3]; gamma/Gamma may be NULL (then they live
+ * in the workspace).  Linv from evc_geneig_prepare. */
+typedef struct {
+  const double *ovlp;        /* [nbatch][n][n]        int1e_ovlp            */
+  const double *hcore;       /* [nbatch][n][n]        scf.hf.get_hcore      */
+  const double *eri;         /* [nbatch][n^4]         int2e                 */
+  const double *ipovlp;      /* [nbatch][3][n][n]     int1e_ipovlp          */
+  const double *hcore_deriv; /* [nbatch][natm][3][n][n] hcore_generator     */
+  const double *eri_ip1;     /* [nbatch][3][n^4]      int2e_ip1             */
+  const double *e_nuc;       /* [nbatch]                                    */
+  const double *grad_nuc;    /* [nbatch][natm][3]                           */
+  const int32_t *aoslices;   /* [natm][2] (ao start, ao stop), shared       */
+} evc_ao_bundle;
+
+int evc_energy_with_grad_workspace_bytes(int layout, int ntrain, int n, int natm,
+                                         int nbatch, size_t *bytes);
+int evc_energy_with_grad(evc_ctx *ctx, int layout, int ntrain, int n, int natm,
+                         const double *one_rdm, const double *two_rdm, const double *Linv,
+                         int nbatch, const evc_ao_bundle *ao, double *E, double *grad,
+                         double *gamma, double *Gamma, double *Cvec,
+                         void *workspace, size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVCONT_B200_H */

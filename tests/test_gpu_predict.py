@@ -1,0 +1,161 @@
+"""K3..K8 parity through the C ABI / the reference-named Python API, against the
+golden vectors produced by the reference itself (tests/golden/make_golden.py) and
+the CPU oracle.  Tolerances from BASELINE.json north_star: 1e-10 Ha on subspace
+energies, 1e-8 Ha/bohr on forces."""
+import numpy as np
+import pytest
+
+from conftest import PREDICT_CASES, load_predict_golden, synthetic_stack
+
+pytestmark = pytest.mark.gpu
+E_TOL, F_TOL = 1e-10, 1e-8
+
+
+def _mol(norb, natm, seed):
+    from evcont_b200.mol import synthetic_mol
+    return synthetic_mol(norb, natm, seed=seed)
+
+
+@pytest.mark.parametrize("norb,natm,ntrain", PREDICT_CASES)
+def test_loewdin_and_integrals(norb, natm, ntrain):
+    from evcont_b200 import electron_integral_utils as eiu
+    g = load_predict_golden(norb, natm, ntrain)
+    mol = _mol(norb, natm, int(g["seed"]))
+    x = eiu.get_loewdin_trafo(mol.intor("int1e_ovlp"))
+    assert np.abs(x - g["loewdin_X"]).max() < 1e-12
+    h1, h2 = eiu.get_integrals(mol, g["loewdin_X"])
+    assert np.abs(h1 - g["h1"]).max() < 1e-11
+    assert np.abs(h2 - g["h2"]).max() < 1e-11
+    t1, t2 = eiu.transform_integrals(g["h1"], g["h2"], g["loewdin_X"])
+    assert np.abs(t1 - g["trafo_h1"]).max() < 1e-11
+    assert np.abs(t2 - g["trafo_h2"]).max() < 1e-11
+    # batched leading axes
+    b1, b2 = eiu.transform_integrals(np.stack([g["h1"], 2 * g["h1"]]), np.stack([g["h2"], 2 * g["h2"]]),
+                                     g["loewdin_X"])
+    assert np.abs(b2[1] - 2 * g["trafo_h2"]).max() < 1e-10 and np.abs(b1[0] - g["trafo_h1"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("norb,natm,ntrain", PREDICT_CASES)
+def test_loewdin_derivative(norb, natm, ntrain):
+    from evcont_b200 import ab_initio_gradients_loewdin as agl
+    from oracle import gradients as og
+    g = load_predict_golden(norb, natm, ntrain)
+    mol = _mol(norb, natm, int(g["seed"]))
+    dx = agl.get_derivative_ao_mo_trafo(mol)
+    assert dx.shape == (norb, norb, natm, 3)
+    assert np.abs(dx - g["dX_dR"]).max() < 1e-10
+    full = agl.loewdin_trafo_grad(mol.intor("int1e_ovlp"))
+    assert np.abs(full - og.loewdin_trafo_grad(mol.intor("int1e_ovlp"))).max() < 1e-10
+    assert np.array_equal(agl.get_overlap_grad(mol), og.get_overlap_grad(mol))
+
+
+@pytest.mark.parametrize("layout", [6, 5, 3, 2])
+@pytest.mark.parametrize("norb,natm,ntrain", PREDICT_CASES)
+def test_subspace_solvers(norb, natm, ntrain, layout):
+    from evcont_b200 import ab_initio_eigenvector_continuation as evc
+    g = load_predict_golden(norb, natm, ntrain)
+    ovlp, one, two = synthetic_stack(norb, ntrain, int(g["seed"]) + 100, layout)
+    e, c = evc.approximate_ground_state(g["h1"], g["h2"], one, two, ovlp)
+    assert abs(e - float(g[f"L{layout}_E0"])) < E_TOL
+    ref = g[f"L{layout}_c0"]
+    assert np.abs(c * np.sign(c[0]) - ref * np.sign(ref[0])).max() < 1e-8
+    assert abs(c @ ovlp @ c - 1.0) < 1e-12
+    nr = min(3, ntrain)
+    em, cm = evc.approximate_multistate(g["h1"], g["h2"], one, two, ovlp, nroots=nr)
+    assert em.shape == (nr,) and cm.shape == (nr, ntrain)
+    assert np.abs(em - g[f"L{layout}_Ems"]).max() < E_TOL
+    for r in range(nr):
+        ref = g[f"L{layout}_Cms"][r]
+        k = np.argmax(np.abs(ref))
+        assert np.abs(cm[r] * np.sign(cm[r][k]) - ref * np.sign(ref[k])).max() < 1e-7
+
+
+@pytest.mark.parametrize("layout", [6, 5, 3, 2])
+@pytest.mark.parametrize("norb,natm,ntrain", PREDICT_CASES)
+def test_energy_with_grad_golden(norb, natm, ntrain, layout):
+    from evcont_b200.ab_initio_gradients_loewdin import get_energy_with_grad
+    g = load_predict_golden(norb, natm, ntrain)
+    mol = _mol(norb, natm, int(g["seed"]))
+    ovlp, one, two = synthetic_stack(norb, ntrain, int(g["seed"]) + 100, layout)
+    e, grad, gam, Gam = get_energy_with_grad(mol, one, two, ovlp, return_density_matrices=True)
+    assert abs(e - float(g[f"L{layout}_Etot"])) < E_TOL
+    assert grad.shape == (natm, 3)
+    assert np.abs(grad - g[f"L{layout}_grad"]).max() < F_TOL
+    assert np.abs(gam - g[f"L{layout}_gamma"]).max() < 1e-9
+    if f"L{layout}_Gamma" in g:
+        assert np.abs(Gam - g[f"L{layout}_Gamma"]).max() < 1e-9
+    e2, grad2 = get_energy_with_grad(mol, one, two, ovlp)
+    assert e2 == e and np.array_equal(grad, grad2)  # deterministic
+
+
+def test_grad_elec_OAO_against_oracle():
+    from evcont_b200.ab_initio_gradients_loewdin import get_grad_elec_OAO
+    from oracle import gradients as og
+    rng = np.random.default_rng(5)
+    mol = _mol(7, 3, 21)
+    gamma = rng.standard_normal((7, 7))
+    Gamma = rng.standard_normal((7,) * 4)
+    ref = og.get_grad_elec_OAO(mol, gamma, Gamma)
+    got = get_grad_elec_OAO(mol, gamma, Gamma)
+    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_batch_matches_single_and_oracle():
+    """A batch of geometries through the fused step == one-by-one == CPU oracle."""
+    from evcont_b200.ab_initio_gradients_loewdin import get_energy_with_grad, get_energy_with_grad_batch
+    from oracle import gradients as og
+    norb, natm, ntrain = 6, 4, 5
+    ovlp, one, two = synthetic_stack(norb, ntrain, 77, 5)
+    mols = [_mol(norb, natm, 300 + k) for k in range(7)]
+    E, G = get_energy_with_grad_batch(mols, one, two, ovlp)
+    for k, m in enumerate(mols):
+        e1, g1 = get_energy_with_grad(m, one, two, ovlp)
+        assert E[k] == e1 and np.array_equal(G[k], g1)
+        oe, ogr = og.get_energy_with_grad(m, one, two, ovlp)
+        assert abs(E[k] - oe) < E_TOL and np.abs(G[k] - ogr).max() < F_TOL
+
+
+def test_h10_size_vs_oracle():
+    """configs[1] sizes: norb 10, 10 atoms, N = 20, tril layout."""
+    from evcont_b200.ab_initio_gradients_loewdin import get_energy_with_grad
+    from oracle import gradients as og
+    ovlp, one, two = synthetic_stack(10, 20, 9, 5)
+    mol = _mol(10, 10, 123)
+    e, grad = get_energy_with_grad(mol, one, two, ovlp)
+    oe, ogr = og.get_energy_with_grad(mol, one, two, ovlp)
+    assert abs(e - oe) < E_TOL
+    assert np.abs(grad - ogr).max() < F_TOL
+
+
+def test_not_positive_definite_overlap_raises():
+    from evcont_b200.ab_initio_eigenvector_continuation import approximate_ground_state
+    g = load_predict_golden(4, 2, 3)
+    ovlp, one, two = synthetic_stack(4, 3, 1, 6)
+    ovlp = ovlp.copy()
+    ovlp[2, 2] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        approximate_ground_state(g["h1"], g["h2"], one, two, ovlp)
+
+
+def test_bad_layout_asserts():
+    from evcont_b200.ab_initio_eigenvector_continuation import approximate_ground_state
+    g = load_predict_golden(4, 2, 3)
+    ovlp, one, two = synthetic_stack(4, 3, 1, 6)
+    with pytest.raises(AssertionError):
+        approximate_ground_state(g["h1"], g["h2"], one, two.reshape(3, 3, 4, 64), ovlp)
+
+
+def test_scanner_surface():
+    from evcont_b200.MD_utils import get_scanner
+    from oracle import gradients as og
+    ovlp, one, two = synthetic_stack(6, 3, 3, 6)
+    mol = _mol(6, 6, 12)
+    sc = get_scanner(mol, one, two, ovlp)
+    e, grad = sc(mol)
+    oe, ogr, ogam, oGam = og.get_energy_with_grad(mol, one, two, ovlp, return_density_matrices=True)
+    assert abs(e - oe) < E_TOL and np.abs(grad - ogr).max() < F_TOL
+    assert sc.base.converged and sc.mol is mol
+    assert np.abs(sc.base.predicted_one_rdm - ogam).max() < 1e-9
+    assert np.abs(sc.base.predicted_two_rdm - oGam).max() < 1e-9
+    e0, g0 = get_scanner(mol, None, None, None)(mol)
+    assert e0 == mol.energy_nuc() and np.array_equal(g0, mol.grad_nuc())
