@@ -36,6 +36,9 @@ SIGNATURES = {
     "evc_ctx_destroy": (C.c_int, [C.c_void_p]),
     "evc_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "evc_ctx_sm_count": (C.c_int, [C.c_void_p]),
+    "evc_launch_count": (C.c_ulonglong, []),
+    "evc_ctx_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "evc_ctx_stage_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "evc_num_strings": (c_i64, [C.c_int, C.c_int]),
     "evc_num_links": (C.c_int, [C.c_int, C.c_int]),
     "evc_make_strings_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),

@@ -7,15 +7,35 @@
 
 #include "evcont_b200.h"
 
+enum {
+  EVC_STAGE_LOEWDIN = 0,
+  EVC_STAGE_AO2OAO,
+  EVC_STAGE_SUBSPACE_H,
+  EVC_STAGE_GENEIG,
+  EVC_STAGE_PREDICT,
+  EVC_STAGE_GRAD,
+  EVC_NSTAGE
+};
+
 struct evc_ctx {
   int device;
   cudaStream_t stream;
   int sm_count;
   size_t smem_optin;
   double last_trdm_flops;
+  // optional per-stage timing of evc_energy_with_grad (evc_ctx_stage_timing)
+  int stage_timing;
+  cudaEvent_t stage_ev[EVC_NSTAGE + 1];
+  double stage_ms[EVC_NSTAGE];
+  long long stage_calls;
+  int stage_pending;
 };
 
+// number of kernel launches issued by this library (all contexts of the process)
+extern unsigned long long g_evc_launches;
+
 void evc_set_error(const char* fmt, ...);
+extern "C" int evc_stage_mark(evc_ctx* ctx, int stage);
 
 #define EVC_CHECK_CUDA(expr)                                                        \
   do {                                                                              \
@@ -35,7 +55,11 @@ void evc_set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
-#define EVC_CHECK_LAUNCH() EVC_CHECK_CUDA(cudaGetLastError())
+#define EVC_CHECK_LAUNCH()              \
+  do {                                  \
+    ++g_evc_launches;                   \
+    EVC_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
 
 static inline size_t evc_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_evc_launches = 0;
 
 void evc_set_error(const char* fmt, ...) {
   va_list ap;
@@ -37,11 +38,25 @@ int evc_ctx_create(int device, void* stream, evc_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->last_trdm_flops = 0.0;
+  c->stage_timing = 0;
+  c->stage_calls = 0;
+  c->stage_pending = 0;
+  for (int k = 0; k < EVC_NSTAGE; ++k) c->stage_ms[k] = 0.0;
+  for (int k = 0; k <= EVC_NSTAGE; ++k) {
+    cudaError_t ee = cudaEventCreate(&c->stage_ev[k]);
+    if (ee != cudaSuccess) {
+      evc_set_error("evc_ctx_create: cudaEventCreate failed: %s", cudaGetErrorString(ee));
+      delete c;
+      return -2;
+    }
+  }
   *out = c;
   return 0;
 }
 
 int evc_ctx_destroy(evc_ctx* ctx) {
+  if (ctx)
+    for (int k = 0; k <= EVC_NSTAGE; ++k) cudaEventDestroy(ctx->stage_ev[k]);
   delete ctx;
   return 0;
 }
@@ -53,5 +68,55 @@ int evc_ctx_set_stream(evc_ctx* ctx, void* stream) {
 }
 
 int evc_ctx_sm_count(const evc_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
+
+unsigned long long evc_launch_count(void) { return g_evc_launches; }
+
+// fold the events of the last timed evc_energy_with_grad call into stage_ms
+static int evc_collect_stage_times(evc_ctx* ctx) {
+  if (!ctx->stage_pending) return 0;
+  EVC_CHECK_CUDA(cudaEventSynchronize(ctx->stage_ev[EVC_NSTAGE]));
+  for (int k = 0; k < EVC_NSTAGE; ++k) {
+    float ms = 0.f;
+    EVC_CHECK_CUDA(cudaEventElapsedTime(&ms, ctx->stage_ev[k], ctx->stage_ev[k + 1]));
+    ctx->stage_ms[k] += ms;
+  }
+  ctx->stage_calls += 1;
+  ctx->stage_pending = 0;
+  return 0;
+}
+
+int evc_stage_mark(evc_ctx* ctx, int stage) {
+  if (!ctx->stage_timing) return 0;
+  if (stage == 0) {
+    int rc = evc_collect_stage_times(ctx);
+    if (rc) return rc;
+  }
+  EVC_CHECK_CUDA(cudaEventRecord(ctx->stage_ev[stage], ctx->stream));
+  if (stage == EVC_NSTAGE) ctx->stage_pending = 1;
+  return 0;
+}
+
+int evc_ctx_stage_timing(evc_ctx* ctx, int enable) {
+  EVC_REQUIRE(ctx != nullptr, "evc_ctx_stage_timing: ctx is NULL");
+  if (ctx->stage_timing) {
+    int rc = evc_collect_stage_times(ctx);
+    if (rc) return rc;
+  }
+  ctx->stage_timing = enable ? 1 : 0;
+  if (enable) {
+    for (int k = 0; k < EVC_NSTAGE; ++k) ctx->stage_ms[k] = 0.0;
+    ctx->stage_calls = 0;
+  }
+  return 0;
+}
+
+int evc_ctx_stage_times(evc_ctx* ctx, double* ms, int64_t* calls) {
+  EVC_REQUIRE(ctx && ms && calls, "evc_ctx_stage_times: NULL argument");
+  int rc = evc_collect_stage_times(ctx);
+  if (rc) return rc;
+  for (int k = 0; k < EVC_NSTAGE; ++k) ms[k] = ctx->stage_ms[k];
+  *calls = ctx->stage_calls;
+  return 0;
+}
 
 }  // extern "C"

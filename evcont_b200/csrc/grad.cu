@@ -359,17 +359,23 @@ int evc_energy_with_grad(evc_ctx* ctx, int layout, int N, int n, int natm, const
   if (gamma_out) gamma = gamma_out;
   if (Gamma_out) Gamma = Gamma_out;
   if (Cvec) C = Cvec;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_LOEWDIN))) return rc;
   if ((rc = evc_loewdin(ctx, nbatch, n, ao->ovlp, X, evals, evecs))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_AO2OAO))) return rc;
   if ((rc = evc_ao2oao(ctx, nbatch, n, ao->hcore, ao->eri, X, 0, h1, h2, t3, scratch, evc_align_up(nbatch * n4 * 8, 256)))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_SUBSPACE_H))) return rc;
   if ((rc = evc_subspace_H(ctx, layout, N, n, one_rdm, two_rdm, nbatch, h1, h2, H, sub_ws, sub_b))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_GENEIG))) return rc;
   if ((rc = evc_geneig(ctx, nbatch, N, H, Linv, 1, E0, C))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_PREDICT))) return rc;
   if ((rc = evc_predict_rdm(ctx, layout, N, n, one_rdm, two_rdm, nbatch, C, N, gamma, Gamma, pred_ws, pred_b))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD))) return rc;
   if ((rc = grad_elec_impl(ctx, nbatch, n, natm, ao->aoslices, evals, evecs, X, ao->hcore, t3, gamma, Gamma,
                            ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b)))
     return rc;
   add_enuc_kernel<<<(nbatch + 127) / 128, 128, 0, ctx->stream>>>(nbatch, E0, ao->e_nuc, E);
   EVC_CHECK_LAUNCH();
-  return 0;
+  return evc_stage_mark(ctx, EVC_NSTAGE);
 }
 
 }  // extern "C"

@@ -67,6 +67,23 @@ class Engine:
                                    device=self.device)
         return self._ws
 
+    STAGES = ("loewdin", "ao2oao", "subspace_H", "geneig", "predict_rdm", "grad")
+
+    def launch_count(self):
+        """Kernel launches issued by the library so far (process-wide)."""
+        return int(self.lib.evc_launch_count())
+
+    def stage_timing(self, enable=True):
+        """Switch per-stage CUDA-event timing of :meth:`energy_with_grad` on/off."""
+        check(self.lib.evc_ctx_stage_timing(self._ctx, 1 if enable else 0))
+
+    def stage_times(self):
+        """``({stage: accumulated ms}, calls)`` since :meth:`stage_timing` was enabled."""
+        ms = (C.c_double * len(self.STAGES))()
+        calls = C.c_int64()
+        check(self.lib.evc_ctx_stage_times(self._ctx, ms, C.byref(calls)))
+        return dict(zip(self.STAGES, list(ms))), int(calls.value)
+
     def empty(self, *shape, dtype=torch.float64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 

@@ -51,6 +51,17 @@ int evc_ctx_create(int device, void *stream, evc_ctx **out);
 int evc_ctx_destroy(evc_ctx *ctx);
 int evc_ctx_set_stream(evc_ctx *ctx, void *stream);
 int evc_ctx_sm_count(const evc_ctx *ctx);
+/* kernel launches issued by this library so far (process-wide; for bench.py's
+ * `gpu_launches`). */
+unsigned long long evc_launch_count(void);
+/* Per-stage device timing of evc_energy_with_grad (CUDA events on the ctx
+ * stream; stages: 0 Loewdin, 1 AO->OAO, 2 subspace H, 3 eigensolve, 4 predicted
+ * RDMs, 5 gradient).  evc_ctx_stage_timing(ctx, 1) resets and enables the
+ * accumulators; evc_ctx_stage_times synchronises on the last call's events and
+ * returns the accumulated milliseconds per stage and the number of calls. */
+#define EVC_NUM_STAGES 6
+int evc_ctx_stage_timing(evc_ctx *ctx, int enable);
+int evc_ctx_stage_times(evc_ctx *ctx, double *ms /* [EVC_NUM_STAGES] */, int64_t *calls);
 
 /* ---- K0: occupation strings and link tables (host, bit-exact) ---------
  * Replaces pyscf.fci.cistring.make_strings / str2addr / gen_linkstr_index, which

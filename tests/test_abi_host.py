@@ -1,0 +1,100 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol
+include/evcont_b200.h declares, the host-side K0 entry points (strings, addresses,
+link tables) are bit-exact against the oracle, and compute entry points fail
+loudly (no CPU fallback) when no device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from evcont_b200 import _lib, cistring
+from oracle import cistring as ocs
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "evcont_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(evc_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    handle = C.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert _lib.lib().evc_abi_version() == 1
+
+
+@pytest.mark.parametrize("norb,nocc", [(1, 0), (1, 1), (2, 1), (4, 2), (5, 3), (6, 3), (8, 4),
+                                       (10, 5), (13, 5), (12, 1), (9, 9)])
+def test_link_tables_bit_exact(norb, nocc):
+    strs = cistring.make_strings(range(norb), nocc)
+    assert strs.dtype == np.int64 and np.array_equal(strs, ocs.make_strings(norb, nocc))
+    tab = cistring.gen_linkstr_index(range(norb), nocc)
+    ref = ocs.gen_linkstr_index(norb, nocc)
+    assert tab.dtype == np.int32 and tab.shape == ref.shape
+    assert np.array_equal(tab, ref)
+    for k in (0, len(strs) // 2, len(strs) - 1):
+        assert cistring.str2addr(norb, nocc, int(strs[k])) == k
+        assert cistring.addr2str(norb, nocc, k) == int(strs[k])
+
+
+def test_link_golden_rows():
+    g = np.load(os.path.join(GOLDEN, "linkindex_n4_k2.npz"))
+    assert np.array_equal(cistring.make_strings(range(4), 2), g["strings"])
+    assert np.array_equal(cistring.gen_linkstr_index(range(4), 2)[0], g["row0"])
+
+
+def test_packed_link_records():
+    tab = cistring.gen_linkstr_index(range(6), 3)
+    nstr, nlink = tab.shape[:2]
+    for link_major in (0, 1):
+        out = np.empty(nstr * nlink, dtype=np.uint64)
+        _lib.check(_lib.lib().evc_linkindex_pack_host(nstr, nlink, tab.ctypes.data, link_major,
+                                                      out.ctypes.data))
+        out = out.reshape((nlink, nstr) if link_major else (nstr, nlink))
+        if link_major:
+            out = out.T
+        assert np.array_equal((out & 0xFFFFFFFF).astype(np.int64), tab[:, :, 2])
+        assert np.array_equal(((out >> 32) & 0xFF).astype(np.int64), tab[:, :, 0])
+        assert np.array_equal(((out >> 40) & 0xFF).astype(np.int64), tab[:, :, 1])
+        assert np.array_equal(((out >> 48) & 0xFF).astype(np.uint8).view(np.int8), tab[:, :, 3])
+
+
+def test_bad_arguments_are_errors():
+    assert _lib.lib().evc_num_strings(4, 5) == -1
+    with pytest.raises(ValueError):
+        cistring.str2addr(4, 2, 0b0111)
+    with pytest.raises(ValueError):
+        cistring.addr2str(4, 2, 6)
+    with pytest.raises(NotImplementedError):
+        cistring.make_strings([0, 2, 3], 2)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    handle = C.c_void_p()
+    rc = _lib.lib().evc_ctx_create(0, None, C.byref(handle))
+    assert rc != 0 and b"no CPU fallback" in _lib.lib().evc_last_error()
+    from evcont_b200.engine import get_engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        get_engine()
+    from evcont_b200.fci import B200FCISolver
+    with pytest.raises(RuntimeError):
+        B200FCISolver().trans_rdm12(np.eye(2), np.eye(2), 2, (1, 1))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "evcont_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), name
