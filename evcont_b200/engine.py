@@ -100,10 +100,12 @@ class Engine:
             from . import cistring
             tab = cistring.gen_linkstr_index(range(norb), nocc)
             nstr, nlink = tab.shape[0], tab.shape[1]
-            sm = np.empty(nstr * nlink, dtype=np.uint64)
-            lm = np.empty(nstr * nlink, dtype=np.uint64)
-            check(self.lib.evc_linkindex_pack_host(nstr, nlink, tab.ctypes.data, 0, sm.ctypes.data))
-            check(self.lib.evc_linkindex_pack_host(nstr, nlink, tab.ctypes.data, 1, lm.ctypes.data))
+            # at least one record so that empty tables (nocc == 0) still have an address
+            sm = np.zeros(max(1, nstr * nlink), dtype=np.uint64)
+            lm = np.zeros(max(1, nstr * nlink), dtype=np.uint64)
+            if nlink:
+                check(self.lib.evc_linkindex_pack_host(nstr, nlink, tab.ctypes.data, 0, sm.ctypes.data))
+                check(self.lib.evc_linkindex_pack_host(nstr, nlink, tab.ctypes.data, 1, lm.ctypes.data))
             self._links[key] = (nstr, nlink,
                                 torch.from_numpy(sm.view(np.int64)).to(self.device),
                                 torch.from_numpy(lm.view(np.int64)).to(self.device))
