@@ -13,6 +13,7 @@
 // vectorised 16-byte loads, a register tile of GB geometries per stack element,
 // fixed-order reductions (bit-reproducible).
 #include "common.cuh"
+#include "dgemm.cuh"
 
 namespace {
 
@@ -111,7 +112,9 @@ __device__ __forceinline__ void tril_unrank(int64_t t, int& a, int& b) {
 }
 
 // H[g][a][b] = one_rdm[a][b] . h1[g] + scale * sum_chunks partial
+// partial element (g, p, c) lives at partial[g*sg + p*sp + c*sc]
 __global__ void assemble_H_kernel(int N, int n2, int tril, double scale, int P, int nchunk,
+                                  int64_t sg, int64_t sp, int64_t sc,
                                   const double* __restrict__ one_rdm, const double* __restrict__ h1,
                                   const double* __restrict__ partial, double* __restrict__ H) {
   const int g = blockIdx.y;
@@ -127,8 +130,8 @@ __global__ void assemble_H_kernel(int N, int n2, int tril, double scale, int P, 
   if (!tril) p = ab;
   else if (a >= b) p = a * (a + 1) / 2 + b;
   if (p >= 0) {
-    const double* pp = partial + (static_cast<int64_t>(g) * P + p) * nchunk;
-    for (int c = 0; c < nchunk; ++c) two += pp[c];
+    const double* pp = partial + g * sg + p * sp;
+    for (int c = 0; c < nchunk; ++c) two += pp[c * sc];
   }
   H[static_cast<int64_t>(g) * N * N + ab] = one + scale * two;
 }
@@ -240,6 +243,18 @@ __global__ void gamma2_finalize_kernel(int n2, int exch, int64_t L, int G, int n
   Gamma[static_cast<int64_t>(g) * n4 + k] = acc;
 }
 
+// Batches of more than kGemvMaxBatch geometries go through the DMMA GEMM kernels
+// (dgemm.cuh); smaller ones through the streaming GEMV-style kernels above, which
+// read the stack exactly once at HBM/L2 speed.
+constexpr int kGemvMaxBatch = 4;
+constexpr int kPlanSms = 148;  // B200; the plan must not depend on the ctx (workspace sizing)
+constexpr int kK5BM = 128, kK5BN = 80;
+
+evc_gemm::Plan k5_plan(int G, int P, int64_t L) {
+  const int tiles = ((G + kK5BM - 1) / kK5BM) * ((P + kK5BN - 1) / kK5BN);
+  return evc_gemm::plan_split(tiles, static_cast<int>(L), kPlanSms, 64);
+}
+
 int axpy_nsplit(int64_t L, int P, int G) {
   const int64_t blocks = ((L + 511) / 512) * ((G + kGB - 1) / kGB);
   int64_t s = (2 * 148 + blocks - 1) / blocks;
@@ -258,7 +273,8 @@ int evc_subspace_workspace_bytes(int layout, int N, int n, int nbatch, size_t* b
   const int64_t n4 = static_cast<int64_t>(n) * n * n * n;
   const int64_t L = layout_is_exch(layout) ? exch_len(n) : n4;
   const int64_t P = layout_is_tril(layout) ? static_cast<int64_t>(N) * (N + 1) / 2 : static_cast<int64_t>(N) * N;
-  const int64_t nchunk = (L + kChunk - 1) / kChunk;
+  int64_t nchunk = (L + kChunk - 1) / kChunk;
+  if (nbatch > kGemvMaxBatch) nchunk = k5_plan(nbatch, static_cast<int>(P), L).nsplit;
   size_t tot = evc_align_up(static_cast<size_t>(nbatch) * P * nchunk * 8, 256);
   if (layout_is_exch(layout)) tot += evc_align_up(static_cast<size_t>(nbatch) * L * 8, 256);
   *bytes = tot;
@@ -277,7 +293,10 @@ int evc_subspace_H(evc_ctx* ctx, int layout, int N, int n, const double* one_rdm
   const bool exch = layout_is_exch(layout), tril = layout_is_tril(layout);
   const int64_t L = exch ? exch_len(n) : n4;
   const int P = tril ? N * (N + 1) / 2 : N * N;
-  const int nchunk = static_cast<int>((L + kChunk - 1) / kChunk);
+  const bool gemm = nbatch > kGemvMaxBatch;
+  EVC_REQUIRE(L < (int64_t(1) << 31), "evc_subspace_H: n=%d too large", n);
+  const evc_gemm::Plan k5 = k5_plan(nbatch, P, L);
+  const int nchunk = gemm ? k5.nsplit : static_cast<int>((L + kChunk - 1) / kChunk);
   evc_arena ar(workspace, workspace_bytes);
   double* partial = ar.take<double>(static_cast<size_t>(nbatch) * P * nchunk);
   double* hc = exch ? ar.take<double>(static_cast<size_t>(nbatch) * L) : nullptr;
@@ -289,7 +308,13 @@ int evc_subspace_H(evc_ctx* ctx, int layout, int N, int n, const double* one_rdm
     EVC_CHECK_LAUNCH();
     hv = hc;
   }
-  {
+  if (gemm) {
+    // partial[z][g][p] = sum_{l in split z} hv[g][l] R2[p][l]   (DMMA, split-K)
+    int rc = evc_gemm::launch<kK5BM, kK5BN, 4, 2, false>(ctx->stream, nbatch, P, static_cast<int>(L), k5, hv, L,
+                                                          two_rdm, L, partial, P,
+                                                          static_cast<int64_t>(nbatch) * P);
+    if (rc) return rc;
+  } else {
     dim3 grid(P, nchunk, (nbatch + kGB - 1) / kGB);
     EVC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "evc_subspace_H: batch/stack too large for one launch");
     const bool vec2 = (L % 2 == 0) && ((reinterpret_cast<uintptr_t>(two_rdm) & 15) == 0) &&
@@ -300,7 +325,10 @@ int evc_subspace_H(evc_ctx* ctx, int layout, int N, int n, const double* one_rdm
   }
   {
     dim3 grid((N * N + 127) / 128, nbatch);
-    assemble_H_kernel<<<grid, 128, 0, ctx->stream>>>(N, n2, tril ? 1 : 0, exch ? 1.0 : 0.5, P, nchunk,
+    const int64_t sg = gemm ? P : static_cast<int64_t>(P) * nchunk;
+    const int64_t sp = gemm ? 1 : nchunk;
+    const int64_t sc = gemm ? static_cast<int64_t>(nbatch) * P : 1;
+    assemble_H_kernel<<<grid, 128, 0, ctx->stream>>>(N, n2, tril ? 1 : 0, exch ? 1.0 : 0.5, P, nchunk, sg, sp, sc,
                                                      one_rdm, h1, partial, H);
     EVC_CHECK_LAUNCH();
   }
@@ -312,7 +340,7 @@ int evc_predict_workspace_bytes(int layout, int N, int n, int nbatch, size_t* by
   const int64_t n4 = static_cast<int64_t>(n) * n * n * n;
   const int64_t L = layout_is_exch(layout) ? exch_len(n) : n4;
   const int P = layout_is_tril(layout) ? N * (N + 1) / 2 : N * N;
-  const int nsplit = axpy_nsplit(L, P, nbatch);
+  const int nsplit = nbatch > kGemvMaxBatch ? 1 : axpy_nsplit(L, P, nbatch);
   *bytes = evc_align_up(static_cast<size_t>(nbatch) * P * 8, 256) +
            evc_align_up(static_cast<size_t>(nsplit) * nbatch * L * 8, 256);
   return 0;
@@ -330,7 +358,9 @@ int evc_predict_rdm(evc_ctx* ctx, int layout, int N, int n, const double* one_rd
   const bool exch = layout_is_exch(layout), tril = layout_is_tril(layout);
   const int64_t L = exch ? exch_len(n) : n4;
   const int P = tril ? N * (N + 1) / 2 : N * N;
-  const int nsplit = axpy_nsplit(L, P, nbatch);
+  const bool gemm = nbatch > kGemvMaxBatch;
+  EVC_REQUIRE(L < (int64_t(1) << 31), "evc_predict_rdm: n=%d too large", n);
+  const int nsplit = gemm ? 1 : axpy_nsplit(L, P, nbatch);
   evc_arena ar(workspace, workspace_bytes);
   double* w = ar.take<double>(static_cast<size_t>(nbatch) * P);
   double* part = ar.take<double>(static_cast<size_t>(nsplit) * nbatch * L);
@@ -345,7 +375,17 @@ int evc_predict_rdm(evc_ctx* ctx, int layout, int N, int n, const double* one_rd
     gamma1_kernel<<<grid, 128, 0, ctx->stream>>>(N, n2, one_rdm, C, c_stride, gamma);
     EVC_CHECK_LAUNCH();
   }
-  {
+  if (gemm) {
+    // Gamma[g][l] = sum_p w[g][p] R2[p][l]   (DMMA; written in place unless the
+    // exchange symmetry still has to be restored)
+    evc_gemm::Plan pl;
+    pl.nsplit = 1;
+    pl.kchunk = (P + evc_gemm::BK - 1) / evc_gemm::BK * evc_gemm::BK;
+    double* dst = exch ? part : Gamma;
+    int rc = evc_gemm::launch<64, 128, 2, 4, true>(ctx->stream, nbatch, static_cast<int>(L), P, pl, w, P, two_rdm, L,
+                                                   dst, L, 0);
+    if (rc) return rc;
+  } else {
     const bool vec2 = (L % 2 == 0) && ((reinterpret_cast<uintptr_t>(two_rdm) & 15) == 0);
     const int64_t per_block = vec2 ? 512 : 256;
     dim3 grid(static_cast<unsigned>((L + per_block - 1) / per_block), nsplit, (nbatch + kGB - 1) / kGB);
@@ -354,7 +394,7 @@ int evc_predict_rdm(evc_ctx* ctx, int layout, int N, int n, const double* one_rd
     else stack_axpy_kernel<false><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, w, nbatch, nsplit, part);
     EVC_CHECK_LAUNCH();
   }
-  {
+  if (!gemm || exch) {
     dim3 grid(static_cast<unsigned>((n4 + 255) / 256), nbatch);
     gamma2_finalize_kernel<<<grid, 256, 0, ctx->stream>>>(n2, exch ? 1 : 0, L, nbatch, nsplit, part, Gamma);
     EVC_CHECK_LAUNCH();

@@ -108,9 +108,13 @@ def test_batch_matches_single_and_oracle():
     ovlp, one, two = synthetic_stack(norb, ntrain, 77, 5)
     mols = [_mol(norb, natm, 300 + k) for k in range(7)]
     E, G = get_energy_with_grad_batch(mols, one, two, ovlp)
+    E2, G2 = get_energy_with_grad_batch(mols, one, two, ovlp)
+    assert np.array_equal(E, E2) and np.array_equal(G, G2)  # run-to-run bit identity
     for k, m in enumerate(mols):
         e1, g1 = get_energy_with_grad(m, one, two, ovlp)
-        assert E[k] == e1 and np.array_equal(G[k], g1)
+        # batches > 4 geometries run the DMMA GEMM kernels, single calls the streaming
+        # GEMV kernels: same numbers up to summation order
+        assert abs(E[k] - e1) < 1e-12 and np.abs(G[k] - g1).max() < 1e-11
         oe, ogr = og.get_energy_with_grad(m, one, two, ovlp)
         assert abs(E[k] - oe) < E_TOL and np.abs(G[k] - ogr).max() < F_TOL
 
@@ -159,3 +163,33 @@ def test_scanner_surface():
     assert np.abs(sc.base.predicted_two_rdm - oGam).max() < 1e-9
     e0, g0 = get_scanner(mol, None, None, None)(mol)
     assert e0 == mol.energy_nuc() and np.array_equal(g0, mol.grad_nuc())
+
+
+@pytest.mark.parametrize("layout", [6, 5, 3, 2])
+@pytest.mark.parametrize("norb,ntrain,G", [(5, 3, 9), (7, 5, 70), (10, 6, 33), (13, 4, 20)])
+def test_batched_stack_contractions_gemm_path(norb, ntrain, G, layout):
+    """K5/K7 on the DMMA GEMM path (batch > 4) against numpy, for all four layouts,
+    odd leading dimensions (norb 5, 7, 13) and ragged tile edges."""
+    from evcont_b200.engine import DeviceStack, get_engine
+    from oracle import gradients as og
+    from oracle import subspace as osub
+    rng = np.random.default_rng(norb * 100 + ntrain)
+    ovlp, one, two = synthetic_stack(norb, ntrain, 40 + norb, layout)
+    eng = get_engine()
+    stack = DeviceStack(ovlp, one, two, engine=eng, norb=norb)
+    h1 = rng.standard_normal((G, norb, norb))
+    h1 = h1 + h1.transpose(0, 2, 1)
+    h2 = rng.standard_normal((G,) + (norb,) * 4)
+    h2 = h2 + h2.transpose(0, 3, 4, 1, 2)
+    H = eng.subspace_H(stack, eng.to_device(h1), eng.to_device(h2)).cpu().numpy()
+    cv = rng.standard_normal((G, ntrain))
+    gam, Gam = eng.predict_rdm(stack, eng.to_device(cv))
+    gam, Gam = gam.cpu().numpy(), Gam.cpu().numpy()
+    il = np.tril_indices(ntrain)
+    for g in range(G):
+        ref = osub.subspace_hamiltonian(h1[g], h2[g], one, two)
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(H[g][il] - ref[il]).max() < 1e-12 * scale * norb ** 2
+        rg, rG = og.predict_rdms(cv[g], one, two, norb)
+        assert np.abs(gam[g] - rg).max() < 1e-11 * max(1.0, np.abs(rg).max())
+        assert np.abs(Gam[g] - rG).max() < 1e-11 * max(1.0, np.abs(rG).max())
