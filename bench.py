@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="geometries per step per GPU")
     ap.add_argument("--ntrain", type=int, default=20)
+    ap.add_argument("--chunk", type=int, default=128, help="geometries per pipelined chunk (e2e)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dgemm-peak", action="store_true")
@@ -71,14 +72,15 @@ def civecs(ntrain):
 
 
 def host_ao_batch(G, seed0, pin):
-    """G seeded synthetic geometries as one dict of (pinned) host tensors."""
+    """G seeded synthetic geometries as one pinned-host HostAO batch."""
     import torch
+    from evcont_b200.engine import HostAO
     from evcont_b200.mol import ao_bundle, synthetic_mol
     n, natm = NORB, NATM
-    shapes = dict(ovlp=(G, n, n), hcore=(G, n, n), eri=(G, n, n, n, n), ipovlp=(G, 3, n, n),
-                  hcore_deriv=(G, natm, 3, n, n), eri_ip1=(G, 3, n, n, n, n), e_nuc=(G,),
-                  grad_nuc=(G, natm, 3))
-    host = {k: torch.empty(s, dtype=torch.float64, pin_memory=pin) for k, s in shapes.items()}
+    b0 = ao_bundle(synthetic_mol(n, natm, seed=seed0))
+    hao = HostAO(G, n, natm, b0["aoslices"], pin=pin)
+    shapes = hao.shapes
+    host = {k: getattr(hao, k) for k in shapes}
     # distinct geometries are cheap to draw but slow to draw by the thousand in
     # Python: draw up to 64 and tile them with a per-geometry scale so no two are equal
     base = [ao_bundle(synthetic_mol(n, natm, seed=seed0 + k)) for k in range(min(G, 64))]
@@ -90,7 +92,7 @@ def host_ao_batch(G, seed0, pin):
             if k in ("hcore", "hcore_deriv", "e_nuc", "grad_nuc"):
                 src = src * f
             host[k][g].copy_(torch.from_numpy(np.ascontiguousarray(src).reshape(shapes[k][1:])))
-    return host, base[0]["aoslices"]
+    return hao, host, base[0]["aoslices"]
 
 
 # ---------------------------------------------------------------------------------
@@ -222,6 +224,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     stack = synthetic_stack_np(args.ntrain)
     per_step_s = max(1.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
     rates, total = [], 0
@@ -383,27 +390,22 @@ def run_b200(args):
     pairs_per_s = len(pairs) / (build_ms * 1e-3)
 
     # ---- phase 2: prediction steps ------------------------------------------------------
-    host, aoslices = host_ao_batch(G, seed0=100 + 1000 * rank, pin=True)
+    hao, host, aoslices = host_ao_batch(G, seed0=100 + 1000 * rank, pin=True)
     ao = DeviceAO(eng, G, n, NATM, aoslices)
     for k in DeviceAO.FIELDS:
         getattr(ao, k).copy_(host[k], non_blocking=True)
     torch.cuda.synchronize()
     E, grad, cvec = eng.empty(G), eng.empty(G, NATM, 3), eng.empty(G, N)
     out = (E, grad, cvec)
-    E_h = torch.empty(G, dtype=torch.float64, pin_memory=True)
-    grad_h = torch.empty(G, NATM, 3, dtype=torch.float64, pin_memory=True)
     h2d_bytes = sum(host[k].numel() * 8 for k in DeviceAO.FIELDS)
-    d2h_bytes = (E_h.numel() + grad_h.numel()) * 8
+    d2h_bytes = (hao.E.numel() + hao.grad.numel()) * 8
 
     def step_resident(_i):
         eng.energy_with_grad(stack, ao, out=out)
 
     def step_e2e(_i):
-        for k in DeviceAO.FIELDS:
-            getattr(ao, k).copy_(host[k], non_blocking=True)
-        eng.energy_with_grad(stack, ao, out=out)
-        E_h.copy_(E, non_blocking=True)
-        grad_h.copy_(grad, non_blocking=True)
+        # the public host-buffer call: pinned host AO arrays in, (E, grad) back on the host
+        eng.energy_with_grad_host(stack, hao, chunk=args.chunk, sync=False)
 
     sampler = ClockSampler(local)
     if rank == 0:

@@ -78,6 +78,12 @@ SIGNATURES = {
                                        c_double_p, c_double_p, C.c_int, C.POINTER(AoBundle),
                                        c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                        C.c_void_p, C.c_size_t]),
+    "evc_energy_with_grad_host_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int,
+                                                            C.c_int, c_sz_p]),
+    "evc_energy_with_grad_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            c_double_p, c_double_p, c_double_p, C.c_int,
+                                            C.POINTER(AoBundle), C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_size_t]),
 }
 
 _lib = None

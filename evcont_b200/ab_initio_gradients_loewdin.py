@@ -9,7 +9,7 @@ once, which is how the GPU is actually kept busy.
 import numpy as np
 import torch
 
-from .engine import DeviceAO, get_engine
+from .engine import DeviceAO, HostAO, get_engine
 from .mol import ao_bundle
 from .stackcache import as_device_stack
 
@@ -108,9 +108,12 @@ def get_energy_with_grad_batch(mols, one_RDM, two_RDM, S, return_density_matrice
     """The same step for a list of geometries in one launch sequence:
     ``(E[G], grad[G, natm, 3][, gamma[G], Gamma[G]])``."""
     stack = as_device_stack(one_RDM, two_RDM, S)
-    ao = DeviceAO.from_bundles(stack.engine, [ao_bundle(m) for m in mols])
-    E, grad, gamma, Gamma, _ = stack.engine.energy_with_grad(stack, ao, want_rdms=return_density_matrices)
-    out = (E.cpu().numpy(), grad.cpu().numpy())
-    if return_density_matrices:
-        out = out + (gamma.cpu().numpy(), Gamma.cpu().numpy())
-    return out
+    bundles = [ao_bundle(m) for m in mols]
+    if not return_density_matrices:
+        # host arrays in, host arrays out: the chunked copy/compute pipeline
+        host = HostAO.from_bundles(bundles)
+        E, grad = stack.engine.energy_with_grad_host(stack, host)
+        return E.numpy().copy(), grad.numpy().copy()
+    ao = DeviceAO.from_bundles(stack.engine, bundles)
+    E, grad, gamma, Gamma, _ = stack.engine.energy_with_grad(stack, ao, want_rdms=True)
+    return E.cpu().numpy(), grad.cpu().numpy(), gamma.cpu().numpy(), Gamma.cpu().numpy()

@@ -29,6 +29,10 @@ struct evc_ctx {
   double stage_ms[EVC_NSTAGE];
   long long stage_calls;
   int stage_pending;
+  // copy/compute pipeline of evc_energy_with_grad_host (created on first use)
+  int pipe_ready;
+  cudaStream_t h2d_stream, d2h_stream;
+  cudaEvent_t ev_h2d[2], ev_compute[2], ev_d2h[2], ev_start;
 };
 
 // number of kernel launches issued by this library (all contexts of the process)

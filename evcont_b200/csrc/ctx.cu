@@ -41,6 +41,7 @@ int evc_ctx_create(int device, void* stream, evc_ctx** out) {
   c->stage_timing = 0;
   c->stage_calls = 0;
   c->stage_pending = 0;
+  c->pipe_ready = 0;
   for (int k = 0; k < EVC_NSTAGE; ++k) c->stage_ms[k] = 0.0;
   for (int k = 0; k <= EVC_NSTAGE; ++k) {
     cudaError_t ee = cudaEventCreate(&c->stage_ev[k]);
@@ -55,8 +56,19 @@ int evc_ctx_create(int device, void* stream, evc_ctx** out) {
 }
 
 int evc_ctx_destroy(evc_ctx* ctx) {
-  if (ctx)
+  if (ctx) {
     for (int k = 0; k <= EVC_NSTAGE; ++k) cudaEventDestroy(ctx->stage_ev[k]);
+    if (ctx->pipe_ready) {
+      cudaStreamDestroy(ctx->h2d_stream);
+      cudaStreamDestroy(ctx->d2h_stream);
+      for (int k = 0; k < 2; ++k) {
+        cudaEventDestroy(ctx->ev_h2d[k]);
+        cudaEventDestroy(ctx->ev_compute[k]);
+        cudaEventDestroy(ctx->ev_d2h[k]);
+      }
+      cudaEventDestroy(ctx->ev_start);
+    }
+  }
   delete ctx;
   return 0;
 }

@@ -275,6 +275,71 @@ class Engine:
             _ptr(cvec), _ptr(ws), ws.numel()))
         return E, grad, gamma, Gamma, cvec
 
+    def energy_with_grad_host(self, stack, host_ao, chunk=256, sync=True):
+        """The prediction step on HOST arrays (:class:`HostAO`): chunked host->device
+        copies, kernels and read-back overlap on three streams.  Results land in
+        ``host_ao.E`` / ``host_ao.grad`` (returned); with ``sync=False`` the caller
+        synchronises the current stream before reading them."""
+        G, n, natm, N = host_ao.nbatch, host_ao.nao, host_ao.natm, stack.ntrain
+        if n != stack.norb:
+            raise ValueError(f"mol.nao={n} does not match the stack's norb={stack.norb}")
+        chunk = max(1, min(int(chunk), G))
+        nbytes = C.c_size_t()
+        check(self.lib.evc_energy_with_grad_host_workspace_bytes(stack.layout, N, n, natm, chunk,
+                                                                 C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        bundle = host_ao.bundle()
+        check(self.lib.evc_energy_with_grad_host(
+            self._ctx, stack.layout, N, n, natm, _ptr(stack.one_rdm), _ptr(stack.two_rdm),
+            _ptr(stack.linv), G, C.byref(bundle), C.c_void_p(host_ao.E.data_ptr()),
+            C.c_void_p(host_ao.grad.data_ptr()), chunk, _ptr(ws), ws.numel()))
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return host_ao.E, host_ao.grad
+
+
+class HostAO:
+    """AO arrays of a batch of geometries in (pinned) HOST memory -- the input of
+    :meth:`Engine.energy_with_grad_host`.  Fields as in :class:`DeviceAO`."""
+
+    FIELDS = ("ovlp", "hcore", "eri", "ipovlp", "hcore_deriv", "eri_ip1", "e_nuc", "grad_nuc")
+
+    def __init__(self, nbatch, nao, natm, aoslices, pin=True):
+        n = nao
+        self.nbatch, self.nao, self.natm = nbatch, nao, natm
+        self.shapes = dict(ovlp=(nbatch, n, n), hcore=(nbatch, n, n), eri=(nbatch, n, n, n, n),
+                           ipovlp=(nbatch, 3, n, n), hcore_deriv=(nbatch, natm, 3, n, n),
+                           eri_ip1=(nbatch, 3, n, n, n, n), e_nuc=(nbatch,),
+                           grad_nuc=(nbatch, natm, 3))
+        pin = bool(pin and torch.cuda.is_available())
+        for k, shp in self.shapes.items():
+            setattr(self, k, torch.empty(shp, dtype=torch.float64, pin_memory=pin))
+        self.aoslices = torch.from_numpy(
+            np.ascontiguousarray(aoslices, dtype=np.int32).reshape(natm, 2).copy())
+        self.E = torch.empty(nbatch, dtype=torch.float64, pin_memory=pin)
+        self.grad = torch.empty(nbatch, natm, 3, dtype=torch.float64, pin_memory=pin)
+
+    @classmethod
+    def from_bundles(cls, bundles, pin=True):
+        b0 = bundles[0]
+        self = cls(len(bundles), b0["nao"], b0["natm"], b0["aoslices"], pin=pin)
+        for k in cls.FIELDS:
+            dst = getattr(self, k).numpy()
+            for g, b in enumerate(bundles):
+                dst[g] = np.asarray(b[k], dtype=np.float64).reshape(self.shapes[k][1:])
+        return self
+
+    def nbytes(self):
+        return sum(getattr(self, k).numel() * 8 for k in self.FIELDS)
+
+    def bundle(self):
+        b = AoBundle()
+        for k in self.FIELDS:
+            setattr(b, k, getattr(self, k).data_ptr())
+        b.aoslices = self.aoslices.data_ptr()
+        return b
+
 
 class DeviceStack:
     """The t-RDM stack resident in HBM, in one of the reference's four layouts.

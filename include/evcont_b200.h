@@ -219,6 +219,21 @@ int evc_energy_with_grad(evc_ctx *ctx, int layout, int ntrain, int n, int natm,
                          double *gamma, double *Gamma, double *Cvec,
                          void *workspace, size_t workspace_bytes);
 
+/* The same step with HOST buffers on both sides -- the form the reference's call
+ * site has (evcont/MD_utils.py:43: numpy arrays from libcint in, (E, grad) out).
+ * Every pointer of `ao_host` (aoslices included), E_host and grad_host are HOST
+ * pointers (pinned memory keeps the call asynchronous); one_rdm / two_rdm / Linv /
+ * workspace are device pointers.  The batch is processed in chunks of `chunk`
+ * geometries: host->device copies, the K3..K8 kernels and the device->host
+ * read-back of consecutive chunks overlap on three streams; completion is ordered
+ * on the ctx stream (synchronise it before reading E_host / grad_host). */
+int evc_energy_with_grad_host_workspace_bytes(int layout, int ntrain, int n, int natm, int chunk,
+                                              size_t *bytes);
+int evc_energy_with_grad_host(evc_ctx *ctx, int layout, int ntrain, int n, int natm,
+                              const double *one_rdm, const double *two_rdm, const double *Linv,
+                              int nbatch, const evc_ao_bundle *ao_host, double *E_host,
+                              double *grad_host, int chunk, void *workspace, size_t workspace_bytes);
+
 #ifdef __cplusplus
 }
 #endif
