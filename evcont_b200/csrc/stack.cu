@@ -17,7 +17,6 @@
 
 namespace {
 
-constexpr int kGB = 4;             // geometries per register tile
 constexpr int64_t kChunk = 16384;  // stack elements per CTA in K5
 
 __host__ __device__ inline int64_t exch_len(int n) {
@@ -49,57 +48,80 @@ __global__ void pack_exchange_kernel(int n2, int64_t Lc, const double* __restric
   hc[static_cast<int64_t>(g) * Lc + t] = (x == y) ? 0.5 * v : v;
 }
 
-__device__ __forceinline__ double block_reduce_sum(double v, double* scratch) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  double tot = 0.0;
-  const int nw = blockDim.x >> 5;
-  for (int w = 0; w < nw; ++w) tot += scratch[w];
-  return tot;
-}
-
-// partial[g][p][chunk] = sum_{l in chunk} R2[p][l] * hv[g][l]
-template <bool VEC2>
+// K5 streaming form (few geometries, stack larger than any tensor-core tile can
+// amortise): partial[g][p][chunk] = sum_{l in chunk} R2[p][l] * hv[g][l].
+// A CTA owns RB consecutive pair rows x one chunk of kChunk stack columns and GB
+// geometries.  Per iteration a thread issues RB independent 16-byte loads of the
+// stack (2 iterations unrolled => 2*RB loads in flight per thread, ~64 KB per CTA)
+// and re-uses the hv vector it holds in registers for all RB rows, so the stack is
+// read exactly once from HBM and hv is re-read only P/RB times from L2.
+template <int RB, int GB, bool VEC2>
 __global__ void __launch_bounds__(256)
 stack_dot_kernel(const double* __restrict__ R2, int64_t L, int P, const double* __restrict__ hv,
                  int G, int nchunk, double* __restrict__ partial) {
-  __shared__ double scratch[8];
-  const int p = blockIdx.x, ch = blockIdx.y, g0 = blockIdx.z * kGB;
+  __shared__ double red[8][RB * GB];
+  const int p0 = blockIdx.x * RB, ch = blockIdx.y, g0 = blockIdx.z * GB;
   const int64_t lo = static_cast<int64_t>(ch) * kChunk;
   const int64_t hi = min(L, lo + kChunk);
-  const double* row = R2 + static_cast<int64_t>(p) * L;
-  const int ng = min(kGB, G - g0);
-  double acc[kGB];
+  const double* row[RB];
 #pragma unroll
-  for (int q = 0; q < kGB; ++q) acc[q] = 0.0;
+  for (int r = 0; r < RB; ++r) row[r] = R2 + static_cast<int64_t>(min(p0 + r, P - 1)) * L;
+  const double* hg[GB];
+#pragma unroll
+  for (int q = 0; q < GB; ++q) hg[q] = hv + static_cast<int64_t>(min(g0 + q, G - 1)) * L;
+  double acc[RB][GB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll
+    for (int q = 0; q < GB; ++q) acc[r][q] = 0.0;
   if (VEC2) {
+#pragma unroll 2
     for (int64_t l = lo + 2 * threadIdx.x; l < hi; l += 512) {
-      const double2 r = __ldg(reinterpret_cast<const double2*>(row + l));
+      double2 rv[RB], h[GB];
 #pragma unroll
-      for (int q = 0; q < kGB; ++q) {
-        if (q < ng) {
-          const double2 h = __ldg(reinterpret_cast<const double2*>(hv + static_cast<int64_t>(g0 + q) * L + l));
-          acc[q] += r.x * h.x;
-          acc[q] += r.y * h.y;
+      for (int r = 0; r < RB; ++r) rv[r] = __ldg(reinterpret_cast<const double2*>(row[r] + l));
+#pragma unroll
+      for (int q = 0; q < GB; ++q) h[q] = __ldg(reinterpret_cast<const double2*>(hg[q] + l));
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int q = 0; q < GB; ++q) {
+          acc[r][q] = fma(rv[r].x, h[q].x, acc[r][q]);
+          acc[r][q] = fma(rv[r].y, h[q].y, acc[r][q]);
         }
-      }
     }
   } else {
+#pragma unroll 2
     for (int64_t l = lo + threadIdx.x; l < hi; l += 256) {
-      const double r = __ldg(row + l);
+      double rv[RB], h[GB];
 #pragma unroll
-      for (int q = 0; q < kGB; ++q)
-        if (q < ng) acc[q] += r * __ldg(hv + static_cast<int64_t>(g0 + q) * L + l);
+      for (int r = 0; r < RB; ++r) rv[r] = __ldg(row[r] + l);
+#pragma unroll
+      for (int q = 0; q < GB; ++q) h[q] = __ldg(hg[q] + l);
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int q = 0; q < GB; ++q) acc[r][q] = fma(rv[r], h[q], acc[r][q]);
     }
   }
+  // fixed-order reduction: lanes (butterfly), then warps 0..7
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int q = 0; q < kGB; ++q) {
-    const double tot = block_reduce_sum(acc[q], scratch);
-    if (threadIdx.x == 0 && q < ng)
-      partial[(static_cast<int64_t>(g0 + q) * P + p) * nchunk + ch] = tot;
+  for (int r = 0; r < RB; ++r)
+#pragma unroll
+    for (int q = 0; q < GB; ++q) {
+      double v = acc[r][q];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][r * GB + q] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < RB * GB) {
+    const int r = threadIdx.x / GB, q = threadIdx.x - r * GB;
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w][threadIdx.x];
+    if (p0 + r < P && g0 + q < G)
+      partial[(static_cast<int64_t>(g0 + q) * P + p0 + r) * nchunk + ch] = tot;
   }
 }
 
@@ -172,54 +194,85 @@ __global__ void gamma1_kernel(int N, int n2, const double* __restrict__ one_rdm,
   gamma[static_cast<int64_t>(g) * n2 + k] = acc;
 }
 
-// part[split][g][l] = sum_{p in split} w[g][p] R2[p][l]
-template <bool VEC2>
+// K7 streaming form: part[split][g][l] = sum_{p in split} w[g][p] R2[p][l].
+// A thread owns two adjacent stack columns and walks the pair rows of its split with
+// 8 independent 16-byte loads in flight; the weights of the split are staged in
+// shared memory (read as broadcasts).  Grid sized by axpy_nsplit() to >= 16 CTAs/SM.
+constexpr int kAxpyWTile = 512;  // weights staged per pass: GB * 512 doubles <= 32 KB
+
+template <int GB, bool VEC2>
 __global__ void __launch_bounds__(256)
 stack_axpy_kernel(const double* __restrict__ R2, int64_t L, int P, const double* __restrict__ w,
                   int G, int nsplit, double* __restrict__ part) {
-  const int split = blockIdx.y, g0 = blockIdx.z * kGB;
+  __shared__ double ws[GB][kAxpyWTile];
+  const int split = blockIdx.y, g0 = blockIdx.z * GB;
   const int p0 = static_cast<int>(static_cast<int64_t>(P) * split / nsplit);
   const int p1 = static_cast<int>(static_cast<int64_t>(P) * (split + 1) / nsplit);
-  const int ng = min(kGB, G - g0);
-  const double* wg = w + static_cast<int64_t>(g0) * P;
-  if (VEC2) {
-    const int64_t l = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 2;
-    if (l >= L) return;
-    double2 acc[kGB];
+  constexpr int W = VEC2 ? 2 : 1;
+  const int64_t l = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * W;
+  const bool live = l < L;
+  const double* col = R2 + (live ? l : 0);
+  double acc[GB][W];
 #pragma unroll
-    for (int q = 0; q < kGB; ++q) acc[q] = make_double2(0.0, 0.0);
-#pragma unroll 4
-    for (int p = p0; p < p1; ++p) {
-      const double2 r = __ldg(reinterpret_cast<const double2*>(R2 + static_cast<int64_t>(p) * L + l));
+  for (int q = 0; q < GB; ++q)
 #pragma unroll
-      for (int q = 0; q < kGB; ++q) {
-        if (q < ng) {
-          const double wv = __ldg(wg + static_cast<int64_t>(q) * P + p);
-          acc[q].x += wv * r.x;
-          acc[q].y += wv * r.y;
-        }
+    for (int e = 0; e < W; ++e) acc[q][e] = 0.0;
+  for (int pt = p0; pt < p1; pt += kAxpyWTile) {
+    const int cnt = min(kAxpyWTile, p1 - pt);
+    __syncthreads();
+    for (int k = threadIdx.x; k < GB * cnt; k += 256) {
+      const int q = k / cnt, j = k - q * cnt;
+      ws[q][j] = (g0 + q < G) ? __ldg(w + static_cast<int64_t>(g0 + q) * P + pt + j) : 0.0;
+    }
+    __syncthreads();
+    if (!live) continue;
+    int j = 0;
+    for (; j + 8 <= cnt; j += 8) {
+      if (VEC2) {
+        double2 rv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          rv[u] = __ldg(reinterpret_cast<const double2*>(col + static_cast<int64_t>(pt + j + u) * L));
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int q = 0; q < GB; ++q) {
+            const double wv = ws[q][j + u];
+            acc[q][0] = fma(wv, rv[u].x, acc[q][0]);
+            acc[q][W - 1] = fma(wv, rv[u].y, acc[q][W - 1]);
+          }
+      } else {
+        double rv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rv[u] = __ldg(col + static_cast<int64_t>(pt + j + u) * L);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int q = 0; q < GB; ++q) acc[q][0] = fma(ws[q][j + u], rv[u], acc[q][0]);
       }
     }
+    for (; j < cnt; ++j) {
+      if (VEC2) {
+        const double2 rv = __ldg(reinterpret_cast<const double2*>(col + static_cast<int64_t>(pt + j) * L));
 #pragma unroll
-    for (int q = 0; q < kGB; ++q)
-      if (q < ng)
-        *reinterpret_cast<double2*>(part + (static_cast<int64_t>(split) * G + g0 + q) * L + l) = acc[q];
-  } else {
-    const int64_t l = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-    if (l >= L) return;
-    double acc[kGB];
+        for (int q = 0; q < GB; ++q) {
+          acc[q][0] = fma(ws[q][j], rv.x, acc[q][0]);
+          acc[q][W - 1] = fma(ws[q][j], rv.y, acc[q][W - 1]);
+        }
+      } else {
+        const double rv = __ldg(col + static_cast<int64_t>(pt + j) * L);
 #pragma unroll
-    for (int q = 0; q < kGB; ++q) acc[q] = 0.0;
-#pragma unroll 4
-    for (int p = p0; p < p1; ++p) {
-      const double r = __ldg(R2 + static_cast<int64_t>(p) * L + l);
-#pragma unroll
-      for (int q = 0; q < kGB; ++q)
-        if (q < ng) acc[q] += __ldg(wg + static_cast<int64_t>(q) * P + p) * r;
+        for (int q = 0; q < GB; ++q) acc[q][0] = fma(ws[q][j], rv, acc[q][0]);
+      }
     }
+  }
+  if (!live) return;
 #pragma unroll
-    for (int q = 0; q < kGB; ++q)
-      if (q < ng) part[(static_cast<int64_t>(split) * G + g0 + q) * L + l] = acc[q];
+  for (int q = 0; q < GB; ++q) {
+    if (g0 + q >= G) continue;
+    double* dst = part + (static_cast<int64_t>(split) * G + g0 + q) * L + l;
+    if (VEC2) *reinterpret_cast<double2*>(dst) = make_double2(acc[q][0], acc[q][W - 1]);
+    else dst[0] = acc[q][0];
   }
 }
 
@@ -246,7 +299,11 @@ __global__ void gamma2_finalize_kernel(int n2, int exch, int64_t L, int G, int n
 // Batches of more than kGemvMaxBatch geometries go through the DMMA GEMM kernels
 // (dgemm.cuh); smaller ones through the streaming GEMV-style kernels above, which
 // read the stack exactly once at HBM/L2 speed.
-constexpr int kGemvMaxBatch = 4;
+constexpr int kGemvMaxBatch = 16;
+
+// geometries per register tile of the streaming kernels
+inline int stream_gb(int G) { return G <= 1 ? 1 : G <= 2 ? 2 : G <= 4 ? 4 : 8; }
+inline int stream_rb(int gb) { return gb <= 2 ? 8 : 4; }
 constexpr int kPlanSms = 148;  // B200; the plan must not depend on the ctx (workspace sizing)
 constexpr int kK5BM = 128, kK5BN = 80;
 
@@ -256,9 +313,10 @@ evc_gemm::Plan k5_plan(int G, int P, int64_t L) {
 }
 
 int axpy_nsplit(int64_t L, int P, int G) {
-  const int64_t blocks = ((L + 511) / 512) * ((G + kGB - 1) / kGB);
-  int64_t s = (2 * 148 + blocks - 1) / blocks;
-  if (s > 16) s = 16;
+  const int gb = stream_gb(G);
+  const int64_t blocks = ((L + 511) / 512) * ((G + gb - 1) / gb);
+  int64_t s = (16 * 148 + blocks - 1) / blocks;
+  if (s > 32) s = 32;
   if (s > P) s = P;
   if (s < 1) s = 1;
   return static_cast<int>(s);
@@ -315,12 +373,23 @@ int evc_subspace_H(evc_ctx* ctx, int layout, int N, int n, const double* one_rdm
                                                           static_cast<int64_t>(nbatch) * P);
     if (rc) return rc;
   } else {
-    dim3 grid(P, nchunk, (nbatch + kGB - 1) / kGB);
+    const int gb = stream_gb(nbatch), rb = stream_rb(gb);
+    dim3 grid((P + rb - 1) / rb, nchunk, (nbatch + gb - 1) / gb);
     EVC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "evc_subspace_H: batch/stack too large for one launch");
     const bool vec2 = (L % 2 == 0) && ((reinterpret_cast<uintptr_t>(two_rdm) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(hv) & 15) == 0);
-    if (vec2) stack_dot_kernel<true><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, hv, nbatch, nchunk, partial);
-    else stack_dot_kernel<false><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, hv, nbatch, nchunk, partial);
+#define EVC_DOT(RB, GB)                                                                                         \
+  do {                                                                                                          \
+    if (vec2) stack_dot_kernel<RB, GB, true><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, hv, nbatch, nchunk, partial); \
+    else stack_dot_kernel<RB, GB, false><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, hv, nbatch, nchunk, partial);     \
+  } while (0)
+    switch (gb) {
+      case 1: EVC_DOT(8, 1); break;
+      case 2: EVC_DOT(8, 2); break;
+      case 4: EVC_DOT(4, 4); break;
+      default: EVC_DOT(4, 8); break;
+    }
+#undef EVC_DOT
     EVC_CHECK_LAUNCH();
   }
   {
@@ -388,10 +457,21 @@ int evc_predict_rdm(evc_ctx* ctx, int layout, int N, int n, const double* one_rd
   } else {
     const bool vec2 = (L % 2 == 0) && ((reinterpret_cast<uintptr_t>(two_rdm) & 15) == 0);
     const int64_t per_block = vec2 ? 512 : 256;
-    dim3 grid(static_cast<unsigned>((L + per_block - 1) / per_block), nsplit, (nbatch + kGB - 1) / kGB);
+    const int gb = stream_gb(nbatch);
+    dim3 grid(static_cast<unsigned>((L + per_block - 1) / per_block), nsplit, (nbatch + gb - 1) / gb);
     EVC_REQUIRE(grid.z <= 65535, "evc_predict_rdm: batch too large for one launch");
-    if (vec2) stack_axpy_kernel<true><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, w, nbatch, nsplit, part);
-    else stack_axpy_kernel<false><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, w, nbatch, nsplit, part);
+#define EVC_AXPY(GB)                                                                                           \
+  do {                                                                                                         \
+    if (vec2) stack_axpy_kernel<GB, true><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, w, nbatch, nsplit, part); \
+    else stack_axpy_kernel<GB, false><<<grid, 256, 0, ctx->stream>>>(two_rdm, L, P, w, nbatch, nsplit, part);     \
+  } while (0)
+    switch (gb) {
+      case 1: EVC_AXPY(1); break;
+      case 2: EVC_AXPY(2); break;
+      case 4: EVC_AXPY(4); break;
+      default: EVC_AXPY(8); break;
+    }
+#undef EVC_AXPY
     EVC_CHECK_LAUNCH();
   }
   if (!gemm || exch) {

@@ -112,8 +112,8 @@ def test_batch_matches_single_and_oracle():
     assert np.array_equal(E, E2) and np.array_equal(G, G2)  # run-to-run bit identity
     for k, m in enumerate(mols):
         e1, g1 = get_energy_with_grad(m, one, two, ovlp)
-        # batches > 4 geometries run the DMMA GEMM kernels, single calls the streaming
-        # GEMV kernels: same numbers up to summation order
+        # the batch and the single call use different register tiles of the streaming
+        # kernels: same numbers up to summation order
         assert abs(E[k] - e1) < 1e-12 and np.abs(G[k] - g1).max() < 1e-11
         oe, ogr = og.get_energy_with_grad(m, one, two, ovlp)
         assert abs(E[k] - oe) < E_TOL and np.abs(G[k] - ogr).max() < F_TOL
@@ -166,10 +166,14 @@ def test_scanner_surface():
 
 
 @pytest.mark.parametrize("layout", [6, 5, 3, 2])
-@pytest.mark.parametrize("norb,ntrain,G", [(5, 3, 9), (7, 5, 70), (10, 6, 33), (13, 4, 20)])
-def test_batched_stack_contractions_gemm_path(norb, ntrain, G, layout):
-    """K5/K7 on the DMMA GEMM path (batch > 4) against numpy, for all four layouts,
-    odd leading dimensions (norb 5, 7, 13) and ragged tile edges."""
+@pytest.mark.parametrize("norb,ntrain,G", [(5, 3, 9), (7, 5, 70), (10, 6, 33), (13, 4, 20),
+                                           (6, 4, 1), (6, 4, 2), (6, 5, 3), (7, 5, 8), (7, 3, 13),
+                                           (13, 4, 16), (10, 6, 17)])
+def test_batched_stack_contractions(norb, ntrain, G, layout):
+    """K5/K7 against numpy on both paths -- the HBM-streaming kernels (batch <= 16, every
+    register-tile variant 1/2/4/8 with ragged last tiles) and the DMMA GEMM kernels
+    (batch > 16) -- for all four layouts, odd leading dimensions (norb 5, 7, 13) and
+    ragged tile edges."""
     from evcont_b200.engine import DeviceStack, get_engine
     from oracle import gradients as og
     from oracle import subspace as osub
