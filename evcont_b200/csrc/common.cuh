@@ -41,6 +41,29 @@ extern unsigned long long g_evc_launches;
 void evc_set_error(const char* fmt, ...);
 extern "C" int evc_stage_mark(evc_ctx* ctx, int stage);
 
+// internal cross-file helpers (not part of the C ABI)
+int evc_launch_rot_pass(cudaStream_t st, int nbatch, int n, const double* in, const double* M,
+                        int transpose_m, double* out);
+int evc_launch_geneig(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H,
+                      const double* Linv, int nroots, double* E, double* C);
+size_t evc_rows_dot_ws_bytes(int64_t L, int P, int G);
+int evc_rows_dot(evc_ctx* ctx, const double* rows, int64_t L, int P, const double* hv, int G, double* out,
+                 void* workspace, size_t workspace_bytes);
+size_t evc_rows_axpy_ws_bytes(int64_t L, int P, int G);
+int evc_rows_axpy(evc_ctx* ctx, const double* rows, int64_t L, int P, const double* w, int G, double* out,
+                  void* workspace, size_t workspace_bytes);
+// packed (8-fold symmetric) prediction step pieces, packed.cu
+constexpr int kPackedMaxNorb = 13;  // per-geometry shared-memory kernels up to this many orbitals
+int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
+                      const double* eri, double* hvec);
+int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices, const double* x,
+                    const double* evals, const double* evecs, const double* hcore, const double* eri,
+                    const double* out7, const double* ipovlp, const double* hcore_deriv,
+                    const double* eri_ip1, const double* grad_nuc, double* grad);
+int evc_packed_hvec_from_full(evc_ctx* ctx, int nbatch, int n, const double* h1, const double* h2, double* hvec);
+int evc_packed_unpack_rdms(evc_ctx* ctx, int nbatch, int n, const double* out7, double* gamma, double* Gamma8);
+int evc_packed_pair_weights(evc_ctx* ctx, int nbatch, int N, const double* C, int64_t c_stride, double* w);
+
 #define EVC_CHECK_CUDA(expr)                                                        \
   do {                                                                              \
     cudaError_t _e = (expr);                                                        \

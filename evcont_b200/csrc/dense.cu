@@ -11,29 +11,52 @@ namespace {
 
 // ---------------------------------------------------------------------------
 // Two-sided Jacobi eigensolver for a symmetric m x m matrix held in shared
-// memory, parallel (round-robin tournament) ordering: every round applies m/2
-// disjoint rotations, rows first then columns, all threads of the CTA
-// cooperating.  On exit diag(A) holds the eigenvalues, the columns of V the
-// eigenvectors (V is initialised to the identity here).
-// cs: scratch of 4*(m/2+1) doubles; red: scratch of 2 + 2*nwarps (<= 18) doubles.
+// memory, parallel (round-robin tournament) ordering.  Every round applies
+// mp/2 disjoint rotations J = prod R(p_k, q_k).  A' = J^T A J decomposes into
+// independent 2x2 blocks A'[{p1,q1},{p2,q2}] = R1^T A[{p1,q1},{p2,q2}] R2, so a
+// round is two phases only: (1) the mp/2 rotation angles, (2) one thread per 2x2
+// block applies the row and the column rotation at once (and V <- V J), i.e. two
+// block barriers per round and no integer division / modulo in the inner loops
+// (the tournament schedule is tabulated once).
+//
+// Storage: A is [mp][lda] with mp = m + (m & 1) (for odd m a zero row/column m is
+// the bye of the tournament; its rotation is the identity), V is [m][ldv] with
+// mp columns used.  On exit diag(A) holds the eigenvalues, the columns of V the
+// eigenvectors.  Scratch: cs 4*(mp/2) doubles, red 18 doubles,
+// sched (mp-1)*(mp/2) uint16 (p | q << 8).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int rr_player(int i, int r, int mp) {
-  return i == 0 ? 0 : 1 + (i - 1 + r) % (mp - 1);
+__host__ __device__ inline size_t jacobi_scratch_bytes(int m) {
+  const int mp = m + (m & 1), half = mp / 2;
+  size_t b = (4 * static_cast<size_t>(half) + 18) * sizeof(double);
+  b += (static_cast<size_t>(mp > 1 ? mp - 1 : 1) * half * sizeof(unsigned short) + 7) / 8 * 8;
+  return b;
 }
 
 __device__ void jacobi_eigh_smem(double* A, int lda, double* V, int ldv, int m, double* cs,
-                                 double* red) {
+                                 double* red, unsigned short* sched) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int k = tid; k < m * m; k += nt) {
-    const int i = k / m, j = k - i * m;
+  const int mp = m + (m & 1);
+  const int half = mp / 2;
+  for (int k = tid; k < m * mp; k += nt) {
+    const int i = k / mp, j = k - i * mp;
     V[i * ldv + j] = (i == j) ? 1.0 : 0.0;
+  }
+  if (m & 1) {  // bye row / column
+    for (int k = tid; k < mp; k += nt) { A[m * lda + k] = 0.0; A[k * lda + m] = 0.0; }
+  }
+  for (int k = tid; k < (mp - 1) * half; k += nt) {
+    const int r = k / half, i = k - r * half;
+    int p = (i == 0) ? 0 : 1 + (i - 1 + r) % (mp - 1);
+    const int i2 = mp - 1 - i;
+    int q = 1 + (i2 - 1 + r) % (mp - 1);
+    if (p > q) { const int t = p; p = q; q = t; }
+    sched[k] = static_cast<unsigned short>(p | (q << 8));
   }
   __syncthreads();
   if (m == 1) return;
-  const int mp = m + (m & 1);
-  const int half = mp / 2;
-  for (int sweep = 0; sweep < 40; ++sweep) {
-    // convergence: sum of squared off-diagonals vs Frobenius norm (fixed
+  const double tol = (static_cast<double>(m) * 2.3e-16) * (static_cast<double>(m) * 2.3e-16);
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    // convergence: squared off-diagonal norm vs squared Frobenius norm (fixed
     // summation order: per-warp partials, then warp 0 .. nwarps-1)
     {
       double off = 0.0, tot = 0.0;
@@ -50,69 +73,58 @@ __device__ void jacobi_eigh_smem(double* A, int lda, double* V, int ldv, int m, 
       if ((tid & 31) == 0) { red[2 + 2 * (tid >> 5)] = off; red[3 + 2 * (tid >> 5)] = tot; }
     }
     __syncthreads();
-    if (tid == 0) {
-      double off = 0.0, tot = 0.0;
-      for (int w = 0; w < (nt + 31) / 32; ++w) { off += red[2 + 2 * w]; tot += red[3 + 2 * w]; }
-      red[0] = off; red[1] = tot;
-    }
+    double off = 0.0, tot = 0.0;
+    for (int w = 0; w < (nt + 31) / 32; ++w) { off += red[2 + 2 * w]; tot += red[3 + 2 * w]; }
     __syncthreads();
-    const bool done = red[0] <= 1.0e-34 * red[1];
-    __syncthreads();
-    if (done) break;
+    if (off <= tol * tot) break;
     for (int r = 0; r < mp - 1; ++r) {
+      const unsigned short* sr = sched + r * half;
       // 1. rotation angles
       for (int k = tid; k < half; k += nt) {
-        int p = rr_player(k, r, mp), q = rr_player(mp - 1 - k, r, mp);
-        if (p > q) { const int t = p; p = q; q = t; }
-        double c = 1.0, s = 0.0, npp = 0.0, nqq = 0.0;
-        if (q < m) {
-          const double app = A[p * lda + p], aqq = A[q * lda + q], apq = A[p * lda + q];
-          npp = app; nqq = aqq;
-          if (fabs(apq) > 1.0e-300) {
-            const double theta = (aqq - app) / (2.0 * apq);
-            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            c = 1.0 / sqrt(t * t + 1.0);
-            s = t * c;
-            npp = app - t * apq;
-            nqq = aqq + t * apq;
-          }
+        const int p = sr[k] & 0xff, q = sr[k] >> 8;
+        const double app = A[p * lda + p], aqq = A[q * lda + q], apq = A[p * lda + q];
+        double c = 1.0, s = 0.0, npp = app, nqq = aqq;
+        if (fabs(apq) > 1.0e-300) {
+          const double theta = (aqq - app) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = rsqrt(t * t + 1.0);
+          s = t * c;
+          npp = app - t * apq;
+          nqq = aqq + t * apq;
         }
         cs[4 * k] = c; cs[4 * k + 1] = s; cs[4 * k + 2] = npp; cs[4 * k + 3] = nqq;
       }
       __syncthreads();
-      // 2. rows:  A <- J^T A
-      for (int idx = tid; idx < half * m; idx += nt) {
-        const int k = idx / m, j = idx - k * m;
-        int p = rr_player(k, r, mp), q = rr_player(mp - 1 - k, r, mp);
-        if (p > q) { const int t = p; p = q; q = t; }
-        if (q >= m) continue;
-        const double c = cs[4 * k], s = cs[4 * k + 1];
-        const double x = A[p * lda + j], y = A[q * lda + j];
-        A[p * lda + j] = c * x - s * y;
-        A[q * lda + j] = s * x + c * y;
-      }
-      __syncthreads();
-      // 3. columns:  A <- A J,  V <- V J ; the 2x2 pivot block is set analytically
-      for (int idx = tid; idx < half * m; idx += nt) {
-        const int k = idx / m, i = idx - k * m;
-        int p = rr_player(k, r, mp), q = rr_player(mp - 1 - k, r, mp);
-        if (p > q) { const int t = p; p = q; q = t; }
-        if (q >= m) continue;
-        const double c = cs[4 * k], s = cs[4 * k + 1];
-        if (i == p) {
-          A[p * lda + p] = cs[4 * k + 2];
-          A[p * lda + q] = 0.0;
-        } else if (i == q) {
-          A[q * lda + p] = 0.0;
-          A[q * lda + q] = cs[4 * k + 3];
+      // 2. 2x2 blocks of A (rows then columns) and V <- V J
+      const int nblk = half * half;
+      for (int idx = tid; idx < nblk + half * m; idx += nt) {
+        if (idx < nblk) {
+          const int k1 = idx / half, k2 = idx - k1 * half;
+          const int p1 = sr[k1] & 0xff, q1 = sr[k1] >> 8;
+          const int p2 = sr[k2] & 0xff, q2 = sr[k2] >> 8;
+          double* a_pp = A + p1 * lda + p2;
+          double* a_pq = A + p1 * lda + q2;
+          double* a_qp = A + q1 * lda + p2;
+          double* a_qq = A + q1 * lda + q2;
+          if (k1 == k2) {
+            *a_pp = cs[4 * k1 + 2]; *a_pq = 0.0; *a_qp = 0.0; *a_qq = cs[4 * k1 + 3];
+          } else {
+            const double c1 = cs[4 * k1], s1 = cs[4 * k1 + 1], c2 = cs[4 * k2], s2 = cs[4 * k2 + 1];
+            const double a = *a_pp, b = *a_pq, c = *a_qp, d = *a_qq;
+            const double ra = c1 * a - s1 * c, rc = s1 * a + c1 * c;  // rows
+            const double rb = c1 * b - s1 * d, rd = s1 * b + c1 * d;
+            *a_pp = c2 * ra - s2 * rb; *a_pq = s2 * ra + c2 * rb;     // columns
+            *a_qp = c2 * rc - s2 * rd; *a_qq = s2 * rc + c2 * rd;
+          }
         } else {
-          const double x = A[i * lda + p], y = A[i * lda + q];
-          A[i * lda + p] = c * x - s * y;
-          A[i * lda + q] = s * x + c * y;
+          const int e = idx - nblk;
+          const int k = e / m, i = e - k * m;
+          const int p = sr[k] & 0xff, q = sr[k] >> 8;
+          const double c = cs[4 * k], s = cs[4 * k + 1];
+          const double vx = V[i * ldv + p], vy = V[i * ldv + q];
+          V[i * ldv + p] = c * vx - s * vy;
+          V[i * ldv + q] = s * vx + c * vy;
         }
-        const double vx = V[i * ldv + p], vy = V[i * ldv + q];
-        V[i * ldv + p] = c * vx - s * vy;
-        V[i * ldv + q] = s * vx + c * vy;
       }
       __syncthreads();
     }
@@ -135,15 +147,17 @@ __device__ __forceinline__ int ascending_rank(const double* A, int lda, int m, i
 // ---------------------------------------------------------------------------
 __global__ void loewdin_kernel(int n, const double* __restrict__ s_ao, double* __restrict__ x,
                                double* __restrict__ evals, double* __restrict__ evecs) {
-  extern __shared__ double sm[];
-  const int lda = n + 1;
-  double* A = sm;
-  double* V = A + n * lda;
+  extern __shared__ __align__(16) double sm[];
+  const int np = n + (n & 1);
+  const int lda = np + 1;
+  double* A = sm;                // [np][lda]
+  double* V = A + np * lda;      // [n][lda]
   double* w = V + n * lda;       // sorted eigenvalues
   double* f = w + n;             // s^-1/2 (0 if s <= 1e-15)
-  int* perm = reinterpret_cast<int*>(f + n);  // perm[rank] = original column
-  double* cs = reinterpret_cast<double*>(perm + n + (n & 1));
-  double* red = cs + 4 * (n / 2 + 1);
+  double* cs = f + n;
+  double* red = cs + 4 * (np / 2);
+  unsigned short* sched = reinterpret_cast<unsigned short*>(red + 18);
+  int* perm = reinterpret_cast<int*>(reinterpret_cast<char*>(cs) + jacobi_scratch_bytes(n));  // perm[rank] = column
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const double* S = s_ao + static_cast<int64_t>(b) * n * n;
   // symmetrise on load: numpy.linalg.eigh reads the lower triangle only
@@ -152,7 +166,7 @@ __global__ void loewdin_kernel(int n, const double* __restrict__ s_ao, double* _
     A[i * lda + j] = (i >= j) ? S[i * n + j] : S[j * n + i];
   }
   __syncthreads();
-  jacobi_eigh_smem(A, lda, V, lda, n, cs, red);
+  jacobi_eigh_smem(A, lda, V, lda, n, cs, red, sched);
   for (int i = tid; i < n; i += nt) {
     const int rk = ascending_rank(A, lda, n, i);
     const double wi = A[i * lda + i];
@@ -426,21 +440,35 @@ __global__ void cholesky_inverse_kernel(int N, const double* __restrict__ S, dou
   }
 }
 
-__global__ void geneig_kernel(int N, const double* __restrict__ H, const double* __restrict__ Linv,
-                              int nroots, double* __restrict__ E, double* __restrict__ C) {
-  extern __shared__ double sm[];
-  const int ld = N + 1;
-  double* A = sm;
-  double* V = A + N * ld;
+// packed_lower != 0: H holds the lower triangle only, [nbatch][N(N+1)/2] in
+// np.tril_indices order (the form the packed K5 GEMM writes).
+__global__ void geneig_kernel(int N, int packed_lower, const double* __restrict__ H,
+                              const double* __restrict__ Linv, int nroots, double* __restrict__ E,
+                              double* __restrict__ C) {
+  extern __shared__ __align__(16) double sm[];
+  const int Np = N + (N & 1);
+  const int ld = Np + 1;
+  double* A = sm;              // [Np][ld]
+  double* V = A + Np * ld;     // [N][ld]
   double* cs = V + N * ld;
-  double* red = cs + 4 * (N / 2 + 1);
-  int* perm = reinterpret_cast<int*>(red + 18);
+  double* red = cs + 4 * (Np / 2);
+  unsigned short* sched = reinterpret_cast<unsigned short*>(red + 18);
+  int* perm = reinterpret_cast<int*>(reinterpret_cast<char*>(cs) + jacobi_scratch_bytes(N));
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  const double* Hb = H + static_cast<int64_t>(b) * N * N;
   // A <- lower triangle of H, mirrored (scipy eigh(H, S) reads the lower triangle)
-  for (int k = tid; k < N * N; k += nt) {
-    const int i = k / N, j = k - i * N;
-    A[i * ld + j] = (i >= j) ? Hb[i * N + j] : Hb[j * N + i];
+  if (packed_lower) {
+    const double* Hb = H + static_cast<int64_t>(b) * (N * (N + 1) / 2);
+    for (int k = tid; k < N * N; k += nt) {
+      const int i = k / N, j = k - i * N;
+      const int hi = i > j ? i : j, lo = i > j ? j : i;
+      A[i * ld + j] = Hb[hi * (hi + 1) / 2 + lo];
+    }
+  } else {
+    const double* Hb = H + static_cast<int64_t>(b) * N * N;
+    for (int k = tid; k < N * N; k += nt) {
+      const int i = k / N, j = k - i * N;
+      A[i * ld + j] = (i >= j) ? Hb[i * N + j] : Hb[j * N + i];
+    }
   }
   __syncthreads();
   // V <- Linv * A
@@ -465,7 +493,7 @@ __global__ void geneig_kernel(int N, const double* __restrict__ H, const double*
     if (j > i) A[i * ld + j] = A[j * ld + i];
   }
   __syncthreads();
-  jacobi_eigh_smem(A, ld, V, ld, N, cs, red);
+  jacobi_eigh_smem(A, ld, V, ld, N, cs, red, sched);
   for (int i = tid; i < N; i += nt) perm[ascending_rank(A, ld, N, i)] = i;
   __syncthreads();
   for (int r = tid; r < nroots; r += nt) E[static_cast<int64_t>(b) * nroots + r] = A[perm[r] * ld + perm[r]];
@@ -479,12 +507,39 @@ __global__ void geneig_kernel(int N, const double* __restrict__ H, const double*
   }
 }
 
+size_t loewdin_smem_bytes(int n) {
+  const int np = n + (n & 1);
+  return (static_cast<size_t>(np + n) * (np + 1) + 2 * n) * sizeof(double) + jacobi_scratch_bytes(n) +
+         (n + 2) * sizeof(int);
+}
+
+size_t geneig_smem_bytes(int N) {
+  const int Np = N + (N & 1);
+  return static_cast<size_t>(Np + N) * (Np + 1) * sizeof(double) + jacobi_scratch_bytes(N) +
+         (N + 2) * sizeof(int);
+}
+
+int launch_geneig(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H, const double* Linv,
+                  int nroots, double* E, double* C) {
+  const size_t smem = geneig_smem_bytes(N);
+  EVC_CHECK_CUDA(cudaFuncSetAttribute(geneig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  geneig_kernel<<<nbatch, N <= 32 ? 128 : 256, smem, ctx->stream>>>(N, packed_lower, H, Linv, nroots, E, C);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace
 
 // exported to the other translation units
 int evc_launch_rot_pass(cudaStream_t st, int nbatch, int n, const double* in, const double* M,
                         int transpose_m, double* out) {
   return launch_rot_pass(st, nbatch, n, in, M, transpose_m, out);
+}
+
+int evc_launch_geneig(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H,
+                      const double* Linv, int nroots, double* E, double* C) {
+  return launch_geneig(ctx, nbatch, N, packed_lower, H, Linv, nroots, E, C);
 }
 
 extern "C" {
@@ -494,8 +549,7 @@ int evc_loewdin(evc_ctx* ctx, int nbatch, int n, const double* s_ao, double* x, 
   EVC_REQUIRE(ctx && s_ao && x && evals && evecs, "evc_loewdin: NULL argument");
   EVC_REQUIRE(n >= 1 && n <= 32, "evc_loewdin: n=%d unsupported (1..32)", n);
   if (nbatch <= 0) return 0;
-  const size_t smem = (2 * n * (n + 1) + 2 * n + 4 * (n / 2 + 1) + 18) * sizeof(double) +
-                      (n + 2) * sizeof(int);
+  const size_t smem = loewdin_smem_bytes(n);
   const int threads = n <= 16 ? 128 : 256;
   loewdin_kernel<<<nbatch, threads, smem, ctx->stream>>>(n, s_ao, x, evals, evecs);
   EVC_CHECK_LAUNCH();
@@ -561,13 +615,7 @@ int evc_geneig(evc_ctx* ctx, int nbatch, int N, const double* H, const double* L
   EVC_REQUIRE(N >= 1 && N <= 112, "evc_geneig: N=%d unsupported (1..112)", N);
   EVC_REQUIRE(nroots >= 1 && nroots <= N, "evc_geneig: nroots=%d out of range (1..%d)", nroots, N);
   if (nbatch <= 0) return 0;
-  const size_t smem = (2 * static_cast<size_t>(N) * (N + 1) + 4 * (N / 2 + 1) + 18) * sizeof(double) +
-                      (N + 2) * sizeof(int);
-  EVC_CHECK_CUDA(cudaFuncSetAttribute(geneig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-  geneig_kernel<<<nbatch, N <= 32 ? 128 : 256, smem, ctx->stream>>>(N, H, Linv, nroots, E, C);
-  EVC_CHECK_LAUNCH();
-  return 0;
+  return launch_geneig(ctx, nbatch, N, 0, H, Linv, nroots, E, C);
 }
 
 }  // extern "C"

@@ -322,7 +322,126 @@ int axpy_nsplit(int64_t L, int P, int G) {
   return static_cast<int>(s);
 }
 
+
+// out[g][k] = sum_{z < nz} part[z * sz + g * sg + k * sk]     (fixed order)
+__global__ void reduce_slabs_kernel(int64_t cols, int nz, int64_t sz, int64_t sg, int64_t sk,
+                                    const double* __restrict__ part, double* __restrict__ out) {
+  const int g = blockIdx.y;
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= cols) return;
+  const double* p = part + g * sg + k * sk;
+  double acc = 0.0;
+  for (int z = 0; z < nz; ++z) acc += p[z * sz];
+  out[static_cast<int64_t>(g) * cols + k] = acc;
+}
+
+constexpr int kRdBM = 128, kRdBN = 80;   // rows_dot GEMM tile (G x P)
+constexpr int kRaBM = 64, kRaBN = 128;   // rows_axpy GEMM tile (G x L)
+
+evc_gemm::Plan rows_dot_plan(int G, int P, int64_t L) {
+  const int tiles = ((G + kRdBM - 1) / kRdBM) * ((P + kRdBN - 1) / kRdBN);
+  return evc_gemm::plan_split(tiles, static_cast<int>(L), kPlanSms, 32);
+}
+
 }  // namespace
+
+// ---- generic row contractions over a row-major matrix rows[P][L] (L % 2 == 0) ----
+// rows_dot : out[g][p] = sum_l rows[p][l] * hv[g][l]      (hv: [G][L])
+// rows_axpy: out[g][l] = sum_p w[g][p] * rows[p][l]       (w: [G][P])
+// Small batches stream the rows once at HBM/L2 speed; larger ones run on the FP64
+// tensor cores (DMMA).  Used by the packed prediction step (packed.cu).
+size_t evc_rows_dot_ws_bytes(int64_t L, int P, int G) {
+  if (G > kGemvMaxBatch) {
+    const evc_gemm::Plan pl = rows_dot_plan(G, P, L);
+    return evc_align_up(static_cast<size_t>(pl.nsplit) * G * P * 8, 256);
+  }
+  const int64_t nchunk = (L + kChunk - 1) / kChunk;
+  return evc_align_up(static_cast<size_t>(G) * P * nchunk * 8, 256);
+}
+
+int evc_rows_dot(evc_ctx* ctx, const double* rows, int64_t L, int P, const double* hv, int G, double* out,
+                 void* workspace, size_t workspace_bytes) {
+  EVC_REQUIRE(L < (int64_t(1) << 31) && (L & 1) == 0, "rows_dot: bad row length %lld", (long long)L);
+  EVC_REQUIRE(workspace_bytes >= evc_rows_dot_ws_bytes(L, P, G), "rows_dot: workspace too small");
+  double* partial = static_cast<double*>(workspace);
+  if (G > kGemvMaxBatch) {
+    const evc_gemm::Plan pl = rows_dot_plan(G, P, L);
+    int rc = evc_gemm::launch<kRdBM, kRdBN, 4, 2, false>(ctx->stream, G, P, static_cast<int>(L), pl, hv, L, rows, L,
+                                                          partial, P, static_cast<int64_t>(G) * P);
+    if (rc) return rc;
+    dim3 grid((P + 127) / 128, G);
+    reduce_slabs_kernel<<<grid, 128, 0, ctx->stream>>>(P, pl.nsplit, static_cast<int64_t>(G) * P, P, 1, partial, out);
+    EVC_CHECK_LAUNCH();
+    return 0;
+  }
+  const int nchunk = static_cast<int>((L + kChunk - 1) / kChunk);
+  const int gb = stream_gb(G), rb = stream_rb(gb);
+  dim3 grid((P + rb - 1) / rb, nchunk, (G + gb - 1) / gb);
+  EVC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "rows_dot: batch/stack too large for one launch");
+  const bool vec2 = ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) && ((reinterpret_cast<uintptr_t>(hv) & 15) == 0);
+#define EVC_DOT(RB, GB)                                                                                  \
+  do {                                                                                                   \
+    if (vec2) stack_dot_kernel<RB, GB, true><<<grid, 256, 0, ctx->stream>>>(rows, L, P, hv, G, nchunk, partial); \
+    else stack_dot_kernel<RB, GB, false><<<grid, 256, 0, ctx->stream>>>(rows, L, P, hv, G, nchunk, partial);     \
+  } while (0)
+  switch (gb) {
+    case 1: EVC_DOT(8, 1); break;
+    case 2: EVC_DOT(8, 2); break;
+    case 4: EVC_DOT(4, 4); break;
+    default: EVC_DOT(4, 8); break;
+  }
+#undef EVC_DOT
+  EVC_CHECK_LAUNCH();
+  {
+    dim3 g2((P + 127) / 128, G);
+    reduce_slabs_kernel<<<g2, 128, 0, ctx->stream>>>(P, nchunk, 1, static_cast<int64_t>(P) * nchunk, nchunk, partial, out);
+    EVC_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+size_t evc_rows_axpy_ws_bytes(int64_t L, int P, int G) {
+  if (G > kGemvMaxBatch) return 256;
+  return evc_align_up(static_cast<size_t>(axpy_nsplit(L, P, G)) * G * L * 8, 256);
+}
+
+int evc_rows_axpy(evc_ctx* ctx, const double* rows, int64_t L, int P, const double* w, int G, double* out,
+                  void* workspace, size_t workspace_bytes) {
+  EVC_REQUIRE(L < (int64_t(1) << 31) && (L & 1) == 0, "rows_axpy: bad row length %lld", (long long)L);
+  EVC_REQUIRE(workspace_bytes >= evc_rows_axpy_ws_bytes(L, P, G), "rows_axpy: workspace too small");
+  if (G > kGemvMaxBatch) {
+    evc_gemm::Plan pl;
+    pl.nsplit = 1;
+    pl.kchunk = (P + evc_gemm::BK - 1) / evc_gemm::BK * evc_gemm::BK;
+    return evc_gemm::launch<kRaBM, kRaBN, 2, 4, true>(ctx->stream, G, static_cast<int>(L), P, pl, w, P, rows, L, out, L, 0);
+  }
+  double* part = static_cast<double*>(workspace);
+  const int nsplit = axpy_nsplit(L, P, G);
+  const bool vec2 = (reinterpret_cast<uintptr_t>(rows) & 15) == 0;
+  const int64_t per_block = vec2 ? 512 : 256;
+  const int gb = stream_gb(G);
+  dim3 grid(static_cast<unsigned>((L + per_block - 1) / per_block), nsplit, (G + gb - 1) / gb);
+  EVC_REQUIRE(grid.z <= 65535, "rows_axpy: batch too large for one launch");
+#define EVC_AXPY(GB)                                                                                  \
+  do {                                                                                                \
+    if (vec2) stack_axpy_kernel<GB, true><<<grid, 256, 0, ctx->stream>>>(rows, L, P, w, G, nsplit, part); \
+    else stack_axpy_kernel<GB, false><<<grid, 256, 0, ctx->stream>>>(rows, L, P, w, G, nsplit, part);     \
+  } while (0)
+  switch (gb) {
+    case 1: EVC_AXPY(1); break;
+    case 2: EVC_AXPY(2); break;
+    case 4: EVC_AXPY(4); break;
+    default: EVC_AXPY(8); break;
+  }
+#undef EVC_AXPY
+  EVC_CHECK_LAUNCH();
+  {
+    dim3 g2(static_cast<unsigned>((L + 255) / 256), G);
+    reduce_slabs_kernel<<<g2, 256, 0, ctx->stream>>>(L, nsplit, static_cast<int64_t>(G) * L, L, 1, part, out);
+    EVC_CHECK_LAUNCH();
+  }
+  return 0;
+}
 
 extern "C" {
 
