@@ -84,6 +84,21 @@ SIGNATURES = {
                                             c_double_p, c_double_p, c_double_p, C.c_int,
                                             C.POINTER(AoBundle), C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_void_p, C.c_size_t]),
+    "evc_packed_row_len": (c_i64, [C.c_int]),
+    "evc_stack_pack8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
+                                  c_double_p, c_double_p]),
+    "evc_energy_with_grad_packed_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int,
+                                                              c_sz_p]),
+    "evc_energy_with_grad_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p,
+                                              c_double_p, c_double_p, C.c_int, C.POINTER(AoBundle),
+                                              c_double_p, c_double_p, c_double_p, C.c_void_p,
+                                              C.c_size_t]),
+    "evc_energy_with_grad_packed_host_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int,
+                                                                   C.c_int, c_sz_p]),
+    "evc_energy_with_grad_packed_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                   c_double_p, c_double_p, c_double_p, C.c_int,
+                                                   C.POINTER(AoBundle), C.c_void_p, C.c_void_p,
+                                                   C.c_int, C.c_void_p, C.c_size_t]),
 }
 
 _lib = None

@@ -55,11 +55,17 @@ int evc_rows_axpy(evc_ctx* ctx, const double* rows, int64_t L, int P, const doub
 // packed (8-fold symmetric) prediction step pieces, packed.cu
 constexpr int kPackedMaxNorb = 13;  // per-geometry shared-memory kernels up to this many orbitals
 int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
-                      const double* eri, double* hvec);
+                      const double* eri, double* hvec, double* Tout);
 int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices, const double* x,
-                    const double* evals, const double* evecs, const double* hcore, const double* eri,
+                    const double* evals, const double* evecs, const double* hcore, const double* Tin,
                     const double* out7, const double* ipovlp, const double* hcore_deriv,
                     const double* eri_ip1, const double* grad_nuc, double* grad);
+// K8 on full (n^4) arrays with the nuclear gradient added (grad.cu)
+int evc_grad_elec_full(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices,
+                       const double* evals, const double* evecs, const double* x, const double* hcore,
+                       const double* t3, const double* gamma, const double* Gamma, const double* ipovlp,
+                       const double* hcore_deriv, const double* eri_ip1, const double* grad_nuc,
+                       double* grad, void* workspace, size_t workspace_bytes);
 int evc_packed_hvec_from_full(evc_ctx* ctx, int nbatch, int n, const double* h1, const double* h2, double* hvec);
 int evc_packed_unpack_rdms(evc_ctx* ctx, int nbatch, int n, const double* out7, double* gamma, double* Gamma8);
 int evc_packed_pair_weights(evc_ctx* ctx, int nbatch, int N, const double* C, int64_t c_stride, double* w);

@@ -20,9 +20,6 @@
 // (derivation and the numpy cross-check against the reference: DESIGN.md).
 #include "common.cuh"
 
-int evc_launch_rot_pass(cudaStream_t st, int nbatch, int n, const double* in, const double* M,
-                        int transpose_m, double* out);
-
 namespace {
 
 __device__ __forceinline__ double block_reduce_sum(double v, double* scratch) {
@@ -279,6 +276,15 @@ size_t grad_ws_bytes(int n, int natm, int nbatch) {
 }
 
 }  // namespace
+
+int evc_grad_elec_full(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices,
+                       const double* evals, const double* evecs, const double* x, const double* hcore,
+                       const double* t3, const double* gamma, const double* Gamma, const double* ipovlp,
+                       const double* hcore_deriv, const double* eri_ip1, const double* grad_nuc,
+                       double* grad, void* workspace, size_t workspace_bytes) {
+  return grad_elec_impl(ctx, nbatch, n, natm, aoslices, evals, evecs, x, hcore, t3, gamma, Gamma, ipovlp,
+                        hcore_deriv, eri_ip1, grad_nuc, grad, workspace, workspace_bytes);
+}
 
 extern "C" {
 

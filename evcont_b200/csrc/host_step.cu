@@ -77,23 +77,19 @@ int evc_energy_with_grad_host_workspace_bytes(int layout, int N, int n, int natm
   return 0;
 }
 
-int evc_energy_with_grad_host(evc_ctx* ctx, int layout, int N, int n, int natm, const double* one_rdm,
-                              const double* two_rdm, const double* Linv, int nbatch,
-                              const evc_ao_bundle* ao_host, double* E_host, double* grad_host, int chunk,
-                              void* workspace, size_t workspace_bytes) {
-  EVC_REQUIRE(ctx && one_rdm && two_rdm && Linv && ao_host && E_host && grad_host && workspace,
-              "evc_energy_with_grad_host: NULL argument");
-  EVC_REQUIRE(ao_host->ovlp && ao_host->hcore && ao_host->eri && ao_host->ipovlp && ao_host->hcore_deriv &&
-                  ao_host->eri_ip1 && ao_host->aoslices,
-              "evc_energy_with_grad_host: incomplete AO bundle");
-  EVC_REQUIRE(chunk >= 1, "evc_energy_with_grad_host: chunk must be >= 1");
-  if (nbatch <= 0) return 0;
-  if (chunk > nbatch) chunk = nbatch;
+}  // extern "C"
+
+namespace {
+
+// step(dev bundle, count, E, grad, step workspace) enqueues the prediction step of
+// one chunk on the ctx stream
+template <typename Step>
+int host_pipeline(evc_ctx* ctx, int n, int natm, int nbatch, const evc_ao_bundle* ao_host, double* E_host,
+                  double* grad_host, int chunk, size_t step_b, void* workspace, size_t workspace_bytes,
+                  Step step) {
   int rc = ensure_pipeline(ctx);
   if (rc) return rc;
   const AoSizes sz = ao_sizes(n, natm);
-  size_t step_b = 0;
-  if ((rc = evc_energy_with_grad_workspace_bytes(layout, N, n, natm, chunk, &step_b))) return rc;
   evc_arena ar(workspace, workspace_bytes);
   char* step_ws = ar.take<char>(step_b);
   int32_t* aosl = ar.take<int32_t>(static_cast<size_t>(natm) * 2);
@@ -138,9 +134,7 @@ int evc_energy_with_grad_host(evc_ctx* ctx, int layout, int N, int n, int natm, 
     dev.e_nuc = ao_host->e_nuc ? s.e_nuc : nullptr;
     dev.grad_nuc = ao_host->grad_nuc ? s.grad_nuc : nullptr;
     dev.aoslices = aosl;
-    if ((rc = evc_energy_with_grad(ctx, layout, N, n, natm, one_rdm, two_rdm, Linv, static_cast<int>(cnt), &dev,
-                                   s.E, s.grad, nullptr, nullptr, nullptr, step_ws, step_b)))
-      return rc;
+    if ((rc = step(&dev, static_cast<int>(cnt), s.E, s.grad, step_ws))) return rc;
     EVC_CHECK_CUDA(cudaEventRecord(ctx->ev_compute[k], cs));
     EVC_CHECK_CUDA(cudaStreamWaitEvent(ds, ctx->ev_compute[k], 0));
     EVC_CHECK_CUDA(cudaMemcpyAsync(E_host + g0, s.E, cnt * sizeof(double), cudaMemcpyDeviceToHost, ds));
@@ -152,6 +146,64 @@ int evc_energy_with_grad_host(evc_ctx* ctx, int layout, int N, int n, int natm, 
   EVC_CHECK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_d2h[0], 0));
   if (nchunk > 1) EVC_CHECK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_d2h[1], 0));
   return 0;
+}
+
+bool host_bundle_ok(const evc_ao_bundle* a) {
+  return a->ovlp && a->hcore && a->eri && a->ipovlp && a->hcore_deriv && a->eri_ip1 && a->aoslices;
+}
+
+}  // namespace
+
+extern "C" {
+
+int evc_energy_with_grad_host(evc_ctx* ctx, int layout, int N, int n, int natm, const double* one_rdm,
+                              const double* two_rdm, const double* Linv, int nbatch,
+                              const evc_ao_bundle* ao_host, double* E_host, double* grad_host, int chunk,
+                              void* workspace, size_t workspace_bytes) {
+  EVC_REQUIRE(ctx && one_rdm && two_rdm && Linv && ao_host && E_host && grad_host && workspace,
+              "evc_energy_with_grad_host: NULL argument");
+  EVC_REQUIRE(host_bundle_ok(ao_host), "evc_energy_with_grad_host: incomplete AO bundle");
+  EVC_REQUIRE(chunk >= 1, "evc_energy_with_grad_host: chunk must be >= 1");
+  if (nbatch <= 0) return 0;
+  if (chunk > nbatch) chunk = nbatch;
+  size_t step_b = 0;
+  int rc = evc_energy_with_grad_workspace_bytes(layout, N, n, natm, chunk, &step_b);
+  if (rc) return rc;
+  return host_pipeline(ctx, n, natm, nbatch, ao_host, E_host, grad_host, chunk, step_b, workspace, workspace_bytes,
+                       [&](const evc_ao_bundle* dev, int cnt, double* E, double* grad, void* ws) {
+                         return evc_energy_with_grad(ctx, layout, N, n, natm, one_rdm, two_rdm, Linv, cnt, dev, E,
+                                                     grad, nullptr, nullptr, nullptr, ws, step_b);
+                       });
+}
+
+int evc_energy_with_grad_packed_host_workspace_bytes(int N, int n, int natm, int chunk, size_t* bytes) {
+  EVC_REQUIRE(bytes != nullptr && chunk >= 1, "evc_energy_with_grad_packed_host_workspace_bytes: bad arguments");
+  size_t step = 0;
+  int rc = evc_energy_with_grad_packed_workspace_bytes(N, n, natm, chunk, &step);
+  if (rc) return rc;
+  *bytes = evc_align_up(step, 256) + 2 * slot_bytes(ao_sizes(n, natm), chunk, natm) +
+           evc_align_up(static_cast<size_t>(natm) * 2 * sizeof(int32_t), 256);
+  return 0;
+}
+
+int evc_energy_with_grad_packed_host(evc_ctx* ctx, int N, int n, int natm, const double* RH, const double* RG,
+                                     const double* Linv, int nbatch, const evc_ao_bundle* ao_host,
+                                     double* E_host, double* grad_host, int chunk, void* workspace,
+                                     size_t workspace_bytes) {
+  EVC_REQUIRE(ctx && RH && RG && Linv && ao_host && E_host && grad_host && workspace,
+              "evc_energy_with_grad_packed_host: NULL argument");
+  EVC_REQUIRE(host_bundle_ok(ao_host), "evc_energy_with_grad_packed_host: incomplete AO bundle");
+  EVC_REQUIRE(chunk >= 1, "evc_energy_with_grad_packed_host: chunk must be >= 1");
+  if (nbatch <= 0) return 0;
+  if (chunk > nbatch) chunk = nbatch;
+  size_t step_b = 0;
+  int rc = evc_energy_with_grad_packed_workspace_bytes(N, n, natm, chunk, &step_b);
+  if (rc) return rc;
+  return host_pipeline(ctx, n, natm, nbatch, ao_host, E_host, grad_host, chunk, step_b, workspace, workspace_bytes,
+                       [&](const evc_ao_bundle* dev, int cnt, double* E, double* grad, void* ws) {
+                         return evc_energy_with_grad_packed(ctx, N, n, natm, RH, RG, Linv, cnt, dev, E, grad,
+                                                            nullptr, ws, step_b);
+                       });
 }
 
 }  // extern "C"

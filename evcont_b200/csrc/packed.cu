@@ -1,0 +1,814 @@
+// Packed prediction step: the same arithmetic as K4/K5/K7/K8 (dense.cu, stack.cu,
+// grad.cu), restated on the 8-fold permutational symmetry of the AO two-electron
+// integrals, (ij|kl) = (ji|kl) = (ij|lk) = (kl|ij), which libcint / PySCF
+// integrals always have (evcont/ab_initio_gradients_loewdin.py:283-284, 338-339).
+//
+// Every contraction of the stack with h2, and every use of the predicted two-body
+// RDM in the gradient, only sees the part of the RDM that is totally symmetric
+// under that 8-element group.  So the stack is packed ONCE into rows
+//
+//   R[p][0 : n^2]             = one_rdm block           (full, no symmetry assumed)
+//   R[p][n^2 + tri(I, K)]     = 1/2 * sum_{distinct (i'j'k'l') in orbit(ijkl)} two_rdm[i'j'k'l']
+//                               I = pair(i >= j), K = pair(k >= l), I >= K
+//
+// for the N(N+1)/2 state pairs a >= b (the eigensolver reads the lower triangle of
+// H only, evcont/ab_initio_eigenvector_continuation.py:75).  Row length
+// L8 = n^2 + np(np+1)/2, np = n(n+1)/2: 1640 doubles instead of 10100 at n = 10, and
+// 210 rows instead of 400 at N = 20 -- 12x fewer bytes and flops in K5 and K7.
+//
+//   K4p  per geometry: ERIp (np x np) -> T = ERIp Q -> h2p = Q^T T,  Q = pair transform
+//        built from X; two DMMA GEMMs in shared memory.   hvec = [h1 | tril(h2p)]
+//   K5p  Hp[g][p]   = hvec[g] . RH[p]            (rows_dot: DMMA GEMM / streaming)
+//   K7p  out7[g][:] = sum_p w[g][p] RG[p][:]     (rows_axpy), w = tril weights of c (x) c
+//   K8p  per geometry: U0 = T Gm, Y from U0; W = P0 Gm P0^T (three DMMA GEMMs in shared
+//        memory); streams int2e_ip1 once against W; one-electron adjoint as in grad.cu.
+//
+// Algebra (derivation and numpy check: DESIGN.md section 4, tools/packed_proto.py):
+//   P0[AB, I] = X_ai X_bj + X_aj X_bi,  Q = diag(1/s_AB) P0,  s = 2 on diagonal pairs
+//   Gm[I, K]  = out7[tri(I,K)] * (I == K ? 2 : 1)   (symmetric np x np)
+//   Y[a, i]   = 2 sum_{b j} X_bj s_(ij) U0[(ab), (ij)]
+//   -1/2 sum_{m in A} sum_{bcd} (d_x m b|c d) W[(mb), (cd)]   is the ERI-derivative term.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kNJ = 4;  // 8x8 output tiles per warp work item (A fragment re-used kNJ times)
+
+__host__ __device__ inline int tri_idx(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+__host__ __device__ inline int npair_of(int n) { return n * (n + 1) / 2; }
+__host__ __device__ inline int64_t packed_len(int n) {
+  const int64_t np = npair_of(n);
+  const int64_t l = static_cast<int64_t>(n) * n + np * (np + 1) / 2;
+  return (l + 1) & ~static_cast<int64_t>(1);
+}
+
+__device__ __forceinline__ void tril_unrank_i(int t, int& a, int& b) {
+  int x = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
+  while (x * (x + 1) / 2 > t) --x;
+  while ((x + 1) * (x + 2) / 2 <= t) ++x;
+  a = x;
+  b = t - x * (x + 1) / 2;
+}
+
+// ---------------------------------------------------------------------------
+// stack packing (once per stack)
+// ---------------------------------------------------------------------------
+struct StackView {
+  const double* two;
+  int layout, N, n;
+  int64_t n4, Lc;
+  __device__ bool has_block(int a, int b) const {
+    return (layout == EVC_LAYOUT_FULL || layout == EVC_LAYOUT_FULL_EXCH) || a >= b;
+  }
+  __device__ double at(int a, int b, int i, int j, int k, int l) const {
+    const bool tril = (layout == EVC_LAYOUT_TRIL || layout == EVC_LAYOUT_TRIL_EXCH);
+    const bool exch = (layout == EVC_LAYOUT_FULL_EXCH || layout == EVC_LAYOUT_TRIL_EXCH);
+    const int64_t blk = tril ? tri_idx(a, b) : static_cast<int64_t>(a) * N + b;
+    const int64_t x = i * n + j, y = k * n + l;
+    if (exch) {
+      const int64_t hi = x > y ? x : y, lo = x > y ? y : x;
+      return two[blk * Lc + hi * (hi + 1) / 2 + lo];
+    }
+    return two[blk * n4 + x * (static_cast<int64_t>(n) * n) + y];
+  }
+  __device__ double orbit_sum(int a, int b, int i, int j, int k, int l, bool same_pair) const {
+    double s = at(a, b, i, j, k, l);
+    if (i != j) s += at(a, b, j, i, k, l);
+    if (k != l) s += at(a, b, i, j, l, k);
+    if (i != j && k != l) s += at(a, b, j, i, l, k);
+    if (!same_pair) {
+      s += at(a, b, k, l, i, j);
+      if (k != l) s += at(a, b, l, k, i, j);
+      if (i != j) s += at(a, b, k, l, j, i);
+      if (i != j && k != l) s += at(a, b, l, k, j, i);
+    }
+    return s;
+  }
+};
+
+__global__ void pack8_stack_kernel(StackView sv, int64_t L8, const double* __restrict__ one_rdm,
+                                   double* __restrict__ RH, double* __restrict__ RG) {
+  const int p = blockIdx.y;
+  const int64_t col = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (col >= L8) return;
+  int a, b;
+  tril_unrank_i(p, a, b);
+  const int n = sv.n, N = sv.N, n2 = n * n, np = npair_of(n);
+  double vh = 0.0, vg = 0.0;
+  if (col < n2) {
+    vh = one_rdm[(static_cast<int64_t>(a) * N + b) * n2 + col];
+    vg = (a == b) ? vh : 0.5 * (vh + one_rdm[(static_cast<int64_t>(b) * N + a) * n2 + col]);
+  } else if (col - n2 < static_cast<int64_t>(np) * (np + 1) / 2) {
+    int I, K, i, j, k, l;
+    tril_unrank_i(static_cast<int>(col - n2), I, K);
+    tril_unrank_i(I, i, j);
+    tril_unrank_i(K, k, l);
+    vh = 0.5 * sv.orbit_sum(a, b, i, j, k, l, I == K);
+    vg = vh;
+    if (a != b && sv.has_block(b, a)) vg = 0.5 * (vh + 0.5 * sv.orbit_sum(b, a, i, j, k, l, I == K));
+  }
+  RH[static_cast<int64_t>(p) * L8 + col] = vh;
+  RG[static_cast<int64_t>(p) * L8 + col] = vg;
+}
+
+// hvec[g] = [h1 | tril(h2 pairs)] from the full OAO integrals (n > kPackedMaxNorb path)
+__global__ void hvec_from_full_kernel(int n, int64_t L8, const double* __restrict__ h1,
+                                      const double* __restrict__ h2, double* __restrict__ hvec) {
+  const int g = blockIdx.y;
+  const int64_t col = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (col >= L8) return;
+  const int n2 = n * n, np = npair_of(n);
+  const int64_t n4 = static_cast<int64_t>(n2) * n2;
+  double v = 0.0;
+  if (col < n2) {
+    v = h1[static_cast<int64_t>(g) * n2 + col];
+  } else if (col - n2 < static_cast<int64_t>(np) * (np + 1) / 2) {
+    int I, K, i, j, k, l;
+    tril_unrank_i(static_cast<int>(col - n2), I, K);
+    tril_unrank_i(I, i, j);
+    tril_unrank_i(K, k, l);
+    v = h2[static_cast<int64_t>(g) * n4 + (static_cast<int64_t>(i) * n + j) * n2 + k * n + l];
+  }
+  hvec[static_cast<int64_t>(g) * L8 + col] = v;
+}
+
+// gamma = out7[0:n^2]; Gamma8[ijkl] = s_I s_K s_IK out7[tri(I,K)] / 4: the totally
+// symmetric part of the predicted two-body RDM (all the gradient sees)
+__global__ void unpack_rdms_kernel(int n, int64_t L8, const double* __restrict__ out7,
+                                   double* __restrict__ gamma, double* __restrict__ Gamma8) {
+  const int g = blockIdx.y;
+  const int64_t k4 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n2 = n * n;
+  const int64_t n4 = static_cast<int64_t>(n2) * n2;
+  if (k4 >= n4) return;
+  const double* o = out7 + static_cast<int64_t>(g) * L8;
+  if (k4 < n2) gamma[static_cast<int64_t>(g) * n2 + k4] = o[k4];
+  const int l = static_cast<int>(k4 % n), k = static_cast<int>((k4 / n) % n);
+  const int j = static_cast<int>((k4 / n2) % n), i = static_cast<int>(k4 / (static_cast<int64_t>(n2) * n));
+  const int I = i >= j ? tri_idx(i, j) : tri_idx(j, i);
+  const int K = k >= l ? tri_idx(k, l) : tri_idx(l, k);
+  const int hi = I > K ? I : K, lo = I > K ? K : I;
+  const double s = (i == j ? 2.0 : 1.0) * (k == l ? 2.0 : 1.0) * (I == K ? 2.0 : 1.0);
+  Gamma8[static_cast<int64_t>(g) * n4 + k4] = 0.25 * s * o[n2 + tri_idx(hi, lo)];
+}
+
+// w[g][p] = c_a^2 (a == b), 2 c_a c_b (a > b)      (ab_initio_gradients_loewdin.py:345-353)
+__global__ void tril_weights_kernel(int N, int P, const double* __restrict__ C, int64_t c_stride,
+                                    double* __restrict__ w) {
+  const int g = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double* c = C + static_cast<int64_t>(g) * c_stride;
+  int a, b;
+  tril_unrank_i(p, a, b);
+  w[static_cast<int64_t>(g) * P + p] = (a == b) ? c[a] * c[a] : 2.0 * c[a] * c[b];
+}
+
+// ---------------------------------------------------------------------------
+// shared-memory geometry of the per-geometry kernels
+// ---------------------------------------------------------------------------
+struct PGeom {
+  int n, np, M8, rows8, K4, pA, pB;
+  size_t szA;  // doubles of an A-type image  [rows8][pA]
+  size_t szB;  // doubles of a B-type image   [K4][pB]
+};
+
+__host__ __device__ inline PGeom pgeom(int n) {
+  PGeom g;
+  g.n = n;
+  g.np = npair_of(n);
+  g.M8 = (g.np + 7) / 8;
+  g.rows8 = g.M8 * 8;
+  g.K4 = (g.np + 3) & ~3;
+  // A-type access (lane (g,tg) reads [row g][col tg]): pitch == 4 (mod 8) is conflict-free;
+  // B-type access ([row tg][col g]): pitch == 8 (mod 16).
+  int pa = g.K4;
+  while ((pa & 7) != 4) ++pa;
+  int pb = g.rows8;
+  while ((pb & 15) != 8) ++pb;
+  g.pA = pa;
+  g.pB = pb;
+  g.szA = static_cast<size_t>(g.rows8) * pa;
+  g.szB = static_cast<size_t>(g.K4) * pb;
+  return g;
+}
+
+// accumulate C(M8*8 x N8*8) = A * B on the FP64 tensor cores; work item = (row tile,
+// group of kNJ column tiles), item `warp + kWarps*r` -> acc[r].
+template <int MAXI, typename LA, typename LB>
+__device__ __forceinline__ void gemm_acc(double (&acc)[MAXI][kNJ][2], int M8, int N8, int K4, bool lower,
+                                         LA la, LB lb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int NG = (N8 + kNJ - 1) / kNJ;
+  const int nitems = M8 * NG;
+#pragma unroll
+  for (int r = 0; r < MAXI; ++r) {
+#pragma unroll
+    for (int j = 0; j < kNJ; ++j) acc[r][j][0] = acc[r][j][1] = 0.0;
+    const int it = warp + kWarps * r;
+    if (it >= nitems) continue;
+    const int mt = it / NG, nt0 = (it - mt * NG) * kNJ;
+    int ntend = min(N8, nt0 + kNJ);
+    if (lower) ntend = min(ntend, mt + 1);
+    if (nt0 >= ntend) continue;
+    for (int k0 = 0; k0 < K4; k0 += 4) {
+      const double a = la(mt * 8 + g, k0 + tg);
+#pragma unroll
+      for (int j = 0; j < kNJ; ++j) {
+        if (nt0 + j < ntend) {
+          const double b = lb(k0 + tg, (nt0 + j) * 8 + g);
+          dmma8x8x4(acc[r][j][0], acc[r][j][1], a, b);
+        }
+      }
+    }
+  }
+}
+
+// st(row, col, v0, v1): accumulator pair for (row, col) and (row, col + 1)
+template <int MAXI, typename ST>
+__device__ __forceinline__ void gemm_store(const double (&acc)[MAXI][kNJ][2], int M8, int N8, bool lower, ST st) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int NG = (N8 + kNJ - 1) / kNJ;
+  const int nitems = M8 * NG;
+#pragma unroll
+  for (int r = 0; r < MAXI; ++r) {
+    const int it = warp + kWarps * r;
+    if (it >= nitems) continue;
+    const int mt = it / NG, nt0 = (it - mt * NG) * kNJ;
+    int ntend = min(N8, nt0 + kNJ);
+    if (lower) ntend = min(ntend, mt + 1);
+#pragma unroll
+    for (int j = 0; j < kNJ; ++j)
+      if (nt0 + j < ntend) st(mt * 8 + g, (nt0 + j) * 8 + tg * 2, acc[r][j][0], acc[r][j][1]);
+  }
+}
+
+// pair tables: pij[I] = i | j << 8 ; pidx[i*n + j] = pair index of (i, j)
+__device__ __forceinline__ void build_pair_tables(int n, unsigned short* pij, unsigned short* pidx) {
+  for (int k = threadIdx.x; k < n * n; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    const int I = i >= j ? tri_idx(i, j) : tri_idx(j, i);
+    pidx[k] = static_cast<unsigned short>(I);
+    if (i >= j) pij[I] = static_cast<unsigned short>(i | (j << 8));
+  }
+}
+
+__host__ __device__ inline size_t table_bytes(int n) {
+  return ((static_cast<size_t>(npair_of(n)) + n * n) * sizeof(unsigned short) + 15) / 16 * 16;
+}
+
+// ---------------------------------------------------------------------------
+// K4p: one CTA per geometry
+// ---------------------------------------------------------------------------
+template <int MAXI>
+__global__ void __launch_bounds__(kThreads)
+packed_ao2oao_kernel(int n, int64_t L8, const double* __restrict__ x, const double* __restrict__ hcore,
+                     const double* __restrict__ eri, double* __restrict__ hvec, double* __restrict__ Tout) {
+  extern __shared__ __align__(16) double sm[];
+  const PGeom pg = pgeom(n);
+  const int np = pg.np, pA = pg.pA, pB = pg.pB, ld = n + 1, n2 = n * n;
+  const size_t szE = pg.szA > pg.szB ? pg.szA : pg.szB;
+  double* Eb = sm;                 // ERIp, A-type [rows8][pA]; later T, B-type [K4][pB]
+  double* Qb = Eb + szE;           // Q, B-type [K4][pB]
+  double* Xs = Qb + pg.szB;        // [n][ld]
+  double* Hs = Xs + n * ld;
+  double* Ts = Hs + n * ld;
+  unsigned short* pij = reinterpret_cast<unsigned short*>(Ts + n * ld);
+  unsigned short* pidx = pij + np;
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const int64_t o2 = static_cast<int64_t>(g) * n2;
+  const double* eg = eri + static_cast<int64_t>(g) * n2 * n2;
+
+  build_pair_tables(n, pij, pidx);
+  for (int k = tid; k < n2; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    Xs[i * ld + j] = x[o2 + k];
+    Hs[i * ld + j] = hcore[o2 + k];
+  }
+  for (int k = tid; k < static_cast<int>(szE); k += kThreads) Eb[k] = 0.0;
+  for (int k = tid; k < static_cast<int>(pg.szB); k += kThreads) Qb[k] = 0.0;
+  __syncthreads();
+  // ERIp[AB][CD] = (ab|cd), a >= b, c >= d: rows of the full tensor read contiguously
+  for (int k = tid; k < np * n2; k += kThreads) {
+    const int AB = k / n2, y = k - AB * n2;
+    const int c = y / n, d = y - c * n;
+    if (c < d) continue;
+    const int a = pij[AB] & 0xff, b = pij[AB] >> 8;
+    Eb[AB * pA + pidx[y]] = eg[static_cast<int64_t>(a * n + b) * n2 + y];
+  }
+  // Q[CD][K] = (X_ck X_dl + X_dk X_cl) / s_CD
+  for (int k = tid; k < np * np; k += kThreads) {
+    const int CD = k / np, K = k - CD * np;
+    const int c = pij[CD] & 0xff, d = pij[CD] >> 8, kk = pij[K] & 0xff, l = pij[K] >> 8;
+    const double v = Xs[c * ld + kk] * Xs[d * ld + l] + Xs[d * ld + kk] * Xs[c * ld + l];
+    Qb[CD * pB + K] = (c == d) ? 0.5 * v : v;
+  }
+  // h1 = X^T (hcore X)
+  for (int k = tid; k < n2; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    double acc = 0.0;
+    for (int r = 0; r < n; ++r) acc += Hs[i * ld + r] * Xs[r * ld + j];
+    Ts[i * ld + j] = acc;
+  }
+  __syncthreads();
+  double* hv = hvec + static_cast<int64_t>(g) * L8;
+  for (int k = tid; k < n2; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    double acc = 0.0;
+    for (int r = 0; r < n; ++r) acc += Xs[r * ld + i] * Ts[r * ld + j];
+    hv[k] = acc;
+  }
+  for (int64_t k = n2 + static_cast<int64_t>(np) * (np + 1) / 2 + tid; k < L8; k += kThreads) hv[k] = 0.0;
+
+  double acc[MAXI][kNJ][2];
+  // T = ERIp Q
+  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
+                 [&](int m, int k) { return Eb[m * pA + k]; },
+                 [&](int k, int c) { return Qb[k * pB + c]; });
+  __syncthreads();  // every warp is done reading ERIp: T may overwrite it
+  double* Tg = Tout + static_cast<int64_t>(g) * np * np;
+  gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+    if (m < pg.K4) {
+      Eb[m * pB + c] = v0;
+      Eb[m * pB + c + 1] = v1;
+    }
+    if (m < np) {
+      if (c < np) Tg[m * np + c] = v0;
+      if (c + 1 < np) Tg[m * np + c + 1] = v1;
+    }
+  });
+  __syncthreads();
+  // h2p = Q^T T, lower triangle only
+  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, true,
+                 [&](int m, int k) { return Qb[k * pB + m]; },
+                 [&](int k, int c) { return Eb[k * pB + c]; });
+  gemm_store<MAXI>(acc, pg.M8, pg.M8, true, [&](int m, int c, double v0, double v1) {
+    if (m < np) {
+      if (c <= m) hv[n2 + tri_idx(m, c)] = v0;
+      if (c + 1 <= m) hv[n2 + tri_idx(m, c + 1)] = v1;
+    }
+  });
+}
+
+size_t ao2oao_smem_bytes(int n) {
+  const PGeom pg = pgeom(n);
+  return ((pg.szA > pg.szB ? pg.szA : pg.szB) + pg.szB + 3 * static_cast<size_t>(n) * (n + 1)) * sizeof(double) +
+         table_bytes(n);
+}
+
+// ---------------------------------------------------------------------------
+// K8p: one CTA per geometry
+// ---------------------------------------------------------------------------
+constexpr int kIpSeg = 4;  // int2e_ip1 rows are cut into this many segments per warp item
+
+template <int MAXI>
+__global__ void __launch_bounds__(kThreads)
+packed_grad_kernel(int n, int natm, int64_t L8, const int32_t* __restrict__ aoslices,
+                   const double* __restrict__ x, const double* __restrict__ evals,
+                   const double* __restrict__ evecs, const double* __restrict__ hcore,
+                   const double* __restrict__ Tin, const double* __restrict__ out7,
+                   const double* __restrict__ ipovlp, const double* __restrict__ hcore_deriv,
+                   const double* __restrict__ eri_ip1, const double* __restrict__ grad_nuc,
+                   double* __restrict__ grad) {
+  extern __shared__ __align__(16) double sm[];
+  const PGeom pg = pgeom(n);
+  const int np = pg.np, pA = pg.pA, pB = pg.pB, ld = n + 1, n2 = n * n;
+  double* B1 = sm;               // T (A-type) -> P0 (A-type)
+  double* B2 = B1 + pg.szA;      // Gm (A-type) -> W (A-type pitch)
+  double* B3 = B2 + pg.szA;      // U0 (pitch pB) -> R (B-type), [K4][pB]
+  double* V = B3 + pg.szB;       // small matrices, [n][ld] each
+  double* X = V + n * ld;
+  double* Hc = X + n * ld;
+  double* Gm1 = Hc + n * ld;     // gamma
+  double* Z = Gm1 + n * ld;
+  double* A = Z + n * ld;
+  double* Bm = A + n * ld;
+  double* rs = Bm + n * ld;      // sqrt(s) or 0
+  double* sv = rs + n;           // s
+  double* t2p = sv + n;          // [3][n][kIpSeg] partials, then T2 -- needs 3*n*kIpSeg doubles
+  unsigned short* pij = reinterpret_cast<unsigned short*>(t2p + 3 * n * kIpSeg);
+  unsigned short* pidx = pij + np;
+  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t o2 = static_cast<int64_t>(g) * n2;
+  const double* o7 = out7 + static_cast<int64_t>(g) * L8;
+
+  build_pair_tables(n, pij, pidx);
+  for (int k = tid; k < n2; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    V[i * ld + j] = evecs[o2 + k];
+    X[i * ld + j] = x[o2 + k];
+    Hc[i * ld + j] = hcore[o2 + k];
+    Gm1[i * ld + j] = o7[k];
+  }
+  for (int k = tid; k < n; k += kThreads) {
+    const double s = evals[static_cast<int64_t>(g) * n + k];
+    sv[k] = s;
+    rs[k] = s > 1.0e-15 ? sqrt(s) : 0.0;
+  }
+  for (int k = tid; k < static_cast<int>(pg.szA); k += kThreads) { B1[k] = 0.0; B2[k] = 0.0; }
+  __syncthreads();
+  {
+    const double* Tg = Tin + static_cast<int64_t>(g) * np * np;
+    for (int k = tid; k < np * np; k += kThreads) {
+      const int r = k / np, c = k - r * np;
+      B1[r * pA + c] = Tg[k];
+      const int hi = r > c ? r : c, lo = r > c ? c : r;
+      const double v = o7[n2 + tri_idx(hi, lo)];
+      B2[r * pA + c] = (r == c) ? 2.0 * v : v;
+    }
+  }
+  __syncthreads();
+  double acc[MAXI][kNJ][2];
+  // U0 = T Gm  (Gm symmetric: B(k, c) = Gm[c][k])
+  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
+                 [&](int m, int k) { return B1[m * pA + k]; },
+                 [&](int k, int c) { return B2[c * pA + k]; });
+  gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+    if (m < pg.K4) {
+      B3[m * pB + c] = v0;
+      B3[m * pB + c + 1] = v1;
+    }
+  });
+  __syncthreads();
+  // Z = 1/2 Y,  Y[a,i] = 2 sum_{b j} X_bj s_(ij) U0[(ab),(ij)]
+  for (int k = tid; k < n2; k += kThreads) {
+    const int a = k / n, i = k - a * n;
+    double s = 0.0;
+    for (int b = 0; b < n; ++b) {
+      const double* urow = B3 + pidx[a * n + b] * pB;
+      for (int j = 0; j < n; ++j) {
+        const double u = urow[pidx[i * n + j]];
+        s += X[b * ld + j] * (i == j ? 2.0 * u : u);
+      }
+    }
+    Z[a * ld + i] = s;
+  }
+  // P0[AB][I] = X_ai X_bj + X_aj X_bi  (overwrites T; U0 is complete)
+  for (int k = tid; k < np * np; k += kThreads) {
+    const int AB = k / np, I = k - AB * np;
+    const int a = pij[AB] & 0xff, b = pij[AB] >> 8, i = pij[I] & 0xff, j = pij[I] >> 8;
+    B1[AB * pA + I] = X[a * ld + i] * X[b * ld + j] + X[a * ld + j] * X[b * ld + i];
+  }
+  __syncthreads();
+  // R = Gm P0^T
+  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
+                 [&](int m, int k) { return B2[m * pA + k]; },
+                 [&](int k, int c) { return B1[c * pA + k]; });
+  gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+    if (m < pg.K4) {
+      B3[m * pB + c] = v0;
+      B3[m * pB + c + 1] = v1;
+    }
+  });
+  __syncthreads();
+  // W = P0 R
+  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
+                 [&](int m, int k) { return B1[m * pA + k]; },
+                 [&](int k, int c) { return B3[k * pB + c]; });
+  gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+    // Gm was last read by the previous GEMM (barrier above); pA may be < rows8
+    if (c < np) B2[m * pA + c] = v0;
+    if (c + 1 < np) B2[m * pA + c + 1] = v1;
+  });
+
+  // ---- one-electron adjoint (same algebra as one_el_adjoint_kernel, grad.cu) ----
+  auto matmul = [&](double* C, const double* P, bool tp, const double* Q, bool tq) {
+    for (int k = tid; k < n2; k += kThreads) {
+      const int i = k / n, j = k - i * n;
+      double a2 = 0.0;
+      for (int r = 0; r < n; ++r)
+        a2 += (tp ? P[r * ld + i] : P[i * ld + r]) * (tq ? Q[j * ld + r] : Q[r * ld + j]);
+      C[i * ld + j] = a2;
+    }
+    __syncthreads();
+  };
+  for (int k = tid; k < n2; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    Bm[i * ld + j] = Gm1[i * ld + j] + Gm1[j * ld + i];
+  }
+  __syncthreads();  // also publishes W and Z
+  matmul(A, X, false, Bm, false);    // A = X (gamma + gamma^T)
+  matmul(Bm, Hc, false, A, false);   // Bm = hcore A
+  for (int k = tid; k < n2; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    Z[i * ld + j] += Bm[i * ld + j];
+  }
+  __syncthreads();
+  matmul(A, V, true, Z, false);      // A = V^T Z
+  matmul(Bm, A, false, V, false);    // Bm = V^T Z V
+  for (int k = tid; k < n2; k += kThreads) {
+    const int p = k / n, q = k - p * n;
+    const double rp = rs[p], rq = rs[q];
+    double gpq = 0.0;
+    if (rp > 0.0 && rq > 0.0) {
+      gpq = -1.0 / (rp * rq * (rp + rq));
+    } else if ((rp > 0.0) != (rq > 0.0)) {
+      const double sp = sv[p], sq = sv[q];
+      if (sp != sq) gpq = ((rp > 0.0 ? 1.0 / rp : 0.0) - (rq > 0.0 ? 1.0 / rq : 0.0)) / (sp - sq);
+    }
+    Bm[p * ld + q] *= gpq;
+  }
+  __syncthreads();
+  matmul(A, V, false, Bm, false);    // A = V B
+  matmul(Z, A, false, V, true);      // Z = Omega
+  matmul(A, X, false, Gm1, false);   // A = X gamma
+  matmul(Bm, A, false, X, true);     // Bm = X gamma X^T = Pao
+
+  // ---- T2[x][m] = sum_{bcd} (d_x m b|c d) W[(mb),(cd)]: int2e_ip1 streamed once ----
+  {
+    const int n3 = n2 * n;
+    const int64_t n4 = static_cast<int64_t>(n3) * n;
+    const double* ip = eri_ip1 + static_cast<int64_t>(g) * 3 * n4;
+    const int seg = (n3 + kIpSeg - 1) / kIpSeg;
+    const float inv_n2 = 1.0f / static_cast<float>(n2);
+    for (int item = warp; item < n * kIpSeg; item += kWarps) {
+      const int m = item / kIpSeg, s = item - m * kIpSeg;
+      const int e0 = s * seg, e1 = min(n3, e0 + seg);
+      const double* r0 = ip + static_cast<int64_t>(m) * n3;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 2
+      for (int e = e0 + lane; e < e1; e += 32) {
+        int b = static_cast<int>((static_cast<float>(e) + 0.5f) * inv_n2);
+        int cd = e - b * n2;
+        if (cd < 0) { --b; cd += n2; } else if (cd >= n2) { ++b; cd -= n2; }
+        const double w = B2[pidx[m * n + b] * pA + pidx[cd]];
+        a0 = fma(__ldg(r0 + e), w, a0);
+        a1 = fma(__ldg(r0 + n4 + e), w, a1);
+        a2 = fma(__ldg(r0 + 2 * n4 + e), w, a2);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      if (lane == 0) {
+        t2p[(0 * n + m) * kIpSeg + s] = a0;
+        t2p[(1 * n + m) * kIpSeg + s] = a1;
+        t2p[(2 * n + m) * kIpSeg + s] = a2;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- grad[A][x] ----
+  for (int item = warp; item < natm * 3; item += kWarps) {
+    const int At = item / 3, xx = item - At * 3;
+    const int p0 = aoslices[2 * At], p1 = aoslices[2 * At + 1];
+    const double* ipo = ipovlp + (static_cast<int64_t>(g) * 3 + xx) * n2;
+    const double* hd = hcore_deriv + ((static_cast<int64_t>(g) * natm + At) * 3 + xx) * n2;
+    double a2 = 0.0;
+    for (int k = p0 * n + lane; k < p1 * n; k += 32) {
+      const int i = k / n, j = k - i * n;
+      a2 -= ipo[k] * (Z[i * ld + j] + Z[j * ld + i]);
+    }
+    for (int k = lane; k < n2; k += 32) {
+      const int i = k / n, j = k - i * n;
+      a2 += hd[k] * Bm[i * ld + j];
+    }
+    for (int m = p0 + lane; m < p1; m += 32) {
+      double t = 0.0;
+#pragma unroll
+      for (int s = 0; s < kIpSeg; ++s) t += t2p[(xx * n + m) * kIpSeg + s];
+      a2 -= 0.5 * t;
+    }
+    for (int o = 16; o > 0; o >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    if (lane == 0) {
+      const int64_t o = (static_cast<int64_t>(g) * natm + At) * 3 + xx;
+      grad[o] = a2 + (grad_nuc ? grad_nuc[o] : 0.0);
+    }
+  }
+}
+
+size_t grad_smem_bytes(int n) {
+  const PGeom pg = pgeom(n);
+  return (2 * pg.szA + pg.szB + static_cast<size_t>(7) * n * (n + 1) + 2 * n + 3 * n * kIpSeg) * sizeof(double) +
+         table_bytes(n);
+}
+
+int maxi_for(int n) {
+  const PGeom pg = pgeom(n);
+  const int nitems = pg.M8 * ((pg.M8 + kNJ - 1) / kNJ);
+  return (nitems + kWarps - 1) / kWarps;
+}
+
+__global__ void add_enuc_kernel_p(int G, const double* __restrict__ e0, const double* __restrict__ e_nuc,
+                                  double* __restrict__ E) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) E[g] = e0[g] + (e_nuc ? e_nuc[g] : 0.0);
+}
+
+}  // namespace
+
+// ---- internal entry points (common.cuh) -------------------------------------
+int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
+                      const double* eri, double* hvec, double* Tout) {
+  EVC_REQUIRE(n >= 1 && n <= kPackedMaxNorb, "packed_ao2oao: n=%d unsupported", n);
+  const size_t smem = ao2oao_smem_bytes(n);
+  EVC_REQUIRE(smem <= ctx->smem_optin, "packed_ao2oao: needs %zu bytes of shared memory", smem);
+  const int64_t L8 = packed_len(n);
+  const int mi = maxi_for(n);
+#define EVC_CASE(MI)                                                                                 \
+  {                                                                                                  \
+    auto kern = packed_ao2oao_kernel<MI>;                                                            \
+    EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                        static_cast<int>(smem)));                                    \
+    kern<<<nbatch, kThreads, smem, ctx->stream>>>(n, L8, x, hcore, eri, hvec, Tout);                 \
+  }
+  if (mi <= 1) EVC_CASE(1) else if (mi <= 2) EVC_CASE(2) else if (mi <= 3) EVC_CASE(3)
+  else if (mi <= 4) EVC_CASE(4) else EVC_CASE(5)
+#undef EVC_CASE
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices, const double* x,
+                    const double* evals, const double* evecs, const double* hcore, const double* Tin,
+                    const double* out7, const double* ipovlp, const double* hcore_deriv,
+                    const double* eri_ip1, const double* grad_nuc, double* grad) {
+  EVC_REQUIRE(n >= 1 && n <= kPackedMaxNorb, "packed_grad: n=%d unsupported", n);
+  const size_t smem = grad_smem_bytes(n);
+  EVC_REQUIRE(smem <= ctx->smem_optin, "packed_grad: needs %zu bytes of shared memory", smem);
+  const int64_t L8 = packed_len(n);
+  const int mi = maxi_for(n);
+#define EVC_CASE(MI)                                                                                 \
+  {                                                                                                  \
+    auto kern = packed_grad_kernel<MI>;                                                              \
+    EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                        static_cast<int>(smem)));                                    \
+    kern<<<nbatch, kThreads, smem, ctx->stream>>>(n, natm, L8, aoslices, x, evals, evecs, hcore, Tin, \
+                                                  out7, ipovlp, hcore_deriv, eri_ip1, grad_nuc, grad); \
+  }
+  if (mi <= 1) EVC_CASE(1) else if (mi <= 2) EVC_CASE(2) else if (mi <= 3) EVC_CASE(3)
+  else if (mi <= 4) EVC_CASE(4) else EVC_CASE(5)
+#undef EVC_CASE
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_packed_hvec_from_full(evc_ctx* ctx, int nbatch, int n, const double* h1, const double* h2, double* hvec) {
+  const int64_t L8 = packed_len(n);
+  dim3 grid(static_cast<unsigned>((L8 + 255) / 256), nbatch);
+  hvec_from_full_kernel<<<grid, 256, 0, ctx->stream>>>(n, L8, h1, h2, hvec);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_packed_unpack_rdms(evc_ctx* ctx, int nbatch, int n, const double* out7, double* gamma, double* Gamma8) {
+  const int64_t L8 = packed_len(n);
+  const int64_t n4 = static_cast<int64_t>(n) * n * n * n;
+  dim3 grid(static_cast<unsigned>((n4 + 255) / 256), nbatch);
+  unpack_rdms_kernel<<<grid, 256, 0, ctx->stream>>>(n, L8, out7, gamma, Gamma8);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_packed_pair_weights(evc_ctx* ctx, int nbatch, int N, const double* C, int64_t c_stride, double* w) {
+  const int P = N * (N + 1) / 2;
+  dim3 grid((P + 127) / 128, nbatch);
+  tril_weights_kernel<<<grid, 128, 0, ctx->stream>>>(N, P, C, c_stride, w);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- C ABI ---------------------------------------------------------------------
+extern "C" {
+
+int64_t evc_packed_row_len(int n) { return n >= 1 ? packed_len(n) : -1; }
+
+int evc_stack_pack8(evc_ctx* ctx, int layout, int N, int n, const double* one_rdm, const double* two_rdm,
+                    double* RH, double* RG) {
+  EVC_REQUIRE(ctx && one_rdm && two_rdm && RH && RG, "evc_stack_pack8: NULL argument");
+  EVC_REQUIRE(layout == EVC_LAYOUT_FULL || layout == EVC_LAYOUT_TRIL || layout == EVC_LAYOUT_FULL_EXCH ||
+                  layout == EVC_LAYOUT_TRIL_EXCH,
+              "evc_stack_pack8: two_RDM layout %d not one of 6/5/3/2", layout);
+  EVC_REQUIRE(N >= 1 && n >= 1 && n <= 255, "evc_stack_pack8: N=%d n=%d unsupported", N, n);
+  StackView sv;
+  sv.two = two_rdm;
+  sv.layout = layout;
+  sv.N = N;
+  sv.n = n;
+  sv.n4 = static_cast<int64_t>(n) * n * n * n;
+  sv.Lc = static_cast<int64_t>(n) * n * (static_cast<int64_t>(n) * n + 1) / 2;
+  const int64_t L8 = packed_len(n);
+  const int P = N * (N + 1) / 2;
+  EVC_REQUIRE(P <= 65535, "evc_stack_pack8: too many state pairs (%d)", P);
+  dim3 grid(static_cast<unsigned>((L8 + 255) / 256), P);
+  pack8_stack_kernel<<<grid, 256, 0, ctx->stream>>>(sv, L8, one_rdm, RH, RG);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_energy_with_grad_packed_workspace_bytes(int N, int n, int natm, int nbatch, size_t* bytes) {
+  EVC_REQUIRE(bytes != nullptr && N >= 1 && n >= 1 && nbatch >= 0, "evc_energy_with_grad_packed_workspace_bytes: bad arguments");
+  const size_t G = static_cast<size_t>(nbatch);
+  const size_t n2 = static_cast<size_t>(n) * n, n4 = n2 * n2;
+  const int64_t L8 = packed_len(n);
+  const int P = N * (N + 1) / 2;
+  const size_t np = npair_of(n);
+  size_t tot = 0;
+  tot += 2 * evc_align_up(G * n2 * 8, 256);        // X, evecs
+  tot += evc_align_up(G * n * 8, 256);             // evals
+  tot += 2 * evc_align_up(G * L8 * 8, 256);        // hvec, out7
+  tot += 2 * evc_align_up(G * P * 8, 256);         // Hp, w
+  tot += evc_align_up(G * 8, 256);                 // E0
+  tot += evc_align_up(G * N * 8, 256);             // C
+  tot += evc_align_up(evc_rows_dot_ws_bytes(L8, P, nbatch), 256);
+  tot += evc_align_up(evc_rows_axpy_ws_bytes(L8, P, nbatch), 256);
+  if (n <= kPackedMaxNorb) {
+    tot += evc_align_up(G * np * np * 8, 256);     // T
+  } else {
+    size_t gb = 0;
+    int rc = evc_grad_workspace_bytes(n, natm, nbatch, &gb);
+    if (rc) return rc;
+    tot += 2 * evc_align_up(G * n2 * 8, 256);      // h1, gamma
+    tot += 4 * evc_align_up(G * n4 * 8, 256);      // h2, t3, rot scratch, Gamma8
+    tot += evc_align_up(gb, 256);
+  }
+  *bytes = tot;
+  return 0;
+}
+
+int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const double* RH, const double* RG,
+                                const double* Linv, int nbatch, const evc_ao_bundle* ao, double* E,
+                                double* grad, double* Cvec, void* workspace, size_t workspace_bytes) {
+  EVC_REQUIRE(ctx && RH && RG && Linv && ao && E && grad && workspace, "evc_energy_with_grad_packed: NULL argument");
+  EVC_REQUIRE(ao->ovlp && ao->hcore && ao->eri && ao->ipovlp && ao->hcore_deriv && ao->eri_ip1 && ao->aoslices,
+              "evc_energy_with_grad_packed: incomplete AO bundle");
+  EVC_REQUIRE(n >= 1 && n <= 32 && N >= 1 && N <= 112, "evc_energy_with_grad_packed: n=%d N=%d unsupported", n, N);
+  if (nbatch <= 0) return 0;
+  const size_t G = static_cast<size_t>(nbatch);
+  const size_t n2 = static_cast<size_t>(n) * n, n4 = n2 * n2;
+  const int64_t L8 = packed_len(n);
+  const int P = N * (N + 1) / 2;
+  const size_t np = npair_of(n);
+  const bool small = n <= kPackedMaxNorb;
+  const size_t dot_b = evc_rows_dot_ws_bytes(L8, P, nbatch), axpy_b = evc_rows_axpy_ws_bytes(L8, P, nbatch);
+  evc_arena ar(workspace, workspace_bytes);
+  double* X = ar.take<double>(G * n2);
+  double* evecs = ar.take<double>(G * n2);
+  double* evals = ar.take<double>(G * n);
+  double* hvec = ar.take<double>(G * L8);
+  double* out7 = ar.take<double>(G * L8);
+  double* Hp = ar.take<double>(G * P);
+  double* w = ar.take<double>(G * P);
+  double* E0 = ar.take<double>(G);
+  double* C = ar.take<double>(G * N);
+  char* dot_ws = ar.take<char>(dot_b);
+  char* axpy_ws = ar.take<char>(axpy_b);
+  EVC_REQUIRE(X && evecs && evals && hvec && out7 && Hp && w && E0 && C && dot_ws && axpy_ws,
+              "evc_energy_with_grad_packed: workspace too small (%zu bytes)", workspace_bytes);
+  double *T = nullptr, *h1 = nullptr, *gamma = nullptr, *h2 = nullptr, *t3 = nullptr, *scratch = nullptr,
+         *Gamma8 = nullptr;
+  char* grad_ws = nullptr;
+  size_t grad_b = 0;
+  int rc;
+  if (small) {
+    T = ar.take<double>(G * np * np);
+    EVC_REQUIRE(T, "evc_energy_with_grad_packed: workspace too small (%zu bytes)", workspace_bytes);
+  } else {
+    if ((rc = evc_grad_workspace_bytes(n, natm, nbatch, &grad_b))) return rc;
+    h1 = ar.take<double>(G * n2);
+    gamma = ar.take<double>(G * n2);
+    h2 = ar.take<double>(G * n4);
+    t3 = ar.take<double>(G * n4);
+    scratch = ar.take<double>(G * n4);
+    Gamma8 = ar.take<double>(G * n4);
+    grad_ws = ar.take<char>(grad_b);
+    EVC_REQUIRE(h1 && gamma && h2 && t3 && scratch && Gamma8 && grad_ws,
+                "evc_energy_with_grad_packed: workspace too small (%zu bytes)", workspace_bytes);
+  }
+  if (Cvec) C = Cvec;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_LOEWDIN))) return rc;
+  if ((rc = evc_loewdin(ctx, nbatch, n, ao->ovlp, X, evals, evecs))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_AO2OAO))) return rc;
+  if (small) {
+    if ((rc = evc_packed_ao2oao(ctx, nbatch, n, X, ao->hcore, ao->eri, hvec, T))) return rc;
+  } else {
+    if ((rc = evc_ao2oao(ctx, nbatch, n, ao->hcore, ao->eri, X, 0, h1, h2, t3, scratch, evc_align_up(G * n4 * 8, 256)))) return rc;
+    if ((rc = evc_packed_hvec_from_full(ctx, nbatch, n, h1, h2, hvec))) return rc;
+  }
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_SUBSPACE_H))) return rc;
+  if ((rc = evc_rows_dot(ctx, RH, L8, P, hvec, nbatch, Hp, dot_ws, dot_b))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_GENEIG))) return rc;
+  if ((rc = evc_launch_geneig(ctx, nbatch, N, 1, Hp, Linv, 1, E0, C))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_PREDICT))) return rc;
+  if ((rc = evc_packed_pair_weights(ctx, nbatch, N, C, N, w))) return rc;
+  if ((rc = evc_rows_axpy(ctx, RG, L8, P, w, nbatch, out7, axpy_ws, axpy_b))) return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD))) return rc;
+  if (small) {
+    if ((rc = evc_packed_grad(ctx, nbatch, n, natm, ao->aoslices, X, evals, evecs, ao->hcore, T, out7, ao->ipovlp,
+                              ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad)))
+      return rc;
+  } else {
+    if ((rc = evc_packed_unpack_rdms(ctx, nbatch, n, out7, gamma, Gamma8))) return rc;
+    if ((rc = evc_grad_elec_full(ctx, nbatch, n, natm, ao->aoslices, evals, evecs, X, ao->hcore, t3, gamma, Gamma8,
+                                 ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b)))
+      return rc;
+  }
+  add_enuc_kernel_p<<<(nbatch + 127) / 128, 128, 0, ctx->stream>>>(nbatch, E0, ao->e_nuc, E);
+  EVC_CHECK_LAUNCH();
+  return evc_stage_mark(ctx, EVC_NSTAGE);
+}
+
+}  // extern "C"

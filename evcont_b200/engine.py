@@ -16,6 +16,9 @@ from ._lib import AoBundle, check
 
 LAYOUT_FULL, LAYOUT_TRIL, LAYOUT_FULL_EXCH, LAYOUT_TRIL_EXCH = 6, 5, 3, 2
 
+#: use the 8-fold-symmetric packed prediction step unless the full RDMs are wanted
+USE_PACKED = True
+
 _engines = {}
 _engines_lock = threading.Lock()
 
@@ -248,11 +251,14 @@ class Engine:
         return grad
 
     # -- fused step ------------------------------------------------------------------------
-    def energy_with_grad(self, stack, ao, want_rdms=False, out=None):
+    def energy_with_grad(self, stack, ao, want_rdms=False, out=None, packed=None):
         """One prediction step for a batch of geometries resident on the device.
 
         ``ao``: :class:`DeviceAO`.  Returns ``(E[G], grad[G,natm,3], gamma, Gamma, cvec)``
-        (gamma/Gamma are ``None`` unless ``want_rdms``).
+        (gamma/Gamma are ``None`` unless ``want_rdms``).  ``packed`` (default
+        :data:`USE_PACKED`) selects the 8-fold-symmetric packed step
+        (``evc_energy_with_grad_packed``); the full predicted RDMs only exist on the
+        unpacked path, so ``want_rdms`` implies ``packed=False``.
         """
         G, n, natm, N = ao.nbatch, ao.nao, ao.natm, stack.ntrain
         if n != stack.norb:
@@ -261,6 +267,18 @@ class Engine:
             E, grad, cvec = self.empty(G), self.empty(G, natm, 3), self.empty(G, N)
         else:
             E, grad, cvec = out
+        packed = (USE_PACKED if packed is None else packed) and not want_rdms
+        if packed:
+            rh, rg = stack.packed()
+            nbytes = C.c_size_t()
+            check(self.lib.evc_energy_with_grad_packed_workspace_bytes(N, n, natm, G, C.byref(nbytes)))
+            ws = self.workspace(nbytes.value)
+            self._bind_stream()
+            bundle = ao.bundle()
+            check(self.lib.evc_energy_with_grad_packed(
+                self._ctx, N, n, natm, _ptr(rh), _ptr(rg), _ptr(stack.linv), G, C.byref(bundle),
+                _ptr(E), _ptr(grad), _ptr(cvec), _ptr(ws), ws.numel()))
+            return E, grad, None, None, cvec
         gamma = self.empty(G, n, n) if want_rdms else None
         Gamma = self.empty(G, n, n, n, n) if want_rdms else None
         nbytes = C.c_size_t()
@@ -275,7 +293,7 @@ class Engine:
             _ptr(cvec), _ptr(ws), ws.numel()))
         return E, grad, gamma, Gamma, cvec
 
-    def energy_with_grad_host(self, stack, host_ao, chunk=256, sync=True):
+    def energy_with_grad_host(self, stack, host_ao, chunk=256, sync=True, packed=None):
         """The prediction step on HOST arrays (:class:`HostAO`): chunked host->device
         copies, kernels and read-back overlap on three streams.  Results land in
         ``host_ao.E`` / ``host_ao.grad`` (returned); with ``sync=False`` the caller
@@ -285,6 +303,20 @@ class Engine:
             raise ValueError(f"mol.nao={n} does not match the stack's norb={stack.norb}")
         chunk = max(1, min(int(chunk), G))
         nbytes = C.c_size_t()
+        if USE_PACKED if packed is None else packed:
+            rh, rg = stack.packed()
+            check(self.lib.evc_energy_with_grad_packed_host_workspace_bytes(N, n, natm, chunk,
+                                                                            C.byref(nbytes)))
+            ws = self.workspace(nbytes.value)
+            self._bind_stream()
+            bundle = host_ao.bundle()
+            check(self.lib.evc_energy_with_grad_packed_host(
+                self._ctx, N, n, natm, _ptr(rh), _ptr(rg), _ptr(stack.linv), G, C.byref(bundle),
+                C.c_void_p(host_ao.E.data_ptr()), C.c_void_p(host_ao.grad.data_ptr()), chunk,
+                _ptr(ws), ws.numel()))
+            if sync:
+                torch.cuda.current_stream(self.device).synchronize()
+            return host_ao.E, host_ao.grad
         check(self.lib.evc_energy_with_grad_host_workspace_bytes(stack.layout, N, n, natm, chunk,
                                                                  C.byref(nbytes)))
         ws = self.workspace(nbytes.value)
@@ -368,6 +400,26 @@ class DeviceStack:
         if self.two_rdm.shape[1] != expect or self.one_rdm.shape[1] != n2:
             raise ValueError("t-RDM stack shapes are inconsistent with norb/ntrain")
         self.linv = eng.geneig_prepare(self.overlap)
+        self._packed = None
+
+    def packed(self):
+        """``(RH, RG)``: the stack packed on the 8-fold integral symmetry
+        (``evc_stack_pack8``), built on first use and kept in HBM."""
+        if self._packed is None:
+            eng = self.engine
+            npairs = self.ntrain * (self.ntrain + 1) // 2
+            row = int(eng.lib.evc_packed_row_len(self.norb))
+            rh, rg = eng.empty(npairs, row), eng.empty(npairs, row)
+            eng._bind_stream()
+            check(eng.lib.evc_stack_pack8(eng._ctx, self.layout, self.ntrain, self.norb,
+                                          _ptr(self.one_rdm), _ptr(self.two_rdm), _ptr(rh), _ptr(rg)))
+            self._packed = (rh, rg)
+        return self._packed
+
+    @property
+    def packed_nbytes(self):
+        rh, rg = self.packed()
+        return rh.numel() * 8 + rg.numel() * 8
 
     @property
     def nbytes(self):

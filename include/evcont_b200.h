@@ -219,6 +219,36 @@ int evc_energy_with_grad(evc_ctx *ctx, int layout, int ntrain, int n, int natm,
                          double *gamma, double *Gamma, double *Cvec,
                          void *workspace, size_t workspace_bytes);
 
+/* ---- packed prediction step (8-fold symmetric form) --------------------------
+ * The same step as evc_energy_with_grad, restated on the permutational symmetry
+ * (ij|kl) = (ji|kl) = (ij|lk) = (kl|ij) of the AO two-electron integrals that
+ * mol.intor('int2e') returns (evcont/ab_initio_gradients_loewdin.py:283, 338-339):
+ * H (ab_initio_eigenvector_continuation.py:38-71) and the gradient
+ * (ab_initio_gradients_loewdin.py:190-305) only see the totally symmetric part of
+ * each two-body t-RDM block, so the stack is packed once into N(N+1)/2 rows of
+ * evc_packed_row_len(n) = n^2 + np(np+1)/2 doubles (np = n(n+1)/2, rounded up to
+ * even): 12x fewer bytes and flops than the (N,N,n,n,n,n) layout at n=10, N=20.
+ *
+ * evc_stack_pack8: any of the four layouts -> RH (rows for H: blocks a >= b, what
+ *   the eigensolver reads) and RG (rows for the predicted RDMs: (block[a,b] +
+ *   block[b,a])/2, used with the weights 2 c_a c_b / c_a^2 of
+ *   ab_initio_gradients_loewdin.py:345-353).  RH, RG: [N(N+1)/2][row_len] each.
+ * evc_energy_with_grad_packed: Loewdin -> packed AO->OAO (two DMMA GEMMs per
+ *   geometry in shared memory, n <= 13; the full-tensor kernels above for larger n)
+ *   -> Hp = hvec . RH -> eigensolve -> out7 = w . RG -> gradient (three DMMA GEMMs
+ *   per geometry in shared memory, int2e_ip1 streamed once).  Same outputs as
+ *   evc_energy_with_grad (E, grad, optional Cvec); the full predicted RDMs are not
+ *   formed -- use evc_energy_with_grad when they are wanted. */
+int64_t evc_packed_row_len(int n);
+int evc_stack_pack8(evc_ctx *ctx, int layout, int ntrain, int n, const double *one_rdm,
+                    const double *two_rdm, double *RH, double *RG);
+int evc_energy_with_grad_packed_workspace_bytes(int ntrain, int n, int natm, int nbatch,
+                                                size_t *bytes);
+int evc_energy_with_grad_packed(evc_ctx *ctx, int ntrain, int n, int natm, const double *RH,
+                                const double *RG, const double *Linv, int nbatch,
+                                const evc_ao_bundle *ao, double *E, double *grad, double *Cvec,
+                                void *workspace, size_t workspace_bytes);
+
 /* The same step with HOST buffers on both sides -- the form the reference's call
  * site has (evcont/MD_utils.py:43: numpy arrays from libcint in, (E, grad) out).
  * Every pointer of `ao_host` (aoslices included), E_host and grad_host are HOST
@@ -233,6 +263,14 @@ int evc_energy_with_grad_host(evc_ctx *ctx, int layout, int ntrain, int n, int n
                               const double *one_rdm, const double *two_rdm, const double *Linv,
                               int nbatch, const evc_ao_bundle *ao_host, double *E_host,
                               double *grad_host, int chunk, void *workspace, size_t workspace_bytes);
+
+/* Packed step with HOST buffers (same pipeline as evc_energy_with_grad_host). */
+int evc_energy_with_grad_packed_host_workspace_bytes(int ntrain, int n, int natm, int chunk,
+                                                     size_t *bytes);
+int evc_energy_with_grad_packed_host(evc_ctx *ctx, int ntrain, int n, int natm, const double *RH,
+                                     const double *RG, const double *Linv, int nbatch,
+                                     const evc_ao_bundle *ao_host, double *E_host, double *grad_host,
+                                     int chunk, void *workspace, size_t workspace_bytes);
 
 #ifdef __cplusplus
 }

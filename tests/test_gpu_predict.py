@@ -84,8 +84,76 @@ def test_energy_with_grad_golden(norb, natm, ntrain, layout):
     assert np.abs(gam - g[f"L{layout}_gamma"]).max() < 1e-9
     if f"L{layout}_Gamma" in g:
         assert np.abs(Gam - g[f"L{layout}_Gamma"]).max() < 1e-9
+    # without the RDMs the step runs in the packed (8-fold symmetric) form
     e2, grad2 = get_energy_with_grad(mol, one, two, ovlp)
-    assert e2 == e and np.array_equal(grad, grad2)  # deterministic
+    assert abs(e2 - float(g[f"L{layout}_Etot"])) < E_TOL
+    assert np.abs(grad2 - g[f"L{layout}_grad"]).max() < F_TOL
+    e3, grad3 = get_energy_with_grad(mol, one, two, ovlp)
+    assert e3 == e2 and np.array_equal(grad3, grad2)  # deterministic
+
+
+@pytest.mark.parametrize("layout", [6, 5, 3, 2])
+@pytest.mark.parametrize("norb,natm,ntrain", PREDICT_CASES)
+def test_packed_and_full_steps_agree(norb, natm, ntrain, layout):
+    """evc_energy_with_grad_packed vs evc_energy_with_grad on the same device inputs."""
+    from evcont_b200.engine import DeviceAO
+    from evcont_b200.mol import ao_bundle
+    from evcont_b200.stackcache import as_device_stack
+    ovlp, one, two = synthetic_stack(norb, ntrain, 40 + layout, layout)
+    stack = as_device_stack(one, two, ovlp)
+    mols = [_mol(norb, natm, 500 + k) for k in range(5)]
+    ao = DeviceAO.from_bundles(stack.engine, [ao_bundle(m) for m in mols])
+    Ep, gp, _, _, cp = stack.engine.energy_with_grad(stack, ao, packed=True)
+    Ef, gf, _, _, cf = stack.engine.energy_with_grad(stack, ao, packed=False)
+    assert (Ep - Ef).abs().max().item() < 1e-11
+    assert (gp - gf).abs().max().item() < 1e-10
+    sgn = torch_sign(cp, cf)
+    assert (cp * sgn - cf).abs().max().item() < 1e-9
+
+
+def torch_sign(a, b):
+    import torch
+    k = b.abs().argmax(dim=1, keepdim=True)
+    return torch.sign(a.gather(1, k)) * torch.sign(b.gather(1, k))
+
+
+@pytest.mark.parametrize("layout", [6, 3])
+def test_packed_step_asymmetric_full_stack(layout):
+    """Full layouts whose [a,b] and [b,a] blocks differ (a user-assigned stack): H reads the
+    lower-triangle blocks only, the predicted RDMs read both (evcont FCI_EVCont.py:117-127,
+    ab_initio_gradients_loewdin.py:343-353)."""
+    from evcont_b200.ab_initio_gradients_loewdin import get_energy_with_grad
+    from oracle import gradients as og
+    norb, natm, ntrain = 6, 3, 4
+    ovlp, one, two = synthetic_stack(norb, ntrain, 8, layout)
+    rng = np.random.default_rng(3)
+    one = one + 0.3 * rng.standard_normal(one.shape)
+    pert = rng.standard_normal((ntrain, ntrain, norb * norb, norb * norb)) / norb
+    pert = pert + pert.transpose(0, 1, 3, 2)
+    if layout == 6:
+        two = two + 0.3 * pert.reshape(two.shape)
+    else:
+        ic = np.tril_indices(norb * norb)
+        two = two + 0.3 * pert[:, :, ic[0], ic[1]]
+    mol = _mol(norb, natm, 77)
+    e, grad = get_energy_with_grad(mol, one, two, ovlp)
+    oe, ogr = og.get_energy_with_grad(mol, one, two, ovlp)
+    assert abs(e - oe) < E_TOL and np.abs(grad - ogr).max() < F_TOL
+
+
+@pytest.mark.parametrize("norb,natm,ntrain,layout", [(13, 3, 4, 5), (11, 4, 3, 2), (12, 5, 3, 6),
+                                                     (14, 4, 3, 5), (16, 5, 3, 2)])
+def test_packed_step_larger_norb_vs_oracle(norb, natm, ntrain, layout):
+    """n = 13 is the H2O/6-31G size (largest shared-memory case); n > 13 takes the
+    full-tensor transform/gradient kernels around the packed stack contractions."""
+    from evcont_b200.ab_initio_gradients_loewdin import get_energy_with_grad
+    from oracle import gradients as og
+    ovlp, one, two = synthetic_stack(norb, ntrain, 19, layout)
+    mol = _mol(norb, natm, 31)
+    e, grad = get_energy_with_grad(mol, one, two, ovlp)
+    oe, ogr = og.get_energy_with_grad(mol, one, two, ovlp)
+    assert abs(e - oe) < E_TOL
+    assert np.abs(grad - ogr).max() < F_TOL
 
 
 def test_grad_elec_OAO_against_oracle():
