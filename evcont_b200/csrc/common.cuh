@@ -46,6 +46,8 @@ int evc_launch_rot_pass(cudaStream_t st, int nbatch, int n, const double* in, co
                         int transpose_m, double* out);
 int evc_launch_geneig(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H,
                       const double* Linv, int nroots, double* E, double* C);
+int evc_launch_geneig_lowest(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H,
+                             const double* Linv, double* E, double* C);
 size_t evc_rows_dot_ws_bytes(int64_t L, int P, int G);
 int evc_rows_dot(evc_ctx* ctx, const double* rows, int64_t L, int P, const double* hv, int G, double* out,
                  void* workspace, size_t workspace_bytes);
@@ -59,7 +61,8 @@ int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const do
 int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices, const double* x,
                     const double* evals, const double* evecs, const double* hcore, const double* Tin,
                     const double* out7, const double* ipovlp, const double* hcore_deriv,
-                    const double* eri_ip1, const double* grad_nuc, double* grad);
+                    const double* eri_ip1, const double* grad_nuc, double* Wg, double* OmS, double* Pao,
+                    double* grad);
 // K8 on full (n^4) arrays with the nuclear gradient added (grad.cu)
 int evc_grad_elec_full(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices,
                        const double* evals, const double* evecs, const double* x, const double* hcore,

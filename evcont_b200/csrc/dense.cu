@@ -521,6 +521,8 @@ size_t geneig_smem_bytes(int N) {
 
 int launch_geneig(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H, const double* Linv,
                   int nroots, double* E, double* C) {
+  // ground state only: tridiagonalisation + bisection + inverse iteration, one warp per geometry
+  if (nroots == 1) return evc_launch_geneig_lowest(ctx, nbatch, N, packed_lower, H, Linv, E, C);
   const size_t smem = geneig_smem_bytes(N);
   EVC_CHECK_CUDA(cudaFuncSetAttribute(geneig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));

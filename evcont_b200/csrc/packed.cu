@@ -361,17 +361,12 @@ size_t ao2oao_smem_bytes(int n) {
 // ---------------------------------------------------------------------------
 // K8p: one CTA per geometry
 // ---------------------------------------------------------------------------
-constexpr int kIpSeg = 4;  // int2e_ip1 rows are cut into this many segments per warp item
-
 template <int MAXI>
 __global__ void __launch_bounds__(kThreads)
-packed_grad_kernel(int n, int natm, int64_t L8, const int32_t* __restrict__ aoslices,
-                   const double* __restrict__ x, const double* __restrict__ evals,
+packed_grad_kernel(int n, int64_t L8, const double* __restrict__ x, const double* __restrict__ evals,
                    const double* __restrict__ evecs, const double* __restrict__ hcore,
                    const double* __restrict__ Tin, const double* __restrict__ out7,
-                   const double* __restrict__ ipovlp, const double* __restrict__ hcore_deriv,
-                   const double* __restrict__ eri_ip1, const double* __restrict__ grad_nuc,
-                   double* __restrict__ grad) {
+                   double* __restrict__ Wout, double* __restrict__ OmSout, double* __restrict__ PaoOut) {
   extern __shared__ __align__(16) double sm[];
   const PGeom pg = pgeom(n);
   const int np = pg.np, pA = pg.pA, pB = pg.pB, ld = n + 1, n2 = n * n;
@@ -387,10 +382,9 @@ packed_grad_kernel(int n, int natm, int64_t L8, const int32_t* __restrict__ aosl
   double* Bm = A + n * ld;
   double* rs = Bm + n * ld;      // sqrt(s) or 0
   double* sv = rs + n;           // s
-  double* t2p = sv + n;          // [3][n][kIpSeg] partials, then T2 -- needs 3*n*kIpSeg doubles
-  unsigned short* pij = reinterpret_cast<unsigned short*>(t2p + 3 * n * kIpSeg);
+  unsigned short* pij = reinterpret_cast<unsigned short*>(sv + n);
   unsigned short* pidx = pij + np;
-  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.x, tid = threadIdx.x;
   const int64_t o2 = static_cast<int64_t>(g) * n2;
   const double* o7 = out7 + static_cast<int64_t>(g) * L8;
 
@@ -467,11 +461,15 @@ packed_grad_kernel(int n, int natm, int64_t L8, const int32_t* __restrict__ aosl
   gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
                  [&](int m, int k) { return B1[m * pA + k]; },
                  [&](int k, int c) { return B3[k * pB + c]; });
-  gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
-    // Gm was last read by the previous GEMM (barrier above); pA may be < rows8
-    if (c < np) B2[m * pA + c] = v0;
-    if (c + 1 < np) B2[m * pA + c + 1] = v1;
-  });
+  {
+    double* Wg = Wout + static_cast<int64_t>(g) * np * np;
+    gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+      if (m < np) {
+        if (c < np) Wg[m * np + c] = v0;
+        if (c + 1 < np) Wg[m * np + c + 1] = v1;
+      }
+    });
+  }
 
   // ---- one-electron adjoint (same algebra as one_el_adjoint_kernel, grad.cu) ----
   auto matmul = [&](double* C, const double* P, bool tp, const double* Q, bool tq) {
@@ -488,7 +486,7 @@ packed_grad_kernel(int n, int natm, int64_t L8, const int32_t* __restrict__ aosl
     const int i = k / n, j = k - i * n;
     Bm[i * ld + j] = Gm1[i * ld + j] + Gm1[j * ld + i];
   }
-  __syncthreads();  // also publishes W and Z
+  __syncthreads();  // also publishes Z
   matmul(A, X, false, Bm, false);    // A = X (gamma + gamma^T)
   matmul(Bm, Hc, false, A, false);   // Bm = hcore A
   for (int k = tid; k < n2; k += kThreads) {
@@ -516,73 +514,113 @@ packed_grad_kernel(int n, int natm, int64_t L8, const int32_t* __restrict__ aosl
   matmul(A, X, false, Gm1, false);   // A = X gamma
   matmul(Bm, A, false, X, true);     // Bm = X gamma X^T = Pao
 
-  // ---- T2[x][m] = sum_{bcd} (d_x m b|c d) W[(mb),(cd)]: int2e_ip1 streamed once ----
+  for (int k = tid; k < n2; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    OmSout[o2 + k] = Z[i * ld + j] + Z[j * ld + i];
+    PaoOut[o2 + k] = Bm[i * ld + j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K8b: streaming contraction of the derivative integrals, one CTA per (atom, geometry)
+//   grad[g][A][x] = - sum_{mu in A, nu} <d_x mu|nu> OmS[mu,nu] + sum_{mu nu} dh[A,x][mu,nu] Pao[mu,nu]
+//                   - 1/2 sum_{m in A} sum_{bcd} (d_x m b|c d) W[(mb),(cd)] + grad_nuc[g][A][x]
+// int2e_ip1, the core-Hamiltonian derivative and int1e_ipovlp are read exactly once,
+// with >= 12 independent 8-byte loads in flight per thread.
+// ---------------------------------------------------------------------------
+constexpr int kStreamThreads = 256;
+
+__global__ void __launch_bounds__(kStreamThreads)
+grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const double* __restrict__ Wg,
+                   const double* __restrict__ OmS, const double* __restrict__ Pao,
+                   const double* __restrict__ ipovlp, const double* __restrict__ hcore_deriv,
+                   const double* __restrict__ eri_ip1, const double* __restrict__ grad_nuc,
+                   double* __restrict__ grad) {
+  extern __shared__ __align__(16) double sm[];
+  const int np = npair_of(n), n2 = n * n, n3 = n2 * n;
+  const int64_t n4 = static_cast<int64_t>(n3) * n;
+  double* Ws = sm;                 // [n][np]: rows (m, b) of W
+  double* Ps = Ws + n * np;        // [n2]
+  double* red = Ps + n2;           // [3][8]
+  unsigned short* pidx = reinterpret_cast<unsigned short*>(red + 24);
+  const int At = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
+  const int p0 = aoslices[2 * At], p1 = aoslices[2 * At + 1];
+  const double* W = Wg + static_cast<int64_t>(g) * np * np;
+  for (int k = tid; k < n2; k += kStreamThreads) {
+    const int i = k / n, j = k - i * n;
+    pidx[k] = static_cast<unsigned short>(i >= j ? tri_idx(i, j) : tri_idx(j, i));
+    Ps[k] = Pao[static_cast<int64_t>(g) * n2 + k];
+  }
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  const float inv_n2 = 1.0f / static_cast<float>(n2);
+  for (int m = p0; m < p1; ++m) {
+    __syncthreads();  // pidx ready / previous rows consumed
+    for (int k = tid; k < n * np; k += kStreamThreads) {
+      const int b = k / np, c = k - b * np;
+      Ws[k] = W[pidx[m * n + b] * np + c];
+    }
+    __syncthreads();
+    const double* r0 = eri_ip1 + static_cast<int64_t>(g) * 3 * n4 + static_cast<int64_t>(m) * n3;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
+    for (int e = tid; e < n3; e += kStreamThreads) {
+      const double v0 = __ldg(r0 + e), v1 = __ldg(r0 + n4 + e), v2 = __ldg(r0 + 2 * n4 + e);
+      int b = static_cast<int>((static_cast<float>(e) + 0.5f) * inv_n2);
+      int cd = e - b * n2;
+      if (cd < 0) { --b; cd += n2; } else if (cd >= n2) { ++b; cd -= n2; }
+      const double w = Ws[b * np + pidx[cd]];
+      s0 = fma(v0, w, s0);
+      s1 = fma(v1, w, s1);
+      s2 = fma(v2, w, s2);
+    }
+    a0 -= 0.5 * s0;
+    a1 -= 0.5 * s1;
+    a2 -= 0.5 * s2;
+  }
   {
-    const int n3 = n2 * n;
-    const int64_t n4 = static_cast<int64_t>(n3) * n;
-    const double* ip = eri_ip1 + static_cast<int64_t>(g) * 3 * n4;
-    const int seg = (n3 + kIpSeg - 1) / kIpSeg;
-    const float inv_n2 = 1.0f / static_cast<float>(n2);
-    for (int item = warp; item < n * kIpSeg; item += kWarps) {
-      const int m = item / kIpSeg, s = item - m * kIpSeg;
-      const int e0 = s * seg, e1 = min(n3, e0 + seg);
-      const double* r0 = ip + static_cast<int64_t>(m) * n3;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const double* hd = hcore_deriv + (static_cast<int64_t>(g) * natm + At) * 3 * n2;
 #pragma unroll 2
-      for (int e = e0 + lane; e < e1; e += 32) {
-        int b = static_cast<int>((static_cast<float>(e) + 0.5f) * inv_n2);
-        int cd = e - b * n2;
-        if (cd < 0) { --b; cd += n2; } else if (cd >= n2) { ++b; cd -= n2; }
-        const double w = B2[pidx[m * n + b] * pA + pidx[cd]];
-        a0 = fma(__ldg(r0 + e), w, a0);
-        a1 = fma(__ldg(r0 + n4 + e), w, a1);
-        a2 = fma(__ldg(r0 + 2 * n4 + e), w, a2);
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-      }
-      if (lane == 0) {
-        t2p[(0 * n + m) * kIpSeg + s] = a0;
-        t2p[(1 * n + m) * kIpSeg + s] = a1;
-        t2p[(2 * n + m) * kIpSeg + s] = a2;
-      }
+    for (int k = tid; k < n2; k += kStreamThreads) {
+      const double p = Ps[k];
+      a0 = fma(__ldg(hd + k), p, a0);
+      a1 = fma(__ldg(hd + n2 + k), p, a1);
+      a2 = fma(__ldg(hd + 2 * n2 + k), p, a2);
+    }
+    const double* ipo = ipovlp + static_cast<int64_t>(g) * 3 * n2;
+    const double* om = OmS + static_cast<int64_t>(g) * n2;
+    for (int k = p0 * n + tid; k < p1 * n; k += kStreamThreads) {
+      const double o = __ldg(om + k);
+      a0 = fma(-__ldg(ipo + k), o, a0);
+      a1 = fma(-__ldg(ipo + n2 + k), o, a1);
+      a2 = fma(-__ldg(ipo + 2 * n2 + k), o, a2);
     }
   }
+  // fixed-order block reduction
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane == 0) { red[warp] = a0; red[8 + warp] = a1; red[16 + warp] = a2; }
   __syncthreads();
-  // ---- grad[A][x] ----
-  for (int item = warp; item < natm * 3; item += kWarps) {
-    const int At = item / 3, xx = item - At * 3;
-    const int p0 = aoslices[2 * At], p1 = aoslices[2 * At + 1];
-    const double* ipo = ipovlp + (static_cast<int64_t>(g) * 3 + xx) * n2;
-    const double* hd = hcore_deriv + ((static_cast<int64_t>(g) * natm + At) * 3 + xx) * n2;
-    double a2 = 0.0;
-    for (int k = p0 * n + lane; k < p1 * n; k += 32) {
-      const int i = k / n, j = k - i * n;
-      a2 -= ipo[k] * (Z[i * ld + j] + Z[j * ld + i]);
-    }
-    for (int k = lane; k < n2; k += 32) {
-      const int i = k / n, j = k - i * n;
-      a2 += hd[k] * Bm[i * ld + j];
-    }
-    for (int m = p0 + lane; m < p1; m += 32) {
-      double t = 0.0;
+  if (tid < 3) {
+    double t = 0.0;
 #pragma unroll
-      for (int s = 0; s < kIpSeg; ++s) t += t2p[(xx * n + m) * kIpSeg + s];
-      a2 -= 0.5 * t;
-    }
-    for (int o = 16; o > 0; o >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    if (lane == 0) {
-      const int64_t o = (static_cast<int64_t>(g) * natm + At) * 3 + xx;
-      grad[o] = a2 + (grad_nuc ? grad_nuc[o] : 0.0);
-    }
+    for (int w = 0; w < kStreamThreads / 32; ++w) t += red[tid * 8 + w];
+    const int64_t o = (static_cast<int64_t>(g) * natm + At) * 3 + tid;
+    grad[o] = t + (grad_nuc ? grad_nuc[o] : 0.0);
   }
+}
+
+size_t grad_stream_smem_bytes(int n) {
+  return (static_cast<size_t>(n) * npair_of(n) + static_cast<size_t>(n) * n + 24) * sizeof(double) +
+         (static_cast<size_t>(n) * n * sizeof(unsigned short) + 15) / 16 * 16;
 }
 
 size_t grad_smem_bytes(int n) {
   const PGeom pg = pgeom(n);
-  return (2 * pg.szA + pg.szB + static_cast<size_t>(7) * n * (n + 1) + 2 * n + 3 * n * kIpSeg) * sizeof(double) +
+  return (2 * pg.szA + pg.szB + static_cast<size_t>(7) * n * (n + 1) + 2 * n) * sizeof(double) +
          table_bytes(n);
 }
 
@@ -625,7 +663,8 @@ int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const do
 int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices, const double* x,
                     const double* evals, const double* evecs, const double* hcore, const double* Tin,
                     const double* out7, const double* ipovlp, const double* hcore_deriv,
-                    const double* eri_ip1, const double* grad_nuc, double* grad) {
+                    const double* eri_ip1, const double* grad_nuc, double* Wg, double* OmS, double* Pao,
+                    double* grad) {
   EVC_REQUIRE(n >= 1 && n <= kPackedMaxNorb, "packed_grad: n=%d unsupported", n);
   const size_t smem = grad_smem_bytes(n);
   EVC_REQUIRE(smem <= ctx->smem_optin, "packed_grad: needs %zu bytes of shared memory", smem);
@@ -636,13 +675,19 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
     auto kern = packed_grad_kernel<MI>;                                                              \
     EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                         static_cast<int>(smem)));                                    \
-    kern<<<nbatch, kThreads, smem, ctx->stream>>>(n, natm, L8, aoslices, x, evals, evecs, hcore, Tin, \
-                                                  out7, ipovlp, hcore_deriv, eri_ip1, grad_nuc, grad); \
+    kern<<<nbatch, kThreads, smem, ctx->stream>>>(n, L8, x, evals, evecs, hcore, Tin, out7, Wg, OmS, Pao); \
   }
   if (mi <= 1) EVC_CASE(1) else if (mi <= 2) EVC_CASE(2) else if (mi <= 3) EVC_CASE(3)
   else if (mi <= 4) EVC_CASE(4) else EVC_CASE(5)
 #undef EVC_CASE
   EVC_CHECK_LAUNCH();
+  {
+    const size_t sm2 = grad_stream_smem_bytes(n);
+    dim3 grid(natm, nbatch);
+    grad_stream_kernel<<<grid, kStreamThreads, sm2, ctx->stream>>>(n, natm, aoslices, Wg, OmS, Pao, ipovlp,
+                                                                    hcore_deriv, eri_ip1, grad_nuc, grad);
+    EVC_CHECK_LAUNCH();
+  }
   return 0;
 }
 
@@ -716,7 +761,8 @@ int evc_energy_with_grad_packed_workspace_bytes(int N, int n, int natm, int nbat
   tot += evc_align_up(evc_rows_dot_ws_bytes(L8, P, nbatch), 256);
   tot += evc_align_up(evc_rows_axpy_ws_bytes(L8, P, nbatch), 256);
   if (n <= kPackedMaxNorb) {
-    tot += evc_align_up(G * np * np * 8, 256);     // T
+    tot += 2 * evc_align_up(G * np * np * 8, 256); // T, W
+    tot += 2 * evc_align_up(G * n2 * 8, 256);      // OmS, Pao
   } else {
     size_t gb = 0;
     int rc = evc_grad_workspace_bytes(n, natm, nbatch, &gb);
@@ -758,14 +804,17 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
   char* axpy_ws = ar.take<char>(axpy_b);
   EVC_REQUIRE(X && evecs && evals && hvec && out7 && Hp && w && E0 && C && dot_ws && axpy_ws,
               "evc_energy_with_grad_packed: workspace too small (%zu bytes)", workspace_bytes);
-  double *T = nullptr, *h1 = nullptr, *gamma = nullptr, *h2 = nullptr, *t3 = nullptr, *scratch = nullptr,
+  double *T = nullptr, *Wg = nullptr, *OmS = nullptr, *Pao = nullptr, *h1 = nullptr, *gamma = nullptr, *h2 = nullptr, *t3 = nullptr, *scratch = nullptr,
          *Gamma8 = nullptr;
   char* grad_ws = nullptr;
   size_t grad_b = 0;
   int rc;
   if (small) {
     T = ar.take<double>(G * np * np);
-    EVC_REQUIRE(T, "evc_energy_with_grad_packed: workspace too small (%zu bytes)", workspace_bytes);
+    Wg = ar.take<double>(G * np * np);
+    OmS = ar.take<double>(G * n2);
+    Pao = ar.take<double>(G * n2);
+    EVC_REQUIRE(T && Wg && OmS && Pao, "evc_energy_with_grad_packed: workspace too small (%zu bytes)", workspace_bytes);
   } else {
     if ((rc = evc_grad_workspace_bytes(n, natm, nbatch, &grad_b))) return rc;
     h1 = ar.take<double>(G * n2);
@@ -798,7 +847,7 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
   if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD))) return rc;
   if (small) {
     if ((rc = evc_packed_grad(ctx, nbatch, n, natm, ao->aoslices, X, evals, evecs, ao->hcore, T, out7, ao->ipovlp,
-                              ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad)))
+                              ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, Wg, OmS, Pao, grad)))
       return rc;
   } else {
     if ((rc = evc_packed_unpack_rdms(ctx, nbatch, n, out7, gamma, Gamma8))) return rc;
