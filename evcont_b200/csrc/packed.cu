@@ -25,15 +25,42 @@
 //
 // Algebra (derivation and numpy check: DESIGN.md section 4, tools/packed_proto.py):
 //   P0[AB, I] = X_ai X_bj + X_aj X_bi,  Q = diag(1/s_AB) P0,  s = 2 on diagonal pairs
-//   Gm[I, K]  = out7[tri(I,K)] * (I == K ? 2 : 1)   (symmetric np x np)
+//   Gm[I, K]  = out7[tri(I,K)]   (symmetric np x np; RG rows carry the diagonal pairs doubled)
 //   Y[a, i]   = 2 sum_{b j} X_bj s_(ij) U0[(ab), (ij)]
 //   -1/2 sum_{m in A} sum_{bcd} (d_x m b|c d) W[(mb), (cd)]   is the ERI-derivative term.
 #include "common.cuh"
 
+// Optional phase timing of the per-geometry kernels (development aid): build with
+// -DEVC_PHASE_TIMING, read with evc_debug_phase_clocks().
+#ifdef EVC_PHASE_TIMING
+__device__ long long g_evc_phase[4][24];
+#define EVC_PHASE(slot, idx)                                                             \
+  do {                                                                                   \
+    __syncthreads();                                                                     \
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 700))                       \
+      g_evc_phase[(slot) * 2 + (blockIdx.x ? 1 : 0)][idx] = clock64();                    \
+  } while (0)
+#define EVC_MARK(slot, idx, cond)                                                        \
+  do {                                                                                   \
+    if ((cond) && (threadIdx.x & 31) == 0 && (blockIdx.x == 0 || blockIdx.x == 700))      \
+      g_evc_phase[(slot) * 2 + (blockIdx.x ? 1 : 0)][idx] = clock64();                    \
+  } while (0)
+#else
+#define EVC_PHASE(slot, idx) do { } while (0)
+#define EVC_MARK(slot, idx, cond) do { } while (0)
+#endif
+
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_all() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+constexpr int kThreads = 256;      // K4p CTA
+constexpr int kGradThreads = 512;  // K8a CTA
 constexpr int kNJ = 4;  // 8x8 output tiles per warp work item (A fragment re-used kNJ times)
 
 __host__ __device__ inline int tri_idx(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
@@ -108,6 +135,7 @@ __global__ void pack8_stack_kernel(StackView sv, int64_t L8, const double* __res
     vh = 0.5 * sv.orbit_sum(a, b, i, j, k, l, I == K);
     vg = vh;
     if (a != b && sv.has_block(b, a)) vg = 0.5 * (vh + 0.5 * sv.orbit_sum(b, a, i, j, k, l, I == K));
+    if (I == K) vg *= 2.0;  // RG carries Gm directly: diagonal pair entries doubled
   }
   RH[static_cast<int64_t>(p) * L8 + col] = vh;
   RG[static_cast<int64_t>(p) * L8 + col] = vg;
@@ -150,7 +178,7 @@ __global__ void unpack_rdms_kernel(int n, int64_t L8, const double* __restrict__
   const int I = i >= j ? tri_idx(i, j) : tri_idx(j, i);
   const int K = k >= l ? tri_idx(k, l) : tri_idx(l, k);
   const int hi = I > K ? I : K, lo = I > K ? K : I;
-  const double s = (i == j ? 2.0 : 1.0) * (k == l ? 2.0 : 1.0) * (I == K ? 2.0 : 1.0);
+  const double s = (i == j ? 2.0 : 1.0) * (k == l ? 2.0 : 1.0);  // (the I == K factor is in RG)
   Gamma8[static_cast<int64_t>(g) * n4 + k4] = 0.25 * s * o[n2 + tri_idx(hi, lo)];
 }
 
@@ -195,47 +223,62 @@ __host__ __device__ inline PGeom pgeom(int n) {
   return g;
 }
 
-// accumulate C(M8*8 x N8*8) = A * B on the FP64 tensor cores; work item = (row tile,
-// group of kNJ column tiles), item `warp + kWarps*r` -> acc[r].
+// Work items of a CTA-level GEMM, C(M8*8 x N8*8) = A * B on the FP64 tensor cores:
+// item = (row tile, group of kNJ column tiles).  DMMA issue is per SM sub-partition
+// (warp % 4), so the host deals the items to warps such that the four sub-partitions
+// carry the same number of tiles (longest-processing-time greedy); the two
+// least-loaded warps also run the one-electron chain of K8a.
+constexpr int kMaxWarps = 16, kMaxSlots = 5;
+struct ItemMap {
+  signed char it[kMaxWarps][kMaxSlots];
+  unsigned char w1, w2;
+};
+
 template <int MAXI, typename LA, typename LB>
-__device__ __forceinline__ void gemm_acc(double (&acc)[MAXI][kNJ][2], int M8, int N8, int K4, bool lower,
-                                         LA la, LB lb) {
+__device__ __forceinline__ void gemm_acc(double (&acc)[MAXI][kNJ][2], const ItemMap& map, int M8, int N8, int K4,
+                                         bool lower, LA la, LB lb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int NG = (N8 + kNJ - 1) / kNJ;
-  const int nitems = M8 * NG;
 #pragma unroll
   for (int r = 0; r < MAXI; ++r) {
 #pragma unroll
     for (int j = 0; j < kNJ; ++j) acc[r][j][0] = acc[r][j][1] = 0.0;
-    const int it = warp + kWarps * r;
-    if (it >= nitems) continue;
+    const int it = map.it[warp][r];
+    if (it < 0) continue;
     const int mt = it / NG, nt0 = (it - mt * NG) * kNJ;
     int ntend = min(N8, nt0 + kNJ);
     if (lower) ntend = min(ntend, mt + 1);
     if (nt0 >= ntend) continue;
-    for (int k0 = 0; k0 < K4; k0 += 4) {
-      const double a = la(mt * 8 + g, k0 + tg);
+    // fragments of step k0 + 4 are fetched while the DMMAs of step k0 issue
+    double a = la(mt * 8 + g, tg), b[kNJ];
 #pragma unroll
-      for (int j = 0; j < kNJ; ++j) {
-        if (nt0 + j < ntend) {
-          const double b = lb(k0 + tg, (nt0 + j) * 8 + g);
-          dmma8x8x4(acc[r][j][0], acc[r][j][1], a, b);
-        }
-      }
+    for (int j = 0; j < kNJ; ++j) b[j] = (nt0 + j < ntend) ? lb(tg, (nt0 + j) * 8 + g) : 0.0;
+    for (int k0 = 0; k0 < K4; k0 += 4) {
+      const int k1 = (k0 + 4 < K4) ? k0 + 4 : k0;
+      const double an = la(mt * 8 + g, k1 + tg);
+      double bn[kNJ];
+#pragma unroll
+      for (int j = 0; j < kNJ; ++j) bn[j] = (nt0 + j < ntend) ? lb(k1 + tg, (nt0 + j) * 8 + g) : 0.0;
+#pragma unroll
+      for (int j = 0; j < kNJ; ++j)
+        if (nt0 + j < ntend) dmma8x8x4(acc[r][j][0], acc[r][j][1], a, b[j]);
+      a = an;
+#pragma unroll
+      for (int j = 0; j < kNJ; ++j) b[j] = bn[j];
     }
   }
 }
 
 // st(row, col, v0, v1): accumulator pair for (row, col) and (row, col + 1)
 template <int MAXI, typename ST>
-__device__ __forceinline__ void gemm_store(const double (&acc)[MAXI][kNJ][2], int M8, int N8, bool lower, ST st) {
+__device__ __forceinline__ void gemm_store(const double (&acc)[MAXI][kNJ][2], const ItemMap& map, int M8, int N8,
+                                           bool lower, ST st) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int NG = (N8 + kNJ - 1) / kNJ;
-  const int nitems = M8 * NG;
 #pragma unroll
   for (int r = 0; r < MAXI; ++r) {
-    const int it = warp + kWarps * r;
-    if (it >= nitems) continue;
+    const int it = map.it[warp][r];
+    if (it < 0) continue;
     const int mt = it / NG, nt0 = (it - mt * NG) * kNJ;
     int ntend = min(N8, nt0 + kNJ);
     if (lower) ntend = min(ntend, mt + 1);
@@ -246,8 +289,9 @@ __device__ __forceinline__ void gemm_store(const double (&acc)[MAXI][kNJ][2], in
 }
 
 // pair tables: pij[I] = i | j << 8 ; pidx[i*n + j] = pair index of (i, j)
+template <int NT>
 __device__ __forceinline__ void build_pair_tables(int n, unsigned short* pij, unsigned short* pidx) {
-  for (int k = threadIdx.x; k < n * n; k += kThreads) {
+  for (int k = threadIdx.x; k < n * n; k += NT) {
     const int i = k / n, j = k - i * n;
     const int I = i >= j ? tri_idx(i, j) : tri_idx(j, i);
     pidx[k] = static_cast<unsigned short>(I);
@@ -262,11 +306,12 @@ __host__ __device__ inline size_t table_bytes(int n) {
 // ---------------------------------------------------------------------------
 // K4p: one CTA per geometry
 // ---------------------------------------------------------------------------
-template <int MAXI>
+template <int MAXI, int NC>
 __global__ void __launch_bounds__(kThreads)
-packed_ao2oao_kernel(int n, int64_t L8, const double* __restrict__ x, const double* __restrict__ hcore,
+packed_ao2oao_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8, const double* __restrict__ x, const double* __restrict__ hcore,
                      const double* __restrict__ eri, double* __restrict__ hvec, double* __restrict__ Tout) {
   extern __shared__ __align__(16) double sm[];
+  const int n = NC > 0 ? NC : n_rt;  // compile-time orbital count for the common sizes
   const PGeom pg = pgeom(n);
   const int np = pg.np, pA = pg.pA, pB = pg.pB, ld = n + 1, n2 = n * n;
   const size_t szE = pg.szA > pg.szB ? pg.szA : pg.szB;
@@ -281,55 +326,84 @@ packed_ao2oao_kernel(int n, int64_t L8, const double* __restrict__ x, const doub
   const int64_t o2 = static_cast<int64_t>(g) * n2;
   const double* eg = eri + static_cast<int64_t>(g) * n2 * n2;
 
-  build_pair_tables(n, pij, pidx);
-  for (int k = tid; k < n2; k += kThreads) {
-    const int i = k / n, j = k - i * n;
-    Xs[i * ld + j] = x[o2 + k];
-    Hs[i * ld + j] = hcore[o2 + k];
-  }
-  for (int k = tid; k < static_cast<int>(szE); k += kThreads) Eb[k] = 0.0;
-  for (int k = tid; k < static_cast<int>(pg.szB); k += kThreads) Qb[k] = 0.0;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = kThreads / 32;
+  EVC_PHASE(0, 0);
+  // ---- asynchronous copies of this geometry's inputs first ----
+  // ERIp[AB][CD] = (ab|cd), a >= b, c >= d: rows of the full tensor, wanted elements only
+  build_pair_tables<kThreads>(n, pij, pidx);  // integer only (no FP64 sqrt: that pipe is the DMMA pipe)
   __syncthreads();
-  // ERIp[AB][CD] = (ab|cd), a >= b, c >= d: rows of the full tensor read contiguously
-  for (int k = tid; k < np * n2; k += kThreads) {
-    const int AB = k / n2, y = k - AB * n2;
-    const int c = y / n, d = y - c * n;
-    if (c < d) continue;
+  for (int AB = warp; AB < np; AB += NW) {
     const int a = pij[AB] & 0xff, b = pij[AB] >> 8;
-    Eb[AB * pA + pidx[y]] = eg[static_cast<int64_t>(a * n + b) * n2 + y];
+    const double* row = eg + static_cast<int64_t>(a * n + b) * n2;
+    double* dst = Eb + AB * pA;
+    for (int y = lane; y < n2; y += 32) {
+      const int c = y / n, d = y - c * n;
+      if (c >= d) cp_async8(dst + tri_idx(c, d), row + y);
+    }
   }
-  // Q[CD][K] = (X_ck X_dl + X_dk X_cl) / s_CD
-  for (int k = tid; k < np * np; k += kThreads) {
-    const int CD = k / np, K = k - CD * np;
-    const int c = pij[CD] & 0xff, d = pij[CD] >> 8, kk = pij[K] & 0xff, l = pij[K] >> 8;
-    const double v = Xs[c * ld + kk] * Xs[d * ld + l] + Xs[d * ld + kk] * Xs[c * ld + l];
-    Qb[CD * pB + K] = (c == d) ? 0.5 * v : v;
-  }
-  // h1 = X^T (hcore X)
   for (int k = tid; k < n2; k += kThreads) {
     const int i = k / n, j = k - i * n;
-    double acc = 0.0;
-    for (int r = 0; r < n; ++r) acc += Hs[i * ld + r] * Xs[r * ld + j];
-    Ts[i * ld + j] = acc;
+    cp_async8(Xs + i * ld + j, x + o2 + k);
+    cp_async8(Hs + i * ld + j, hcore + o2 + k);
+  }
+  cp_async_commit_all();
+  {
+    // zero padding of ERIp (A-type) and of Q (B-type); the data regions are filled below
+    const int padc = pA - np;
+    for (int k = tid; k < np * padc; k += kThreads) {
+      const int r = k / padc, c = np + (k - r * padc);
+      Eb[r * pA + c] = 0.0;
+    }
+    for (int k = np * pA + tid; k < static_cast<int>(szE); k += kThreads) Eb[k] = 0.0;
+    const int padq = pB - np;
+    for (int k = tid; k < np * padq; k += kThreads) {
+      const int r = k / padq, c = np + (k - r * padq);
+      Qb[r * pB + c] = 0.0;
+    }
+    for (int k = np * pB + tid; k < static_cast<int>(pg.szB); k += kThreads) Qb[k] = 0.0;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  EVC_PHASE(0, 1);
+  // Q[CD][K] = (X_ck X_dl + X_dk X_cl) / s_CD
+  for (int CD = warp; CD < np; CD += NW) {
+    const int c = pij[CD] & 0xff, d = pij[CD] >> 8;
+    const double sc = (c == d) ? 0.5 : 1.0;
+    for (int K = lane; K < np; K += 32) {
+      const int kk = pij[K] & 0xff, l = pij[K] >> 8;
+      Qb[CD * pB + K] = sc * (Xs[c * ld + kk] * Xs[d * ld + l] + Xs[d * ld + kk] * Xs[c * ld + l]);
+    }
+  }
+  // h1 = X^T (hcore X): first half
+  for (int k = tid; k < n2; k += kThreads) {
+    const int i = k / n, j = k - i * n;
+    double acc1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < (NC > 0 ? NC : n); ++r) acc1 += Hs[i * ld + r] * Xs[r * ld + j];
+    Ts[i * ld + j] = acc1;
   }
   __syncthreads();
+  EVC_PHASE(0, 2);
   double* hv = hvec + static_cast<int64_t>(g) * L8;
   for (int k = tid; k < n2; k += kThreads) {
     const int i = k / n, j = k - i * n;
-    double acc = 0.0;
-    for (int r = 0; r < n; ++r) acc += Xs[r * ld + i] * Ts[r * ld + j];
-    hv[k] = acc;
+    double acc1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < (NC > 0 ? NC : n); ++r) acc1 += Xs[r * ld + i] * Ts[r * ld + j];
+    hv[k] = acc1;
   }
   for (int64_t k = n2 + static_cast<int64_t>(np) * (np + 1) / 2 + tid; k < L8; k += kThreads) hv[k] = 0.0;
 
   double acc[MAXI][kNJ][2];
   // T = ERIp Q
-  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
+  gemm_acc<MAXI>(acc, mfull, pg.M8, pg.M8, pg.K4, false,
                  [&](int m, int k) { return Eb[m * pA + k]; },
                  [&](int k, int c) { return Qb[k * pB + c]; });
   __syncthreads();  // every warp is done reading ERIp: T may overwrite it
+  EVC_PHASE(0, 3);
   double* Tg = Tout + static_cast<int64_t>(g) * np * np;
-  gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+  gemm_store<MAXI>(acc, mfull, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
     if (m < pg.K4) {
       Eb[m * pB + c] = v0;
       Eb[m * pB + c + 1] = v1;
@@ -340,16 +414,18 @@ packed_ao2oao_kernel(int n, int64_t L8, const double* __restrict__ x, const doub
     }
   });
   __syncthreads();
+  EVC_PHASE(0, 4);
   // h2p = Q^T T, lower triangle only
-  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, true,
+  gemm_acc<MAXI>(acc, mlow, pg.M8, pg.M8, pg.K4, true,
                  [&](int m, int k) { return Qb[k * pB + m]; },
                  [&](int k, int c) { return Eb[k * pB + c]; });
-  gemm_store<MAXI>(acc, pg.M8, pg.M8, true, [&](int m, int c, double v0, double v1) {
+  gemm_store<MAXI>(acc, mlow, pg.M8, pg.M8, true, [&](int m, int c, double v0, double v1) {
     if (m < np) {
       if (c <= m) hv[n2 + tri_idx(m, c)] = v0;
       if (c + 1 <= m) hv[n2 + tri_idx(m, c + 1)] = v1;
     }
   });
+  EVC_PHASE(0, 5);
 }
 
 size_t ao2oao_smem_bytes(int n) {
@@ -361,15 +437,16 @@ size_t ao2oao_smem_bytes(int n) {
 // ---------------------------------------------------------------------------
 // K8p: one CTA per geometry
 // ---------------------------------------------------------------------------
-template <int MAXI>
-__global__ void __launch_bounds__(kThreads)
-packed_grad_kernel(int n, int64_t L8, const double* __restrict__ x, const double* __restrict__ evals,
+template <int MAXI, int NC>
+__global__ void __launch_bounds__(kGradThreads)
+packed_grad_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8, const double* __restrict__ x, const double* __restrict__ evals,
                    const double* __restrict__ evecs, const double* __restrict__ hcore,
                    const double* __restrict__ Tin, const double* __restrict__ out7,
                    double* __restrict__ Wout, double* __restrict__ OmSout, double* __restrict__ PaoOut) {
   extern __shared__ __align__(16) double sm[];
+  const int n = NC > 0 ? NC : n_rt;
   const PGeom pg = pgeom(n);
-  const int np = pg.np, pA = pg.pA, pB = pg.pB, ld = n + 1, n2 = n * n;
+  const int np = pg.np, pA = pg.pA, pB = pg.pB, ld = n | 1, n2 = n * n;  // odd pitch for the n x n matrices
   double* B1 = sm;               // T (A-type) -> P0 (A-type)
   double* B2 = B1 + pg.szA;      // Gm (A-type) -> W (A-type pitch)
   double* B3 = B2 + pg.szA;      // U0 (pitch pB) -> R (B-type), [K4][pB]
@@ -380,144 +457,219 @@ packed_grad_kernel(int n, int64_t L8, const double* __restrict__ x, const double
   double* Z = Gm1 + n * ld;
   double* A = Z + n * ld;
   double* Bm = A + n * ld;
-  double* rs = Bm + n * ld;      // sqrt(s) or 0
+  double* PaoS = Bm + n * ld;    // X gamma X^T
+  double* Qh = PaoS + n * ld;    // hcore X (gamma + gamma^T)
+  double* Gs = Qh + n * ld;      // divided differences of s^-1/2
+  double* rs = Gs + n * ld;      // sqrt(s) or 0
   double* sv = rs + n;           // s
+  double* Yp = B1;               // [n2][n] partial sums of Y over b (T is dead by then)
   unsigned short* pij = reinterpret_cast<unsigned short*>(sv + n);
   unsigned short* pidx = pij + np;
   const int g = blockIdx.x, tid = threadIdx.x;
   const int64_t o2 = static_cast<int64_t>(g) * n2;
   const double* o7 = out7 + static_cast<int64_t>(g) * L8;
+  constexpr int NT = kGradThreads;
 
-  build_pair_tables(n, pij, pidx);
-  for (int k = tid; k < n2; k += kThreads) {
-    const int i = k / n, j = k - i * n;
-    V[i * ld + j] = evecs[o2 + k];
-    X[i * ld + j] = x[o2 + k];
-    Hc[i * ld + j] = hcore[o2 + k];
-    Gm1[i * ld + j] = o7[k];
+  const int warp = tid >> 5, lane = tid & 31;
+  EVC_PHASE(1, 0);
+  // ---- all global inputs of this geometry as asynchronous copies, issued first ----
+  {
+    const double* Tg = Tin + static_cast<int64_t>(g) * np * np;
+    for (int r = warp; r < np; r += NT / 32) {
+      const int rr = r * (r + 1) / 2;
+      for (int c = lane; c < np; c += 32) {
+        cp_async8(B1 + r * pA + c, Tg + r * np + c);                                               // T
+        cp_async8(B2 + r * pA + c, o7 + n2 + (r >= c ? rr + c : c * (c + 1) / 2 + r));             // Gm = sym(out7)
+      }
+    }
+    for (int k = tid; k < n2; k += NT) {
+      const int i = k / n, j = k - i * n;
+      cp_async8(V + i * ld + j, evecs + o2 + k);
+      cp_async8(X + i * ld + j, x + o2 + k);
+      cp_async8(Hc + i * ld + j, hcore + o2 + k);
+      cp_async8(Gm1 + i * ld + j, o7 + k);
+    }
+    cp_async_commit_all();
   }
-  for (int k = tid; k < n; k += kThreads) {
+  build_pair_tables<NT>(n, pij, pidx);
+  for (int k = tid; k < n; k += NT) {
     const double s = evals[static_cast<int64_t>(g) * n + k];
     sv[k] = s;
     rs[k] = s > 1.0e-15 ? sqrt(s) : 0.0;
   }
-  for (int k = tid; k < static_cast<int>(pg.szA); k += kThreads) { B1[k] = 0.0; B2[k] = 0.0; }
-  __syncthreads();
   {
-    const double* Tg = Tin + static_cast<int64_t>(g) * np * np;
-    for (int k = tid; k < np * np; k += kThreads) {
-      const int r = k / np, c = k - r * np;
-      B1[r * pA + c] = Tg[k];
-      const int hi = r > c ? r : c, lo = r > c ? c : r;
-      const double v = o7[n2 + tri_idx(hi, lo)];
-      B2[r * pA + c] = (r == c) ? 2.0 * v : v;
+    // zero padding: columns [np, pA) of the data rows, and the rows [np, rows8)
+    const int padc = pA - np;
+    for (int k = tid; k < np * padc; k += NT) {
+      const int r = k / padc, c = np + (k - r * padc);
+      B1[r * pA + c] = 0.0;
+      B2[r * pA + c] = 0.0;
     }
+    for (int k = np * pA + tid; k < pg.rows8 * pA; k += NT) { B1[k] = 0.0; B2[k] = 0.0; }
   }
+  cp_async_wait_all();
   __syncthreads();
+  EVC_PHASE(1, 2);
+
+  // single-warp n x n product for the one-electron chain on the tensor cores (the FP64
+  // FMA pipe is the DMMA datapath: scalar DFMAs would queue behind the GEMM warps), run
+  // by a warp that has no (or little) GEMM work
+  auto warp_mm = [&](double* C, const double* P, bool tp, const double* Q, bool tq) {
+    const int gq = lane >> 2, tq4 = lane & 3;
+    const int n8 = (n + 7) >> 3, k4 = (n + 3) & ~3;
+    for (int mt = 0; mt < n8; ++mt)
+      for (int nt = 0; nt < n8; ++nt) {
+        double c0 = 0.0, c1 = 0.0;
+        const int row = mt * 8 + gq, col = nt * 8 + gq;
+        for (int k0 = 0; k0 < k4; k0 += 4) {
+          const int kk = k0 + tq4;
+          const double av = (row < n && kk < n) ? (tp ? P[kk * ld + row] : P[row * ld + kk]) : 0.0;
+          const double bv = (col < n && kk < n) ? (tq ? Q[col * ld + kk] : Q[kk * ld + col]) : 0.0;
+          dmma8x8x4(c0, c1, av, bv);
+        }
+        const int cc = nt * 8 + tq4 * 2;
+        if (row < n) {
+          if (cc < n) C[row * ld + cc] = c0;
+          if (cc + 1 < n) C[row * ld + cc + 1] = c1;
+        }
+      }
+    __syncwarp();
+  };
+  const int kW1 = mfull.w1, kW2 = mfull.w2;  // the chain warps (least GEMM work)
+
   double acc[MAXI][kNJ][2];
   // U0 = T Gm  (Gm symmetric: B(k, c) = Gm[c][k])
-  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
-                 [&](int m, int k) { return B1[m * pA + k]; },
-                 [&](int k, int c) { return B2[c * pA + k]; });
-  gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
-    if (m < pg.K4) {
-      B3[m * pB + c] = v0;
-      B3[m * pB + c + 1] = v1;
-    }
-  });
-  __syncthreads();
-  // Z = 1/2 Y,  Y[a,i] = 2 sum_{b j} X_bj s_(ij) U0[(ab),(ij)]
-  for (int k = tid; k < n2; k += kThreads) {
-    const int a = k / n, i = k - a * n;
-    double s = 0.0;
-    for (int b = 0; b < n; ++b) {
-      const double* urow = B3 + pidx[a * n + b] * pB;
-      for (int j = 0; j < n; ++j) {
-        const double u = urow[pidx[i * n + j]];
-        s += X[b * ld + j] * (i == j ? 2.0 * u : u);
+  gemm_acc<MAXI>(acc, mfull, pg.M8, pg.M8, pg.K4, false,
+                     [&](int m, int k) { return B1[m * pA + k]; },
+                     [&](int k, int c) { return B2[c * pA + k]; });
+  EVC_MARK(1, 12, warp == 0);
+  EVC_MARK(1, 13, warp == 5);
+  if (warp == kW2) {          // Pao = X gamma X^T  -> PaoS
+    warp_mm(A, X, false, Gm1, false);
+    warp_mm(PaoS, A, false, X, true);
+    // G_pq = -1/(sqrt(s_p) sqrt(s_q) (sqrt(s_p) + sqrt(s_q))), exact divided differences
+    for (int k = lane; k < n2; k += 32) {
+      const int p = k / n, q = k - p * n;
+      const double rp = rs[p], rq = rs[q];
+      double gpq = 0.0;
+      if (rp > 0.0 && rq > 0.0) {
+        gpq = -1.0 / (rp * rq * (rp + rq));
+      } else if ((rp > 0.0) != (rq > 0.0)) {
+        const double sp = sv[p], sq = sv[q];
+        if (sp != sq) gpq = ((rp > 0.0 ? 1.0 / rp : 0.0) - (rq > 0.0 ? 1.0 / rq : 0.0)) / (sp - sq);
       }
+      Gs[p * ld + q] = gpq;
     }
-    Z[a * ld + i] = s;
+    EVC_MARK(1, 14, true);
+  } else if (warp == kW1) {   // Qh = hcore X (gamma + gamma^T)
+    for (int k = lane; k < n2; k += 32) {
+      const int i = k / n, j = k - i * n;
+      Bm[i * ld + j] = Gm1[i * ld + j] + Gm1[j * ld + i];
+    }
+    __syncwarp();
+    warp_mm(Z, X, false, Bm, false);
+    warp_mm(Qh, Hc, false, Z, false);
+    EVC_MARK(1, 15, true);
   }
-  // P0[AB][I] = X_ai X_bj + X_aj X_bi  (overwrites T; U0 is complete)
-  for (int k = tid; k < np * np; k += kThreads) {
-    const int AB = k / np, I = k - AB * np;
-    const int a = pij[AB] & 0xff, b = pij[AB] >> 8, i = pij[I] & 0xff, j = pij[I] >> 8;
-    B1[AB * pA + I] = X[a * ld + i] * X[b * ld + j] + X[a * ld + j] * X[b * ld + i];
-  }
-  __syncthreads();
-  // R = Gm P0^T
-  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
-                 [&](int m, int k) { return B2[m * pA + k]; },
-                 [&](int k, int c) { return B1[c * pA + k]; });
-  gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+  gemm_store<MAXI>(acc, mfull, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
     if (m < pg.K4) {
       B3[m * pB + c] = v0;
       B3[m * pB + c + 1] = v1;
     }
   });
   __syncthreads();
-  // W = P0 R
-  gemm_acc<MAXI>(acc, pg.M8, pg.M8, pg.K4, false,
-                 [&](int m, int k) { return B1[m * pA + k]; },
-                 [&](int k, int c) { return B3[k * pB + c]; });
+  EVC_PHASE(1, 3);
+  // Yp[(a,i), b] = sum_j X_bj s_(ij) U0[(ab),(ij)];  Y = 2 sum_b Yp  (Yp overwrites T)
+  for (int t = tid; t < n2 * n; t += NT) {
+    const int ab = t / n, i = t - ab * n;   // lanes run over i: distinct words of one U0 row
+    const int a = ab / n, b = ab - a * n;
+    const double* urow = B3 + pidx[ab] * pB;
+    double sacc = 0.0;
+#pragma unroll
+    for (int j = 0; j < (NC > 0 ? NC : n); ++j) {
+      const double u = urow[pidx[i * n + j]];
+      sacc += X[b * ld + j] * (i == j ? 2.0 * u : u);
+    }
+    Yp[(a * n + i) * n + b] = sacc;
+  }
+  __syncthreads();
+  // Z = Y/2 + hcore X (gamma + gamma^T)
+  for (int k = tid; k < n2; k += NT) {
+    const int i = k / n, j = k - i * n;
+    double t = Qh[i * ld + j];
+#pragma unroll
+    for (int b = 0; b < (NC > 0 ? NC : n); ++b) t += Yp[k * n + b];
+    Z[i * ld + j] = t;
+  }
+  __syncthreads();
+  EVC_PHASE(1, 4);
+  // P0[AB][I] = X_ai X_bj + X_aj X_bi  (overwrites the Y partials)
+  for (int AB = warp; AB < np; AB += NT / 32) {
+    const int a = pij[AB] & 0xff, b = pij[AB] >> 8;
+    for (int I = lane; I < np; I += 32) {
+      const int i = pij[I] & 0xff, j = pij[I] >> 8;
+      B1[AB * pA + I] = X[a * ld + i] * X[b * ld + j] + X[a * ld + j] * X[b * ld + i];
+    }
+  }
+  {
+    // re-zero what the Y partials left in the padding of P0
+    const int padc = pA - np;
+    for (int k = tid; k < np * padc; k += NT) {
+      const int r = k / padc, c = np + (k - r * padc);
+      B1[r * pA + c] = 0.0;
+    }
+    for (int k = np * pA + tid; k < pg.rows8 * pA; k += NT) B1[k] = 0.0;
+  }
+  __syncthreads();
+  EVC_PHASE(1, 5);
+  // R = Gm P0^T
+  gemm_acc<MAXI>(acc, mfull, pg.M8, pg.M8, pg.K4, false,
+                     [&](int m, int k) { return B2[m * pA + k]; },
+                     [&](int k, int c) { return B1[c * pA + k]; });
+  EVC_MARK(1, 16, warp == 0);
+  EVC_MARK(1, 17, warp == 5);
+  if (warp == kW1) {  // Bm = G o (V^T Z V)
+    warp_mm(A, V, true, Z, false);
+    warp_mm(Bm, A, false, V, false);
+    for (int k = lane; k < n2; k += 32) {
+      const int p = k / n, q = k - p * n;
+      Bm[p * ld + q] *= Gs[p * ld + q];
+    }
+    __syncwarp();
+    EVC_MARK(1, 18, true);
+  }
+  // (every warp passed the barrier above after its last read of U0)
+  gemm_store<MAXI>(acc, mfull, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+    if (m < pg.K4) {
+      B3[m * pB + c] = v0;
+      B3[m * pB + c + 1] = v1;
+    }
+  });
+  __syncthreads();
+  EVC_PHASE(1, 6);
+  // W = P0 R  (symmetric: lower triangle only, the reader takes (max, min))
+  gemm_acc<MAXI>(acc, mlow, pg.M8, pg.M8, pg.K4, true,
+                     [&](int m, int k) { return B1[m * pA + k]; },
+                     [&](int k, int c) { return B3[k * pB + c]; });
+  if (warp == kW1) {  // Omega = V Bm V^T -> Z
+    warp_mm(A, V, false, Bm, false);
+    warp_mm(Z, A, false, V, true);
+  }
   {
     double* Wg = Wout + static_cast<int64_t>(g) * np * np;
-    gemm_store<MAXI>(acc, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
+    gemm_store<MAXI>(acc, mlow, pg.M8, pg.M8, true, [&](int m, int c, double v0, double v1) {
       if (m < np) {
         if (c < np) Wg[m * np + c] = v0;
         if (c + 1 < np) Wg[m * np + c + 1] = v1;
       }
     });
   }
-
-  // ---- one-electron adjoint (same algebra as one_el_adjoint_kernel, grad.cu) ----
-  auto matmul = [&](double* C, const double* P, bool tp, const double* Q, bool tq) {
-    for (int k = tid; k < n2; k += kThreads) {
-      const int i = k / n, j = k - i * n;
-      double a2 = 0.0;
-      for (int r = 0; r < n; ++r)
-        a2 += (tp ? P[r * ld + i] : P[i * ld + r]) * (tq ? Q[j * ld + r] : Q[r * ld + j]);
-      C[i * ld + j] = a2;
-    }
-    __syncthreads();
-  };
-  for (int k = tid; k < n2; k += kThreads) {
-    const int i = k / n, j = k - i * n;
-    Bm[i * ld + j] = Gm1[i * ld + j] + Gm1[j * ld + i];
-  }
-  __syncthreads();  // also publishes Z
-  matmul(A, X, false, Bm, false);    // A = X (gamma + gamma^T)
-  matmul(Bm, Hc, false, A, false);   // Bm = hcore A
-  for (int k = tid; k < n2; k += kThreads) {
-    const int i = k / n, j = k - i * n;
-    Z[i * ld + j] += Bm[i * ld + j];
-  }
   __syncthreads();
-  matmul(A, V, true, Z, false);      // A = V^T Z
-  matmul(Bm, A, false, V, false);    // Bm = V^T Z V
-  for (int k = tid; k < n2; k += kThreads) {
-    const int p = k / n, q = k - p * n;
-    const double rp = rs[p], rq = rs[q];
-    double gpq = 0.0;
-    if (rp > 0.0 && rq > 0.0) {
-      gpq = -1.0 / (rp * rq * (rp + rq));
-    } else if ((rp > 0.0) != (rq > 0.0)) {
-      const double sp = sv[p], sq = sv[q];
-      if (sp != sq) gpq = ((rp > 0.0 ? 1.0 / rp : 0.0) - (rq > 0.0 ? 1.0 / rq : 0.0)) / (sp - sq);
-    }
-    Bm[p * ld + q] *= gpq;
-  }
-  __syncthreads();
-  matmul(A, V, false, Bm, false);    // A = V B
-  matmul(Z, A, false, V, true);      // Z = Omega
-  matmul(A, X, false, Gm1, false);   // A = X gamma
-  matmul(Bm, A, false, X, true);     // Bm = X gamma X^T = Pao
-
-  for (int k = tid; k < n2; k += kThreads) {
+  EVC_PHASE(1, 7);
+  for (int k = tid; k < n2; k += NT) {
     const int i = k / n, j = k - i * n;
     OmSout[o2 + k] = Z[i * ld + j] + Z[j * ld + i];
-    PaoOut[o2 + k] = Bm[i * ld + j];
+    PaoOut[o2 + k] = PaoS[i * ld + j];
   }
 }
 
@@ -530,7 +682,15 @@ packed_grad_kernel(int n, int64_t L8, const double* __restrict__ x, const double
 // ---------------------------------------------------------------------------
 constexpr int kStreamThreads = 256;
 
-__global__ void __launch_bounds__(kStreamThreads)
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+
+// The three x/y/z rows (d_x m b|c d), m fixed, are contiguous runs of n^3 doubles: they are
+// staged in shared memory with asynchronous 16-byte copies (no register staging, so 7-8 CTAs
+// of ~27 KB in flight per SM), issued before anything that has to wait.
+__global__ void __launch_bounds__(kStreamThreads, 6)
 grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const double* __restrict__ Wg,
                    const double* __restrict__ OmS, const double* __restrict__ Pao,
                    const double* __restrict__ ipovlp, const double* __restrict__ hcore_deriv,
@@ -538,61 +698,113 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
                    double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   const int np = npair_of(n), n2 = n * n, n3 = n2 * n;
+  const int n3p = (n3 + 1) & ~1, n2p = (n2 + 1) & ~1;
   const int64_t n4 = static_cast<int64_t>(n3) * n;
-  double* Ws = sm;                 // [n][np]: rows (m, b) of W
-  double* Ps = Ws + n * np;        // [n2]
-  double* red = Ps + n2;           // [3][8]
+  double* stage = sm;                    // [3][n3p]  int2e_ip1 rows of the current m
+  double* hds = stage + 3 * n3p;         // [3][n2p]  d hcore / d(A, x)
+  double* Ws = hds + 3 * n2p;            // [n][np]   rows (m, b) of W
+  double* red = Ws + n * np;             // [3][8]
   unsigned short* pidx = reinterpret_cast<unsigned short*>(red + 24);
   const int At = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
   const int p0 = aoslices[2 * At], p1 = aoslices[2 * At + 1];
   const double* W = Wg + static_cast<int64_t>(g) * np * np;
+  const double* ipg = eri_ip1 + static_cast<int64_t>(g) * 3 * n4;
+  const double* hd = hcore_deriv + (static_cast<int64_t>(g) * natm + At) * 3 * n2;
+  const bool vec = ((n3 & 1) == 0);      // rows start 16-byte aligned iff n^3 is even
+
+  auto issue_rows = [&](int m) {
+    const double* r0 = ipg + static_cast<int64_t>(m) * n3;
+    if (vec) {
+      for (int e = 2 * tid; e < n3; e += 2 * kStreamThreads) {
+        cp_async16(stage + e, r0 + e);
+        cp_async16(stage + n3p + e, r0 + n4 + e);
+        cp_async16(stage + 2 * n3p + e, r0 + 2 * n4 + e);
+      }
+    } else {
+      for (int e = tid; e < n3; e += kStreamThreads) {
+        cp_async8(stage + e, r0 + e);
+        cp_async8(stage + n3p + e, r0 + n4 + e);
+        cp_async8(stage + 2 * n3p + e, r0 + 2 * n4 + e);
+      }
+    }
+  };
+  // rows (m, b), b < n, of W (stored as its lower triangle); pair index computed, not looked up,
+  // so the copies can be issued before any table exists
+  auto issue_w = [&](int m) {
+    for (int b = tid >> 5; b < n; b += kStreamThreads / 32) {
+      const int r = m >= b ? tri_idx(m, b) : tri_idx(b, m);
+      for (int c = tid & 31; c < np; c += 32) cp_async8(Ws + b * np + c, W + (r > c ? r * np + c : c * np + r));
+    }
+  };
+  if (p0 < p1) {
+    issue_rows(p0);
+    issue_w(p0);
+  }
+  for (int k = tid; k < n2; k += kStreamThreads) {
+    cp_async8(hds + k, hd + k);
+    cp_async8(hds + n2p + k, hd + n2 + k);
+    cp_async8(hds + 2 * n2p + k, hd + 2 * n2 + k);
+  }
+  cp_async_commit_all();
+
   for (int k = tid; k < n2; k += kStreamThreads) {
     const int i = k / n, j = k - i * n;
     pidx[k] = static_cast<unsigned short>(i >= j ? tri_idx(i, j) : tri_idx(j, i));
-    Ps[k] = Pao[static_cast<int64_t>(g) * n2 + k];
   }
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  {  // overlap term: - sum_{mu in A, nu} <d_x mu|nu> OmS[mu,nu]
+    const double* ipo = ipovlp + static_cast<int64_t>(g) * 3 * n2;
+    const double* om = OmS + static_cast<int64_t>(g) * n2;
+    for (int k = p0 * n + tid; k < p1 * n; k += kStreamThreads) {
+      const double i0 = __ldg(ipo + k), i1 = __ldg(ipo + n2 + k), i2 = __ldg(ipo + 2 * n2 + k), o = __ldg(om + k);
+      a0 = fma(-i0, o, a0);
+      a1 = fma(-i1, o, a1);
+      a2 = fma(-i2, o, a2);
+    }
+  }
   const float inv_n2 = 1.0f / static_cast<float>(n2);
   for (int m = p0; m < p1; ++m) {
-    __syncthreads();  // pidx ready / previous rows consumed
-    for (int k = tid; k < n * np; k += kStreamThreads) {
-      const int b = k / np, c = k - b * np;
-      Ws[k] = W[pidx[m * n + b] * np + c];
+    if (m > p0) {
+      __syncthreads();  // Ws and stage of the previous m consumed
+      issue_rows(m);
+      issue_w(m);
+      cp_async_commit_all();
     }
+    cp_async_wait_all();
     __syncthreads();
-    const double* r0 = eri_ip1 + static_cast<int64_t>(g) * 3 * n4 + static_cast<int64_t>(m) * n3;
+    if (m == p0) {  // core-Hamiltonian derivative term (staged with the first rows)
+      const double* pa = Pao + static_cast<int64_t>(g) * n2;
+      for (int k = tid; k < n2; k += kStreamThreads) {
+        const double p = __ldg(pa + k);
+        a0 = fma(hds[k], p, a0);
+        a1 = fma(hds[n2p + k], p, a1);
+        a2 = fma(hds[2 * n2p + k], p, a2);
+      }
+    }
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll 4
+#pragma unroll 2
     for (int e = tid; e < n3; e += kStreamThreads) {
-      const double v0 = __ldg(r0 + e), v1 = __ldg(r0 + n4 + e), v2 = __ldg(r0 + 2 * n4 + e);
       int b = static_cast<int>((static_cast<float>(e) + 0.5f) * inv_n2);
       int cd = e - b * n2;
       if (cd < 0) { --b; cd += n2; } else if (cd >= n2) { ++b; cd -= n2; }
       const double w = Ws[b * np + pidx[cd]];
-      s0 = fma(v0, w, s0);
-      s1 = fma(v1, w, s1);
-      s2 = fma(v2, w, s2);
+      s0 = fma(stage[e], w, s0);
+      s1 = fma(stage[n3p + e], w, s1);
+      s2 = fma(stage[2 * n3p + e], w, s2);
     }
     a0 -= 0.5 * s0;
     a1 -= 0.5 * s1;
     a2 -= 0.5 * s2;
   }
-  {
-    const double* hd = hcore_deriv + (static_cast<int64_t>(g) * natm + At) * 3 * n2;
-#pragma unroll 2
+  if (p0 >= p1) {  // atom without basis functions: only the core-Hamiltonian derivative term
+    cp_async_wait_all();
+    __syncthreads();
+    const double* pa = Pao + static_cast<int64_t>(g) * n2;
     for (int k = tid; k < n2; k += kStreamThreads) {
-      const double p = Ps[k];
-      a0 = fma(__ldg(hd + k), p, a0);
-      a1 = fma(__ldg(hd + n2 + k), p, a1);
-      a2 = fma(__ldg(hd + 2 * n2 + k), p, a2);
-    }
-    const double* ipo = ipovlp + static_cast<int64_t>(g) * 3 * n2;
-    const double* om = OmS + static_cast<int64_t>(g) * n2;
-    for (int k = p0 * n + tid; k < p1 * n; k += kStreamThreads) {
-      const double o = __ldg(om + k);
-      a0 = fma(-__ldg(ipo + k), o, a0);
-      a1 = fma(-__ldg(ipo + n2 + k), o, a1);
-      a2 = fma(-__ldg(ipo + 2 * n2 + k), o, a2);
+      const double p = __ldg(pa + k);
+      a0 = fma(hds[k], p, a0);
+      a1 = fma(hds[n2p + k], p, a1);
+      a2 = fma(hds[2 * n2p + k], p, a2);
     }
   }
   // fixed-order block reduction
@@ -614,20 +826,67 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
 }
 
 size_t grad_stream_smem_bytes(int n) {
-  return (static_cast<size_t>(n) * npair_of(n) + static_cast<size_t>(n) * n + 24) * sizeof(double) +
-         (static_cast<size_t>(n) * n * sizeof(unsigned short) + 15) / 16 * 16;
+  const size_t n2 = static_cast<size_t>(n) * n, n3 = n2 * n;
+  return (3 * ((n3 + 1) & ~static_cast<size_t>(1)) + 3 * ((n2 + 1) & ~static_cast<size_t>(1)) +
+          static_cast<size_t>(n) * npair_of(n) + 24) * sizeof(double) +
+         (n2 * sizeof(unsigned short) + 15) / 16 * 16;
 }
 
 size_t grad_smem_bytes(int n) {
   const PGeom pg = pgeom(n);
-  return (2 * pg.szA + pg.szB + static_cast<size_t>(7) * n * (n + 1) + 2 * n) * sizeof(double) +
+  return (2 * pg.szA + pg.szB + static_cast<size_t>(10) * n * (n | 1) + 2 * n) * sizeof(double) +
          table_bytes(n);
 }
 
-int maxi_for(int n) {
+int maxi_for(int n, int nthreads) {
   const PGeom pg = pgeom(n);
   const int nitems = pg.M8 * ((pg.M8 + kNJ - 1) / kNJ);
-  return (nitems + kWarps - 1) / kWarps;
+  const int warps = nthreads / 32;
+  return (nitems + warps - 1) / warps;
+}
+
+// deal the GEMM items to warps so that the four SM sub-partitions (warp % 4) carry equal tile counts
+ItemMap build_item_map(int n, int nthreads, bool lower) {
+  const PGeom pg = pgeom(n);
+  const int M8 = pg.M8, NG = (M8 + kNJ - 1) / kNJ, nitems = M8 * NG, warps = nthreads / 32;
+  const int slots = (nitems + warps - 1) / warps;
+  ItemMap m;
+  for (int w = 0; w < kMaxWarps; ++w)
+    for (int r = 0; r < kMaxSlots; ++r) m.it[w][r] = -1;
+  int size[256], order[256];
+  for (int it = 0; it < nitems; ++it) {
+    const int mt = it / NG, nt0 = (it % NG) * kNJ;
+    int ntend = nt0 + kNJ < M8 ? nt0 + kNJ : M8;
+    if (lower && ntend > mt + 1) ntend = mt + 1;
+    size[it] = ntend > nt0 ? ntend - nt0 : 0;
+    order[it] = it;
+  }
+  for (int i = 0; i < nitems; ++i)  // selection sort, largest first (stable)
+    for (int j = i + 1; j < nitems; ++j)
+      if (size[order[j]] > size[order[i]]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+  int wload[kMaxWarps] = {0}, wcount[kMaxWarps] = {0}, sload[4] = {0};
+  for (int q = 0; q < nitems; ++q) {
+    const int it = order[q];
+    int best = -1;
+    for (int w = 0; w < warps; ++w) {
+      if (wcount[w] >= slots) continue;
+      if (best < 0) { best = w; continue; }
+      const int sb = sload[best & 3], sw = sload[w & 3];
+      if (sw < sb || (sw == sb && wload[w] < wload[best])) best = w;
+    }
+    m.it[best][wcount[best]++] = static_cast<signed char>(it);
+    wload[best] += size[it];
+    sload[best & 3] += size[it];
+  }
+  int w1 = warps - 1, w2 = warps > 1 ? warps - 2 : 0;
+  for (int w = warps - 1; w >= 0; --w)
+    if (wload[w] < wload[w1]) w1 = w;
+  w2 = (w1 == warps - 1) ? (warps > 1 ? warps - 2 : 0) : warps - 1;
+  for (int w = warps - 1; w >= 0; --w)
+    if (w != w1 && wload[w] < wload[w2]) w2 = w;
+  m.w1 = static_cast<unsigned char>(w1);
+  m.w2 = static_cast<unsigned char>(w2);
+  return m;
 }
 
 __global__ void add_enuc_kernel_p(int G, const double* __restrict__ e0, const double* __restrict__ e_nuc,
@@ -645,16 +904,19 @@ int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const do
   const size_t smem = ao2oao_smem_bytes(n);
   EVC_REQUIRE(smem <= ctx->smem_optin, "packed_ao2oao: needs %zu bytes of shared memory", smem);
   const int64_t L8 = packed_len(n);
-  const int mi = maxi_for(n);
-#define EVC_CASE(MI)                                                                                 \
+  const int mi = maxi_for(n, kThreads);
+  const ItemMap mf = build_item_map(n, kThreads, false), ml = build_item_map(n, kThreads, true);
+#define EVC_CASE(MI, NCV)                                                                            \
   {                                                                                                  \
-    auto kern = packed_ao2oao_kernel<MI>;                                                            \
+    auto kern = packed_ao2oao_kernel<MI, NCV>;                                                       \
     EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                         static_cast<int>(smem)));                                    \
-    kern<<<nbatch, kThreads, smem, ctx->stream>>>(n, L8, x, hcore, eri, hvec, Tout);                 \
+    kern<<<nbatch, kThreads, smem, ctx->stream>>>(mf, ml, n, L8, x, hcore, eri, hvec, Tout);                 \
   }
-  if (mi <= 1) EVC_CASE(1) else if (mi <= 2) EVC_CASE(2) else if (mi <= 3) EVC_CASE(3)
-  else if (mi <= 4) EVC_CASE(4) else EVC_CASE(5)
+  // compile-time orbital counts for the benchmark systems (H6, H10, H2O/6-31G), generic otherwise
+  if (n == 6) EVC_CASE(1, 6) else if (n == 10) EVC_CASE(2, 10) else if (n == 13) EVC_CASE(5, 13)
+  else if (mi <= 1) EVC_CASE(1, 0) else if (mi <= 2) EVC_CASE(2, 0) else if (mi <= 3) EVC_CASE(3, 0)
+  else if (mi <= 4) EVC_CASE(4, 0) else EVC_CASE(5, 0)
 #undef EVC_CASE
   EVC_CHECK_LAUNCH();
   return 0;
@@ -669,20 +931,25 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
   const size_t smem = grad_smem_bytes(n);
   EVC_REQUIRE(smem <= ctx->smem_optin, "packed_grad: needs %zu bytes of shared memory", smem);
   const int64_t L8 = packed_len(n);
-  const int mi = maxi_for(n);
-#define EVC_CASE(MI)                                                                                 \
+  const int mi = maxi_for(n, kGradThreads);
+  const ItemMap mf = build_item_map(n, kGradThreads, false), ml = build_item_map(n, kGradThreads, true);
+#define EVC_CASE(MI, NCV)                                                                            \
   {                                                                                                  \
-    auto kern = packed_grad_kernel<MI>;                                                              \
+    auto kern = packed_grad_kernel<MI, NCV>;                                                         \
     EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                         static_cast<int>(smem)));                                    \
-    kern<<<nbatch, kThreads, smem, ctx->stream>>>(n, L8, x, evals, evecs, hcore, Tin, out7, Wg, OmS, Pao); \
+    kern<<<nbatch, kGradThreads, smem, ctx->stream>>>(mf, ml, n, L8, x, evals, evecs, hcore, Tin, out7, Wg, OmS, Pao); \
   }
-  if (mi <= 1) EVC_CASE(1) else if (mi <= 2) EVC_CASE(2) else if (mi <= 3) EVC_CASE(3)
-  else if (mi <= 4) EVC_CASE(4) else EVC_CASE(5)
+  if (n == 6) EVC_CASE(1, 6) else if (n == 10) EVC_CASE(1, 10) else if (n == 13) EVC_CASE(3, 13)
+  else if (mi <= 1) EVC_CASE(1, 0) else if (mi <= 2) EVC_CASE(2, 0) else EVC_CASE(3, 0)
 #undef EVC_CASE
   EVC_CHECK_LAUNCH();
   {
     const size_t sm2 = grad_stream_smem_bytes(n);
+    EVC_CHECK_CUDA(cudaFuncSetAttribute(grad_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(sm2)));
+    EVC_CHECK_CUDA(cudaFuncSetAttribute(grad_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     dim3 grid(natm, nbatch);
     grad_stream_kernel<<<grid, kStreamThreads, sm2, ctx->stream>>>(n, natm, aoslices, Wg, OmS, Pao, ipovlp,
                                                                     hcore_deriv, eri_ip1, grad_nuc, grad);
@@ -718,6 +985,17 @@ int evc_packed_pair_weights(evc_ctx* ctx, int nbatch, int N, const double* C, in
 
 // ---- C ABI ---------------------------------------------------------------------
 extern "C" {
+
+// development aid: phase clocks of the per-geometry kernels (zeros unless built with
+// -DEVC_PHASE_TIMING); out: [4][24] int64
+int evc_debug_phase_clocks(long long* out_host) {
+#ifdef EVC_PHASE_TIMING
+  EVC_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_evc_phase, sizeof(long long) * 4 * 24));
+#else
+  for (int i = 0; i < 4 * 24; ++i) out_host[i] = 0;
+#endif
+  return 0;
+}
 
 int64_t evc_packed_row_len(int n) { return n >= 1 ? packed_len(n) : -1; }
 
