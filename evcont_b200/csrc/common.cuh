@@ -13,7 +13,8 @@ enum {
   EVC_STAGE_SUBSPACE_H,
   EVC_STAGE_GENEIG,
   EVC_STAGE_PREDICT,
-  EVC_STAGE_GRAD,
+  EVC_STAGE_GRAD,         // K8 (full path) / K8a: per-geometry GEMMs of the gradient (packed path)
+  EVC_STAGE_GRAD_STREAM,  // K8b: streaming contraction of the derivative integrals (packed path)
   EVC_NSTAGE
 };
 

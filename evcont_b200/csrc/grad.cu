@@ -379,6 +379,7 @@ int evc_energy_with_grad(evc_ctx* ctx, int layout, int N, int n, int natm, const
   if ((rc = grad_elec_impl(ctx, nbatch, n, natm, ao->aoslices, evals, evecs, X, ao->hcore, t3, gamma, Gamma,
                            ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b)))
     return rc;
+  if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM))) return rc;
   add_enuc_kernel<<<(nbatch + 127) / 128, 128, 0, ctx->stream>>>(nbatch, E0, ao->e_nuc, E);
   EVC_CHECK_LAUNCH();
   return evc_stage_mark(ctx, EVC_NSTAGE);

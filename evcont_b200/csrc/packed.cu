@@ -945,6 +945,8 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
 #undef EVC_CASE
   EVC_CHECK_LAUNCH();
   {
+    int rcm = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM);
+    if (rcm) return rcm;
     const size_t sm2 = grad_stream_smem_bytes(n);
     EVC_CHECK_CUDA(cudaFuncSetAttribute(grad_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(sm2)));
@@ -1133,6 +1135,7 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
                                  ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b)))
       return rc;
   }
+  if (!small && (rc = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM))) return rc;
   add_enuc_kernel_p<<<(nbatch + 127) / 128, 128, 0, ctx->stream>>>(nbatch, E0, ao->e_nuc, E);
   EVC_CHECK_LAUNCH();
   return evc_stage_mark(ctx, EVC_NSTAGE);

@@ -70,7 +70,7 @@ class Engine:
                                    device=self.device)
         return self._ws
 
-    STAGES = ("loewdin", "ao2oao", "subspace_H", "geneig", "predict_rdm", "grad")
+    STAGES = ("loewdin", "ao2oao", "subspace_H", "geneig", "predict_rdm", "grad", "grad_stream")
 
     def launch_count(self):
         """Kernel launches issued by the library so far (process-wide)."""

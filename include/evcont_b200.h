@@ -56,10 +56,11 @@ int evc_ctx_sm_count(const evc_ctx *ctx);
 unsigned long long evc_launch_count(void);
 /* Per-stage device timing of evc_energy_with_grad (CUDA events on the ctx
  * stream; stages: 0 Loewdin, 1 AO->OAO, 2 subspace H, 3 eigensolve, 4 predicted
- * RDMs, 5 gradient).  evc_ctx_stage_timing(ctx, 1) resets and enables the
+ * RDMs, 5 gradient (packed step: its per-geometry GEMM kernel), 6 streaming
+ * contraction of the derivative integrals (packed step only).  evc_ctx_stage_timing(ctx, 1) resets and enables the
  * accumulators; evc_ctx_stage_times synchronises on the last call's events and
  * returns the accumulated milliseconds per stage and the number of calls. */
-#define EVC_NUM_STAGES 6
+#define EVC_NUM_STAGES 7
 int evc_ctx_stage_timing(evc_ctx *ctx, int enable);
 int evc_ctx_stage_times(evc_ctx *ctx, double *ms /* [EVC_NUM_STAGES] */, int64_t *calls);
 
