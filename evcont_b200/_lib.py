@@ -99,6 +99,13 @@ SIGNATURES = {
                                                    c_double_p, c_double_p, c_double_p, C.c_int,
                                                    C.POINTER(AoBundle), C.c_void_p, C.c_void_p,
                                                    C.c_int, C.c_void_p, C.c_size_t]),
+    "evc_sbasis_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "evc_sbasis_destroy": (C.c_int, [C.c_void_p]),
+    "evc_sbasis_nao": (C.c_int, [C.c_void_p]),
+    "evc_sbasis_natm": (C.c_int, [C.c_void_p]),
+    "evc_sbasis_aoslices": (C.c_void_p, [C.c_void_p]),
+    "evc_ao_integrals_s": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9),
 }
 
 _lib = None

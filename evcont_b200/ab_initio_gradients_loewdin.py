@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from .engine import DeviceAO, HostAO, get_engine
-from .mol import ao_bundle
+from .mol import MolLite, ao_bundle
 from .stackcache import as_device_stack
 
 
@@ -63,7 +63,13 @@ def get_one_el_grad_ao(mol):
 
 def _device_inputs(mol, one_RDM, two_RDM, S):
     stack = as_device_stack(one_RDM, two_RDM, S)
-    ao = DeviceAO.from_bundles(stack.engine, [ao_bundle(mol)])
+    if isinstance(mol, MolLite):
+        # integrals on the device straight from the coordinates (K9): nothing but
+        # natm x 3 doubles crosses PCIe
+        eng = stack.engine
+        ao = eng.ao_integrals(mol.sbasis(eng), mol.atom_coords()[None])
+    else:
+        ao = DeviceAO.from_bundles(stack.engine, [ao_bundle(mol)])
     return stack, ao
 
 
@@ -117,3 +123,15 @@ def get_energy_with_grad_batch(mols, one_RDM, two_RDM, S, return_density_matrice
     ao = DeviceAO.from_bundles(stack.engine, bundles)
     E, grad, gamma, Gamma, _ = stack.engine.energy_with_grad(stack, ao, want_rdms=True)
     return E.cpu().numpy(), grad.cpu().numpy(), gamma.cpu().numpy(), Gamma.cpu().numpy()
+
+
+def get_energy_with_grad_coords(mol, coords, one_RDM, two_RDM, S):
+    """The step for many geometries of one molecule given as coordinates only:
+    ``mol`` (:class:`evcont_b200.mol.MolLite`) fixes atoms and basis, ``coords`` is
+    ``(G, natm, 3)`` in bohr.  Integrals (K9) and prediction (K3..K8) run on the device;
+    returns ``(E[G], grad[G, natm, 3])`` as numpy arrays."""
+    stack = as_device_stack(one_RDM, two_RDM, S)
+    eng = stack.engine
+    coords = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1, mol.natm, 3)
+    E, grad, _, _, _ = eng.energy_with_grad_coords(stack, mol.sbasis(eng), coords)
+    return E.cpu().numpy(), grad.cpu().numpy()

@@ -210,12 +210,14 @@ __host__ __device__ inline PGeom pgeom(int n) {
   g.M8 = (g.np + 7) / 8;
   g.rows8 = g.M8 * 8;
   g.K4 = (g.np + 3) & ~3;
-  // A-type access (lane (g,tg) reads [row g][col tg]): pitch == 4 (mod 8) is conflict-free;
-  // B-type access ([row tg][col g]): pitch == 8 (mod 16).
+  // 8-byte shared-memory loads are served one half-warp (lanes 0-15: g = 0..3, tg = 0..3) at a
+  // time over 16 double-wide banks.  A-type access (lane (g,tg) reads [row g][col tg], word
+  // g*pitch + tg) and B-type access ([row tg][col g], word tg*pitch + g) are both conflict-free
+  // when pitch == 4 (mod 8): the four row offsets land on banks {0,4,8,12}.
   int pa = g.K4;
   while ((pa & 7) != 4) ++pa;
   int pb = g.rows8;
-  while ((pb & 15) != 8) ++pb;
+  while ((pb & 7) != 4) ++pb;
   g.pA = pa;
   g.pB = pb;
   g.szA = static_cast<size_t>(g.rows8) * pa;

@@ -55,6 +55,7 @@ class Engine:
         self._ctx = handle
         self.sm_count = self.lib.evc_ctx_sm_count(handle)
         self._links = {}
+        self._sbases = {}
         self._ws = None
 
     # -- plumbing ------------------------------------------------------------
@@ -250,6 +251,35 @@ class Engine:
                                      _ptr(ws), ws.numel()))
         return grad
 
+    # -- K9 --------------------------------------------------------------------------------
+    def sbasis(self, symbols, basis):
+        """Device handle (:class:`SBasis`) of an s-shell basis for the atoms ``symbols``."""
+        key = (tuple(s.capitalize() for s in symbols), basis.lower())
+        if key not in self._sbases:
+            self._sbases[key] = SBasis(self, symbols, basis)
+        return self._sbases[key]
+
+    def ao_integrals(self, sbasis, coords, out=None):
+        """AO integrals of a batch of geometries on the device: ``coords`` (G, natm, 3) in
+        bohr (device tensor or numpy) -> :class:`DeviceAO` (filled in place if given)."""
+        coords = self.to_device(coords).reshape(-1, sbasis.natm, 3)
+        G = coords.shape[0]
+        ao = out if out is not None else DeviceAO(self, G, sbasis.nao, sbasis.natm, sbasis.aoslices_host)
+        if ao.nbatch != G or ao.nao != sbasis.nao or ao.natm != sbasis.natm:
+            raise ValueError("DeviceAO does not match the basis / batch size")
+        self._bind_stream()
+        check(self.lib.evc_ao_integrals_s(self._ctx, sbasis.handle, G, _ptr(coords), _ptr(ao.ovlp),
+                                          _ptr(ao.hcore), _ptr(ao.eri), _ptr(ao.ipovlp),
+                                          _ptr(ao.hcore_deriv), _ptr(ao.eri_ip1), _ptr(ao.e_nuc),
+                                          _ptr(ao.grad_nuc)))
+        return ao
+
+    def energy_with_grad_coords(self, stack, sbasis, coords, ao=None, out=None, want_rdms=False):
+        """The whole MD step from nuclear coordinates: K9 (integrals) then K3..K8.
+        ``coords`` (G, natm, 3) bohr.  Same return value as :meth:`energy_with_grad`."""
+        ao = self.ao_integrals(sbasis, coords, out=ao)
+        return self.energy_with_grad(stack, ao, want_rdms=want_rdms, out=out)
+
     # -- fused step ------------------------------------------------------------------------
     def energy_with_grad(self, stack, ao, want_rdms=False, out=None, packed=None):
         """One prediction step for a batch of geometries resident on the device.
@@ -329,6 +359,40 @@ class Engine:
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
         return host_ao.E, host_ao.grad
+
+
+class SBasis:
+    """Device tables of an s-shell Gaussian basis (``evc_sbasis``) for a fixed list of atoms."""
+
+    def __init__(self, engine, symbols, basis):
+        from .basis import s_basis_tables
+        self.engine = engine
+        self.symbols = tuple(s.capitalize() for s in symbols)
+        self.basis = basis.lower()
+        t = s_basis_tables(self.symbols, self.basis)
+        self.tables = t
+        self.natm, self.nao = len(self.symbols), len(t["ao_atom"])
+        handle = C.c_void_p()
+        with torch.cuda.device(engine.device):
+            check(engine.lib.evc_sbasis_create(
+                engine._ctx, self.natm, t["charges"].ctypes.data, self.nao, t["ao_atom"].ctypes.data,
+                t["ao_nprim"].ctypes.data, t["prim_exp"].ctypes.data, t["prim_wt"].ctypes.data,
+                C.byref(handle)))
+        self.handle = handle
+        sl = np.zeros((self.natm, 2), dtype=np.int32)
+        for A in range(self.natm):
+            idx = np.flatnonzero(t["ao_atom"] == A)
+            sl[A] = (idx[0], idx[-1] + 1) if len(idx) else (0, 0)
+        self.aoslices_host = sl
+        self.charges = t["charges"]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.engine.lib.evc_sbasis_destroy(self.handle)
+                self.handle = None
+        except Exception:  # interpreter shutdown
+            pass
 
 
 class HostAO:

@@ -76,6 +76,115 @@ class ArrayMol:
         return self._grad_nuc
 
 
+BOHR = 0.52917721092  # Angstrom per bohr (the value pyscf.data.nist.BOHR carries)
+
+
+def _parse_atoms(atom):
+    if isinstance(atom, str):
+        out = []
+        for line in atom.replace(";", "\n").splitlines():
+            f = line.replace(",", " ").split()
+            if f:
+                out.append((f[0], tuple(float(v) for v in f[1:4])))
+        return out
+    return [(a[0], tuple(float(v) for v in (a[1] if len(a) == 2 else a[1:4]))) for a in atom]
+
+
+class MolLite:
+    """A ``pyscf.gto.Mole`` stand-in whose integrals come from the device engine (K9).
+
+    Covers what the reference touches on the prediction path ("mol duck
+    type"): ``nao, natm, nelec, atom_coords(), set_geom_(), copy(), energy_nuc(),
+    intor(name, comp=), aoslice_by_atom()`` and, as methods, the PySCF free functions
+    ``get_hcore / hcore_generator / grad_nuc``.  s shells only (``evcont_b200.basis``).
+    The reference scripts build their molecules as
+    ``gto.Mole().build(atom=[("H", (x, 0, 0)), ...], basis="sto-6g", unit="Bohr")``
+    (examples/H10_continuation_3D_replacements.py:84-102); ``MolLite(atom, basis, unit)``
+    takes the same arguments.
+    """
+
+    def __init__(self, atom, basis="sto-6g", unit="Bohr", charge=0, spin=0):
+        atoms = _parse_atoms(atom)
+        self._symbols = [a[0].capitalize() for a in atoms]
+        scale = 1.0 if unit.lower().startswith(("b", "au")) else 1.0 / BOHR
+        self._coords = np.array([a[1] for a in atoms], dtype=np.float64).reshape(-1, 3) * scale
+        self.basis, self.charge, self.spin, self.unit = basis, charge, spin, unit
+        from .basis import CHARGES, s_basis_tables
+        self._tables = s_basis_tables(self._symbols, basis)
+        self.natm = len(atoms)
+        self.nao = int(len(self._tables["ao_atom"]))
+        nel = int(sum(CHARGES[s] for s in self._symbols)) - int(charge)
+        self.nelectron = nel
+        self.nelec = ((nel + spin) // 2, (nel - spin) // 2)
+        self._cache = None
+
+    # --- geometry --------------------------------------------------------------
+    def atom_coords(self, unit="Bohr"):
+        c = self._coords.copy()
+        return c if unit.lower().startswith(("b", "au")) else c * BOHR
+
+    def atom_symbol(self, i):
+        return self._symbols[i]
+
+    def atom_charges(self):
+        return self._tables["charges"].astype(int)
+
+    def set_geom_(self, coords, unit="Bohr", inplace=True):
+        mol = self if inplace else self.copy()
+        scale = 1.0 if unit.lower().startswith(("b", "au")) else 1.0 / BOHR
+        mol._coords = np.array(coords, dtype=np.float64).reshape(self.natm, 3) * scale
+        mol._cache = None
+        return mol
+
+    def copy(self):
+        other = object.__new__(MolLite)
+        other.__dict__.update(self.__dict__)
+        other._coords = self._coords.copy()
+        other._cache = None
+        return other
+
+    def aoslice_by_atom(self):
+        t = self._tables["ao_atom"]
+        out = np.zeros((self.natm, 4), dtype=np.int64)
+        for A in range(self.natm):
+            idx = np.flatnonzero(t == A)
+            if len(idx):
+                out[A, 2:] = (idx[0], idx[-1] + 1)
+        return out
+
+    # --- integrals (device, cached per geometry) -----------------------------------
+    def sbasis(self, engine=None):
+        from .engine import get_engine
+        return (engine or get_engine()).sbasis(self._symbols, self.basis)
+
+    def _arrays(self):
+        if self._cache is None:
+            from .engine import DeviceAO, get_engine
+            eng = get_engine()
+            ao = eng.ao_integrals(self.sbasis(eng), self._coords[None])
+            self._cache = {k: getattr(ao, k)[0].cpu().numpy() for k in DeviceAO.FIELDS}
+        return self._cache
+
+    def intor(self, name, comp=None):
+        key = {"int1e_ovlp": "ovlp", "int1e_ipovlp": "ipovlp", "int2e": "eri", "int2e_ip1": "eri_ip1"}.get(name)
+        if key is None:
+            raise KeyError(f"MolLite serves {_INTOR_NAMES}, not {name!r}")
+        return self._arrays()[key]
+
+    def energy_nuc(self):
+        return float(self._arrays()["e_nuc"])
+
+    def get_hcore(self):
+        return self._arrays()["hcore"]
+
+    def hcore_generator(self):
+        hd = self._arrays()["hcore_deriv"]
+        return lambda atm_id: hd[atm_id]
+
+    def grad_nuc(self):
+        return self._arrays()["grad_nuc"]
+
+
 def synthetic_mol(norb, natm, seed=0, nelec=None):
     """Seeded synthetic AO arrays with the symmetries of real integrals.
 

@@ -273,6 +273,38 @@ int evc_energy_with_grad_packed_host(evc_ctx *ctx, int ntrain, int n, int natm, 
                                      const evc_ao_bundle *ao_host, double *E_host, double *grad_host,
                                      int chunk, void *workspace, size_t workspace_bytes);
 
+/* ---- K9: AO integrals over contracted s-type Gaussians, on the device ------------
+ * Replaces, for s shells (H / He: STO-nG, 6-31G), what the reference asks PySCF /
+ * libcint for on every prediction step
+ * (evcont/ab_initio_gradients_loewdin.py:25 int1e_ipovlp, :130/:338 int1e_ovlp,
+ * :147 grad.RHF.hcore_generator [int1e_ipkin, int1e_ipnuc, int1e_iprinv],
+ * :177/:338 scf.hf.get_hcore [int1e_kin + int1e_nuc], :283 int2e, :284 int2e_ip1,
+ * :339 ao2mo.kernel, :370 grad_nuc, :378 energy_nuc): closed-form Gaussian
+ * integrals with tabulated Boys functions, one warp per contracted quartet.
+ *
+ * evc_sbasis_create: host description of the basis (AOs grouped by atom, in atom
+ *   order, as pyscf.gto orders them): charges_host[natm], ao_atom_host[nao],
+ *   ao_nprim_host[nao], then the primitives of AO 0, AO 1, ... in
+ *   prim_exp_host / prim_wt_host, where wt = contraction coefficient x primitive
+ *   norm (2a/pi)^(3/4) x the factor that gives the contracted function unit
+ *   self-overlap.  The handle owns small device tables (allocated here, never
+ *   during evc_ao_integrals_s).  natm <= 64, nao <= 64, <= 16 primitives per AO.
+ * evc_ao_integrals_s: coords [nbatch][natm][3] (bohr, device) -> the evc_ao_bundle
+ *   arrays of every geometry, in the layouts documented at evc_ao_bundle;
+ *   aoslices for the bundle come from evc_sbasis_aoslices (device, [natm][2]). */
+typedef struct evc_sbasis evc_sbasis;
+int evc_sbasis_create(evc_ctx *ctx, int natm, const double *charges_host, int nao,
+                      const int32_t *ao_atom_host, const int32_t *ao_nprim_host,
+                      const double *prim_exp_host, const double *prim_wt_host,
+                      evc_sbasis **out);
+int evc_sbasis_destroy(evc_sbasis *basis);
+int evc_sbasis_nao(const evc_sbasis *basis);
+int evc_sbasis_natm(const evc_sbasis *basis);
+const int32_t *evc_sbasis_aoslices(const evc_sbasis *basis);
+int evc_ao_integrals_s(evc_ctx *ctx, const evc_sbasis *basis, int nbatch, const double *coords,
+                       double *ovlp, double *hcore, double *eri, double *ipovlp,
+                       double *hcore_deriv, double *eri_ip1, double *e_nuc, double *grad_nuc);
+
 #ifdef __cplusplus
 }
 #endif

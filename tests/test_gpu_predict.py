@@ -156,6 +156,25 @@ def test_packed_step_larger_norb_vs_oracle(norb, natm, ntrain, layout):
     assert np.abs(grad - ogr).max() < F_TOL
 
 
+@pytest.mark.parametrize("norb,natm,ntrain,layout", [(28, 7, 6, 2), (30, 30, 5, 6), (30, 30, 4, 5),
+                                                     (28, 7, 4, 3), (20, 6, 5, 2)])
+def test_large_norb_configs_vs_oracle(norb, natm, ntrain, layout):
+    """BASELINE configs[3] (H30/STO-6G: 30 orbitals, 30 atoms) and configs[4] (Zundel/6-31G:
+    28 orbitals, 7 atoms, exchange-compressed tril layout) at their orbital counts: the
+    HBM-resident transform / gradient kernels, single geometry and a small batch."""
+    from evcont_b200.ab_initio_gradients_loewdin import get_energy_with_grad, get_energy_with_grad_batch
+    from oracle import gradients as og
+    ovlp, one, two = synthetic_stack(norb, ntrain, 41, layout)
+    mols = [_mol(norb, natm, 700 + k) for k in range(3)]
+    E, G = get_energy_with_grad_batch(mols, one, two, ovlp)
+    for k, m in enumerate(mols[:2]):
+        oe, ogr = og.get_energy_with_grad(m, one, two, ovlp)
+        assert abs(E[k] - oe) < E_TOL * max(1.0, abs(oe))
+        assert np.abs(G[k] - ogr).max() < F_TOL * max(1.0, np.abs(ogr).max())
+    e1, g1 = get_energy_with_grad(mols[2], one, two, ovlp)
+    assert abs(E[2] - e1) < 1e-11 * max(1.0, abs(e1)) and np.abs(G[2] - g1).max() < 1e-10 * max(1.0, np.abs(g1).max())
+
+
 def test_grad_elec_OAO_against_oracle():
     from evcont_b200.ab_initio_gradients_loewdin import get_grad_elec_OAO
     from oracle import gradients as og

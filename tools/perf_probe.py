@@ -126,10 +126,34 @@ def probe_step(args):
                       "stage_ms": {k: v / max(1, calls) for k, v in stage.items()}}), flush=True)
 
 
+def probe_ints(args):
+    """K9: device AO integrals of an H chain (s shells) + the whole step from coordinates."""
+    import torch
+    from evcont_b200.engine import DeviceAO, DeviceStack, get_engine
+    eng = get_engine()
+    n, N, G = args.norb, args.ntrain, args.batch
+    rng = np.random.default_rng(1)
+    co = np.zeros((G, n, 3))
+    co[:, :, 0] = 1.78596 * np.arange(n)
+    v = rng.standard_normal((G, n, 3))
+    co += 0.3 * v / np.linalg.norm(v, axis=2)[..., None]
+    sb = eng.sbasis(["H"] * n, args.basis)
+    cd = eng.to_device(co)
+    ao = DeviceAO(eng, G, sb.nao, n, sb.aoslices_host)
+    ms_i = timed(torch, lambda: eng.ao_integrals(sb, cd, out=ao), args.reps)
+    S, one, two = synthetic_stack_dev(eng, torch, sb.nao, N, args.layout)
+    stack = DeviceStack(S, one, two, engine=eng, norb=sb.nao)
+    out = (eng.empty(G), eng.empty(G, n, 3), eng.empty(G, N))
+    ms_s = timed(torch, lambda: eng.energy_with_grad_coords(stack, sb, cd, ao=ao, out=out), args.reps)
+    print(json.dumps({"probe": "ints", "natm": n, "nao": sb.nao, "basis": args.basis, "batch": G,
+                      "integrals_ms": ms_i, "geoms_per_s": G / ms_i * 1e3,
+                      "step_from_coords_ms": ms_s, "steps_per_s": G / ms_s * 1e3}), flush=True)
+
+
 def main():
     _peaks()
     ap = argparse.ArgumentParser()
-    ap.add_argument("probe", choices=["trdm", "stack", "step"])
+    ap.add_argument("probe", choices=["trdm", "stack", "step", "ints"])
     ap.add_argument("--norb", type=int, default=10)
     ap.add_argument("--nocc", type=int, default=5)
     ap.add_argument("--nvec", type=int, default=20)
@@ -138,8 +162,9 @@ def main():
     ap.add_argument("--layout", type=int, default=6)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--basis", default="sto-6g")
     args = ap.parse_args()
-    {"trdm": probe_trdm, "stack": probe_stack, "step": probe_step}[args.probe](args)
+    {"trdm": probe_trdm, "stack": probe_stack, "step": probe_step, "ints": probe_ints}[args.probe](args)
 
 
 if __name__ == "__main__":
