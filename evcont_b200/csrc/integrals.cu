@@ -34,10 +34,11 @@
 
 namespace {
 
-constexpr int kBoysOrder = 7;        // table holds F_0 .. F_7 per grid point
-constexpr int kBoysPerUnit = 16;     // grid spacing 1/16
+constexpr int kBoysTop = 6;          // the table holds F_6 and exp(-T0) per grid point; F_5..F_0 by recursion
+constexpr int kBoysPerUnit = 64;     // grid spacing 1/64
 constexpr int kBoysTmax = 32;        // asymptotic form beyond
 constexpr int kBoysN = kBoysTmax * kBoysPerUnit + 1;
+constexpr double kScreen = 1.0e-17;  // primitive quartets with Schwarz bound below this are skipped
 constexpr int kIntThreads = 256;
 constexpr int kMaxAtoms = 64;
 
@@ -53,9 +54,9 @@ struct evc_sbasis {
   double* prim_exp;    // [nprim]
   double* prim_wt;     // [nprim] contraction coefficient x primitive and contracted norms
   double* charges;     // [natm]
-  double* pe1;         // [npe][4]: p, (pi/p)^1.5, 2 pi/p, 0
+  double* pe1;         // [npe][4]: p, (pi/p)^1.5, 2 pi/p, sqrt(f(p,p))
   double* pp;          // [npe][npe][2]: rho, 2 pi^2.5 / (p q sqrt(p+q))
-  double* boys;        // [kBoysOrder + 1][kBoysN]
+  double* boys;        // [kBoysN][2]: F_6(T0), exp(-T0), T0 = i/64
   int32_t* pc_off;     // [npc + 1] primitive-pair offsets of the contracted pairs a >= b
 };
 
@@ -84,20 +85,38 @@ __device__ __forceinline__ void tri_unrank(int t, int& a, int& b) {
   b = t - x * (x + 1) / 2;
 }
 
-// F0(T), F1(T) from the shared-memory table tab[k][i] = F_k(i/16): 6th-order Taylor series
-// around the nearest grid point (|d| <= 1/32: truncation < 1e-15); asymptotic beyond Tmax.
+// F0(T), F1(T): the shared-memory table holds (F_6(T0), exp(-T0)) on the grid T0 = i/64 -- one
+// 16-byte load per evaluation instead of one load per Taylor coefficient (the kernel is bound
+// by shared-memory wavefronts, not FP64 issue).  F_5..F_0 at T0 follow from the downward
+// recursion F_{k-1} = (2 T0 F_k + exp(-T0)) / (2k - 1) (all terms positive: stable), then a
+// 5th-order Taylor series in d = T0 - T, F_m(T) = sum_k F_{m+k}(T0) d^k / k!  (|d| <= 1/128:
+// truncation < 4e-16).  Asymptotic form beyond Tmax (error < exp(-32)/64).
 __device__ __forceinline__ void boys01(double T, const double* __restrict__ tab, double& f0, double& f1) {
   if (T < static_cast<double>(kBoysTmax)) {
-    const int i = __double2int_rn(T * kBoysPerUnit);
-    const double d = static_cast<double>(i) * (1.0 / kBoysPerUnit) - T;
-    const double r0 = tab[i], r1 = tab[kBoysN + i], r2 = tab[2 * kBoysN + i], r3 = tab[3 * kBoysN + i],
-                 r4 = tab[4 * kBoysN + i], r5 = tab[5 * kBoysN + i], r6 = tab[6 * kBoysN + i],
-                 r7 = tab[7 * kBoysN + i];
-    const double d2 = d * 0.5, d3 = d * (1.0 / 3.0), d4 = d * 0.25, d5 = d * 0.2, d6 = d * (1.0 / 6.0);
-    f0 = fma(d, fma(d2, fma(d3, fma(d4, fma(d5, fma(d6, r6, r5), r4), r3), r2), r1), r0);
-    f1 = fma(d, fma(d2, fma(d3, fma(d4, fma(d5, fma(d6, r7, r6), r5), r4), r3), r2), r1);
+    // round T to the grid with the 1.5 * 2^52 trick: no F2I / I2F on the critical path
+    const double r = fma(T, static_cast<double>(kBoysPerUnit), 6755399441055744.0);
+    const int i = __double2loint(r);
+    const double t0 = (r - 6755399441055744.0) * (1.0 / kBoysPerUnit);
+    const double d = t0 - T, tt = t0 + t0;
+    const double2 fe = *reinterpret_cast<const double2*>(tab + 2 * i);
+    const double r6 = fe.x, e = fe.y;
+    // r_{k-1} = (tt r_k + e) / (2k - 1), the division folded into both FMA operands so that
+    // the dependent chain is one FMA per step
+    const double r5 = fma(tt * (1.0 / 11.0), r6, e * (1.0 / 11.0));
+    const double r4 = fma(tt * (1.0 / 9.0), r5, e * (1.0 / 9.0));
+    const double r3 = fma(tt * (1.0 / 7.0), r4, e * (1.0 / 7.0));
+    const double r2 = fma(tt * (1.0 / 5.0), r3, e * (1.0 / 5.0));
+    const double r1 = fma(tt * (1.0 / 3.0), r2, e * (1.0 / 3.0));
+    const double r0 = fma(tt, r1, e);
+    const double d2 = d * 0.5, d3 = d * (1.0 / 3.0), d4 = d * 0.25, d5 = d * 0.2;
+    f0 = fma(d, fma(d2, fma(d3, fma(d4, fma(d5, r5, r4), r3), r2), r1), r0);
+    f1 = fma(d, fma(d2, fma(d3, fma(d4, fma(d5, r6, r5), r4), r3), r2), r1);
   } else {
-    const double r = rsqrt(T);
+    // 1/sqrt(T): single-precision seed + two Newton steps (relative error < 1e-15 for T >= 32)
+    double r = static_cast<double>(rsqrtf(static_cast<float>(T)));
+    const double h = -0.5 * T;
+    r = r * fma(h, r * r, 1.5);
+    r = r * fma(h, r * r, 1.5);
     f0 = 0.88622692545275801365 * r;
     f1 = 0.5 * f0 * r * r;
   }
@@ -119,22 +138,29 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// shared memory: boys table | pp table (if it fits) | atom coordinates | primitive pairs
-//   primitive pair record (4 doubles): bh = a_j/p, mu, Kc, pe (int in the low word)
+// shared memory: boys table | pp table (if it fits) | atom coordinates | primitive pairs | bounds
+//   primitive pair record, two arrays of double2: (bh = a_j/p, mu) and (Kc, pe as an int in the
+//   low word) -- 16-byte stride keeps the lane-consecutive 16-byte loads conflict-free; the records
+//   of a contracted pair are sorted by their Schwarz bound sqrt([ij|ij]) (descending, in sb[])
+//   so that the significant primitive quartets of (ab|cd) form a leading rectangle.
 template <bool PP_IN_SMEM>
-__global__ void __launch_bounds__(kIntThreads)
+__global__ void __launch_bounds__(kIntThreads, 2)
 sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
   extern __shared__ __align__(16) double sm[];
   const int n = bs.nao, natm = bs.natm, npe = bs.npe;
   double* boys = sm;
-  double* ppt = boys + (kBoysOrder + 1) * kBoysN;                 // [npe][npe][2]
+  double* ppt = boys + 2 * kBoysN + 2;                            // [npe][npe][2]
   double* R = ppt + (PP_IN_SMEM ? 2 * npe * npe : 0);             // [natm][3]
-  double4* prs = reinterpret_cast<double4*>(R + ((3 * natm + 1) & ~1));  // [maxpp]
+  double2* pra = reinterpret_cast<double2*>(R + ((3 * natm + 1) & ~1));  // [maxpp] (bh, mu)
+  double2* prb = pra + bs.maxpp;                                         // [maxpp] (Kc, pe)
+  float* sb = reinterpret_cast<float*>(prb + bs.maxpp);           // [maxpp] sorted bounds
+  // unsorted bounds (scratch of the pair build): in the Boys region, which is filled afterwards
+  float* su = (static_cast<size_t>(bs.maxpp) * sizeof(float) <= 2 * kBoysN * sizeof(double))
+                  ? reinterpret_cast<float*>(boys) : sb + bs.maxpp;
   const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NW = kIntThreads / 32;
   const double* Rg = coords + static_cast<int64_t>(g) * natm * 3;
 
-  for (int k = tid; k < (kBoysOrder + 1) * kBoysN; k += kIntThreads) boys[k] = __ldg(bs.boys + k);
   if (PP_IN_SMEM)
     for (int k = tid; k < 2 * npe * npe; k += kIntThreads) ppt[k] = __ldg(bs.pp + k);
   for (int k = tid; k < 3 * natm; k += kIntThreads) R[k] = Rg[k];
@@ -149,8 +175,8 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
     const double* B = R + 3 * bs.ao_atom[b];
     const double abx = A[0] - B[0], aby = A[1] - B[1], abz = A[2] - B[2];
     const double r2 = abx * abx + aby * aby + abz * abz;
-    const int off = bs.pc_off[I];
-    for (int t = lane; t < na * nb; t += 32) {
+    const int off = bs.pc_off[I], m = na * nb;
+    auto record = [&](int t, float& bound) {
       const int i = t / nb, j = t - i * nb;
       const double ai = bs.prim_exp[pa0 + i], aj = bs.prim_exp[pb0 + j];
       const int di = bs.prim_de[pa0 + i], dj = bs.prim_de[pb0 + j];
@@ -162,9 +188,31 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
       rec.y = mu;
       rec.z = bs.prim_wt[pa0 + i] * bs.prim_wt[pb0 + j] * exp(-mu * r2);
       rec.w = __longlong_as_double(static_cast<long long>(pe));
-      prs[off + t] = rec;
+      // sqrt([ij|ij]) = |Kc| sqrt(f(p,p)); rounded up so that the float never under-estimates
+      bound = static_cast<float>(fabs(rec.z) * bs.pe1[4 * pe + 3]) * 1.000001f;
+      return rec;
+    };
+    for (int t = lane; t < m; t += 32) {
+      float bd;
+      record(t, bd);
+      su[off + t] = bd;
+    }
+    __syncwarp();
+    for (int t = lane; t < m; t += 32) {
+      float bd;
+      const double4 rec = record(t, bd);
+      int rank = 0;
+      for (int u = 0; u < m; ++u) {
+        const float o = su[off + u];
+        rank += (o > bd || (o == bd && u < t)) ? 1 : 0;
+      }
+      pra[off + rank] = make_double2(rec.x, rec.y);
+      prb[off + rank] = make_double2(rec.z, rec.w);
+      sb[off + rank] = bd;
     }
   }
+  __syncthreads();
+  for (int k = tid; k < 2 * kBoysN; k += kIntThreads) boys[k] = __ldg(bs.boys + k);
   __syncthreads();
 
   const int64_t n2 = static_cast<int64_t>(n) * n, n3 = n2 * n, n4 = n2 * n2;
@@ -186,38 +234,54 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
     const double abx = A[0] - B[0], aby = A[1] - B[1], abz = A[2] - B[2];
     const double cdx = Cc[0] - D[0], cdy = Cc[1] - D[1], cdz = Cc[2] - D[2];
     const double acx = A[0] - Cc[0], acy = A[1] - Cc[1], acz = A[2] - Cc[2];
-    const int offI = bs.pc_off[I], mI = bs.pc_off[I + 1] - offI;
-    const int offK = bs.pc_off[K], mK = bs.pc_off[K + 1] - offK;
-    const float inv_mK = 1.0f / static_cast<float>(mK);
+    const int offI = bs.pc_off[I], offK = bs.pc_off[K];
+    int mI = bs.pc_off[I + 1] - offI, mK = bs.pc_off[K + 1] - offK;
+    {
+      // leading rectangle of primitive quartets whose Schwarz bound reaches kScreen
+      const float thr = static_cast<float>(kScreen);
+      const float topI = sb[offI], topK = sb[offK];
+      int cI = 0, cK = 0;
+      for (int l = lane; l < mI; l += 32) cI += (sb[offI + l] * topK >= thr) ? 1 : 0;
+      for (int l = lane; l < mK; l += 32) cK += (sb[offK + l] * topI >= thr) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cI += __shfl_xor_sync(0xffffffffu, cI, o);
+        cK += __shfl_xor_sync(0xffffffffu, cK, o);
+      }
+      mI = cI;
+      mK = cK;
+    }
     double E = 0, Mab = 0, Mcd = 0, U = 0, Ub = 0, Ud = 0, Ubb = 0, Ubd = 0, Udd = 0;
     const int tot = mI * mK;
+    int bi = 0, ki = lane;
+    while (ki >= mK && mK > 0) { ki -= mK; ++bi; }
+    // lanes run over the flattened rectangle of significant primitive quartets
     for (int t = lane; t < tot; t += 32) {
-      int bi = static_cast<int>((static_cast<float>(t) + 0.5f) * inv_mK);
-      int ki = t - bi * mK;
-      if (ki < 0) { --bi; ki += mK; } else if (ki >= mK) { ++bi; ki -= mK; }
-      const double4 br = prs[offI + bi];
-      const double4 kt = prs[offK + ki];
-      const int peb = static_cast<int>(__double_as_longlong(br.w));
-      const int pek = static_cast<int>(__double_as_longlong(kt.w));
+      const double2 b1 = pra[offI + bi], b2 = prb[offI + bi];   // (bh, mu), (Kc, pe)
+      const double2 k1 = pra[offK + ki], k2 = prb[offK + ki];
+      const int peb = static_cast<int>(__double_as_longlong(b2.y));
+      const int pek = static_cast<int>(__double_as_longlong(k2.y));
       const double2 rf = *reinterpret_cast<const double2*>(ppg + 2 * (peb * npe + pek));
-      const double px = fma(kt.x, cdx, fma(-br.x, abx, acx));
-      const double py = fma(kt.x, cdy, fma(-br.x, aby, acy));
-      const double pz = fma(kt.x, cdz, fma(-br.x, abz, acz));
+      const double px = fma(k1.x, cdx, fma(-b1.x, abx, acx));
+      const double py = fma(k1.x, cdy, fma(-b1.x, aby, acy));
+      const double pz = fma(k1.x, cdz, fma(-b1.x, abz, acz));
       const double T = rf.x * fma(px, px, fma(py, py, pz * pz));
       double f0, f1;
       boys01(T, boys, f0, f1);
-      const double w = rf.y * br.z * kt.z;
+      const double w = rf.y * b2.x * k2.x;
       const double i0 = w * f0, u = rf.x * w * f1;
-      const double ub = br.x * u, ud = kt.x * u;
+      const double ub = b1.x * u, ud = k1.x * u;
       E += i0;
-      Mab = fma(br.y, i0, Mab);
-      Mcd = fma(kt.y, i0, Mcd);
+      Mab = fma(b1.y, i0, Mab);
+      Mcd = fma(k1.y, i0, Mcd);
       U += u;
       Ub += ub;
       Ud += ud;
-      Ubb = fma(br.x, ub, Ubb);
-      Ubd = fma(br.x, ud, Ubd);
-      Udd = fma(kt.x, ud, Udd);
+      Ubb = fma(b1.x, ub, Ubb);
+      Ubd = fma(b1.x, ud, Ubd);
+      Udd = fma(k1.x, ud, Udd);
+      ki += 32;
+      while (ki >= mK) { ki -= mK; ++bi; }
     }
     E = warp_sum(E); Mab = warp_sum(Mab); Mcd = warp_sum(Mcd);
     U = warp_sum(U); Ub = warp_sum(Ub); Ud = warp_sum(Ud);
@@ -280,7 +344,8 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
     // overlap-type sums: lanes over primitive pairs
     double s0 = 0, s1 = 0, t0 = 0, t1 = 0;
     for (int t = lane; t < m; t += 32) {
-      const double4 pr = prs[off + t];
+      const double2 q1 = pra[off + t], q2 = prb[off + t];
+      const double4 pr = make_double4(q1.x, q1.y, q2.x, q2.y);
       const int pe = static_cast<int>(__double_as_longlong(pr.w));
       const double sp = bs.pe1[4 * pe + 1] * pr.z, mu = pr.y;
       s0 += sp;
@@ -301,7 +366,8 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
         acx = A[0] - R[3 * C]; acy = A[1] - R[3 * C + 1]; acz = A[2] - R[3 * C + 2];
         z = bs.charges[C];
         for (int t = 0; t < m; ++t) {
-          const double4 pr = prs[off + t];
+          const double2 q1 = pra[off + t], q2 = prb[off + t];
+      const double4 pr = make_double4(q1.x, q1.y, q2.x, q2.y);
           const int pe = static_cast<int>(__double_as_longlong(pr.w));
           const double p = bs.pe1[4 * pe], gpre = bs.pe1[4 * pe + 2] * pr.z;
           const double px = fma(-pr.x, abx, acx), py = fma(-pr.x, aby, acy), pz = fma(-pr.x, abz, acz);
@@ -393,9 +459,10 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
 }
 
 size_t sint_smem_bytes(const evc_sbasis* b, bool pp_in_smem) {
-  size_t d = static_cast<size_t>(kBoysOrder + 1) * kBoysN + (pp_in_smem ? 2 * static_cast<size_t>(b->npe) * b->npe : 0) +
+  size_t d = 2 * static_cast<size_t>(kBoysN) + 2 + (pp_in_smem ? 2 * static_cast<size_t>(b->npe) * b->npe : 0) +
              ((3 * static_cast<size_t>(b->natm) + 1) & ~static_cast<size_t>(1));
-  return d * sizeof(double) + static_cast<size_t>(b->maxpp) * sizeof(double4);
+  const bool su_in_boys = static_cast<size_t>(b->maxpp) * sizeof(float) <= 2 * kBoysN * sizeof(double);
+  return d * sizeof(double) + static_cast<size_t>(b->maxpp) * (sizeof(double4) + (su_in_boys ? 1 : 2) * sizeof(float));
 }
 
 template <typename T>
@@ -461,7 +528,8 @@ int evc_sbasis_create(evc_ctx* ctx, int natm, const double* charges_host, int na
       pe1[4 * e] = static_cast<double>(p);
       pe1[4 * e + 1] = static_cast<double>(powl(pi / p, 1.5L));
       pe1[4 * e + 2] = static_cast<double>(2.0L * pi / p);
-      pe1[4 * e + 3] = 0.0;
+      // sqrt(f(p, p)) = sqrt(2 pi^2.5 / (p^2 sqrt(2p))): Schwarz factor of a primitive pair
+      pe1[4 * e + 3] = static_cast<double>(sqrtl(2.0L * powl(pi, 2.5L) / (p * p * sqrtl(2.0L * p))));
     }
   for (int e = 0; e < npe; ++e)
     for (int f = 0; f < npe; ++f) {
@@ -470,11 +538,13 @@ int evc_sbasis_create(evc_ctx* ctx, int natm, const double* charges_host, int na
       pp[2 * (static_cast<size_t>(e) * npe + f) + 1] =
           static_cast<double>(2.0L * powl(pi, 2.5L) / (p * q * sqrtl(p + q)));
     }
-  std::vector<double> boys(static_cast<size_t>(kBoysOrder + 1) * kBoysN);
+  std::vector<double> boys(2 * static_cast<size_t>(kBoysN));
   for (int i = 0; i < kBoysN; ++i) {
-    long double f[kBoysOrder + 1];
-    boys_host(kBoysOrder, static_cast<long double>(i) / kBoysPerUnit, f);
-    for (int k = 0; k <= kBoysOrder; ++k) boys[static_cast<size_t>(k) * kBoysN + i] = static_cast<double>(f[k]);
+    long double f[kBoysTop + 1];
+    const long double t0 = static_cast<long double>(i) / kBoysPerUnit;
+    boys_host(kBoysTop, t0, f);
+    boys[2 * static_cast<size_t>(i)] = static_cast<double>(f[kBoysTop]);
+    boys[2 * static_cast<size_t>(i) + 1] = static_cast<double>(expl(-t0));
   }
   const int npc = nao * (nao + 1) / 2;
   std::vector<int32_t> pc_off(npc + 1, 0);
@@ -533,7 +603,7 @@ int evc_ao_integrals_s(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const doub
   int split = 1;
   const int nq = b->npc * (b->npc + 1) / 2, nw = kIntThreads / 32;
   while (static_cast<long long>(nbatch) * split < 2LL * ctx->sm_count && split * nw * 4 <= nq) split *= 2;
-  const bool pp_in = sint_smem_bytes(b, true) <= 110 * 1024;
+  const bool pp_in = sint_smem_bytes(b, true) <= 113 * 1024;  // two CTAs per SM
   const size_t smem = sint_smem_bytes(b, pp_in);
   dim3 grid(split, nbatch);
   if (pp_in) {
