@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dgemm-peak", action="store_true")
+    ap.add_argument("--no-coords", action="store_true", help="skip the from-coordinates leg (K9)")
     ap.add_argument("--no-settle", action="store_true",
                     help="skip the 0.4 s clock-settling loop (for runs under ncu)")
     return ap.parse_args()
@@ -290,6 +291,61 @@ def stage_work(n, natm, ntrain, G):
     }
 
 
+def h10_geometries(G, seed):
+    """The test-geometry sampler of the reference's H10 script (examples/
+    H10_continuation_3D_replacements.py:130-147): equidistant chain, d0 = 1.78596 bohr, every atom
+    displaced by 0.3 bohr in a random direction."""
+    rng = np.random.default_rng(seed)
+    co = np.zeros((G, NATM, 3))
+    co[:, :, 0] = 1.78596 * np.arange(NATM)
+    v = rng.standard_normal((G, NATM, 3))
+    return co + 0.3 * v / np.linalg.norm(v, axis=2)[..., None]
+
+
+def run_coords_leg(args, eng, stack, timed, world, rank, torch):
+    """MD steps/s when only the nuclear coordinates come from the host: pinned coordinates in,
+    AO integrals on the device (K9, s shells, STO-6G), prediction step, (E, grad) back in pinned
+    host memory.  Also times the integral kernel alone for its FP64 roofline."""
+    from evcont_b200.engine import DeviceAO
+    G, K, W, N = args.batch, args.steps, args.warmup, args.ntrain
+    sb = eng.sbasis(["H"] * NATM, "sto-6g")
+    co_h = torch.from_numpy(h10_geometries(G, 4000 + rank)).pin_memory()
+    co_d = eng.empty(G, NATM, 3)
+    ao = DeviceAO(eng, G, sb.nao, NATM, sb.aoslices_host)
+    out = (eng.empty(G), eng.empty(G, NATM, 3), eng.empty(G, N))
+    E_h = torch.empty(G, dtype=torch.float64).pin_memory()
+    g_h = torch.empty(G, NATM, 3, dtype=torch.float64).pin_memory()
+
+    def step(_i):
+        co_d.copy_(co_h, non_blocking=True)
+        eng.energy_with_grad_coords(stack, sb, co_d, ao=ao, out=out)
+        E_h.copy_(out[0], non_blocking=True)
+        g_h.copy_(out[1], non_blocking=True)
+
+    for i in range(W):
+        step(i)
+    launches0 = eng.launch_count()
+    ms = timed(step, K)
+    launches = eng.launch_count() - launches0
+    ints_ms = timed(lambda i: eng.ao_integrals(sb, co_d, out=ao), K) / K
+    # algorithmic work of K9: contracted quartets (ab|cd), (ab) >= (cd), times the primitive quartets
+    # of each, ~45 FMA per primitive quartet (PQ, T, Boys F0/F1, 9 accumulators); DESIGN.md section 4
+    npc = NORB * (NORB + 1) // 2
+    prim_quartets = npc * (npc + 1) // 2 * 6 ** 4
+    flops = G * prim_quartets * 90.0
+    peak_tf = 64 * 2 * eng.sm_count * 1.965e9 / 1e12  # 64 DFMA lanes/clk/SM (tools/fp64_latency.cu)
+    ach = flops / (ints_ms * 1e-3) / 1e12
+    return {"value": world * G * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+            "h2d_bytes_per_step": int(co_h.numel() * 8), "d2h_bytes_per_step": int((E_h.numel() + g_h.numel()) * 8),
+            "basis": "STO-6G (s shells), integrals by evc_ao_integrals_s", "gpu_launches": int(launches),
+            "integrals_ms_per_step": ints_ms,
+            "integrals_roofline": {"kernel": "sint_kernel", "bound": "fp64 fma pipe", "achieved": ach, "peak": peak_tf,
+                                   "unit": "TFLOP/s", "frac": ach / peak_tf,
+                                   "work": f"{prim_quartets} primitive quartets per geometry x 90 flop, before "
+                                           "Schwarz screening",
+                                   "peak_source": "64 DFMA lanes/clk/SM x SMs x 1.965 GHz (tools/fp64_latency.cu)"}}
+
+
 def measure_dgemm_peak(torch, dev):
     m = 6144
     a = torch.randn(m, m, dtype=torch.float64, device=dev)
@@ -437,6 +493,10 @@ def run_b200(args):
     for i in range(W):
         step_e2e(i)
     e2e_ms = timed(step_e2e, K)
+    # ---- the same step from nuclear coordinates only (K9: AO integrals on the device) ----
+    coords_leg = None
+    if not args.no_coords:
+        coords_leg = run_coords_leg(args, eng, stack, timed, world, rank, torch)
     t1 = time.time()
     clocks = sampler.stop(window=(t0, t1)) if rank == 0 else None
     value = world * G * K / (total_ms * 1e-3)
@@ -492,6 +552,7 @@ def run_b200(args):
         "gpu_launches": int(step_launches),
         "roofline": roofline, "trans_rdm12": trdm, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "fp64_dgemm_tflops": dgemm_tf,
+        "from_coordinates": coords_leg,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

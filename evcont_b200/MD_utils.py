@@ -1,10 +1,13 @@
 """``get_scanner``: the drop-in boundary for MD drivers (evcont/MD_utils.py:20-57).
 
 Returns an object PySCF's ``md.NVE`` / ``md.NVTBerendson`` (or any velocity-Verlet
-loop) can call as ``scanner(mol) -> (E_total, grad)``.  The trajectory drivers
-``get_trajectory`` / ``converge_EVCont_MD`` are host orchestration over PySCF's
-integrators and are not part of this package.
+loop) can call as ``scanner(mol) -> (E_total, grad)``.  ``get_trajectory`` runs the NVE
+trajectory itself on the device (``evcont_b200.md.DeviceNVE``) when given a
+:class:`evcont_b200.mol.MolLite`; ``converge_EVCont_MD`` (the active-learning outer loop over
+FCI solves, evcont/MD_utils.py:128-502) is host orchestration and not part of this package.
 """
+import numpy as np
+
 from .ab_initio_gradients_loewdin import get_energy_with_grad
 from .mol import ao_bundle
 
@@ -44,3 +47,29 @@ def get_scanner(mol, one_rdm, two_rdm, overlap, hermitian=True):
             return b["e_nuc"], b["grad_nuc"]
 
     return Scanner()
+
+
+def get_trajectory(init_mol, overlap, one_rdm, two_rdm, dt=10.0, steps=10, init_veloc=None, hermitian=True,
+                   trajectory_output=None, energy_output=None):
+    """MD trajectory from the continuation, ``(steps, natm, 3)`` in bohr (evcont/MD_utils.py:60-125:
+    ``pyscf.md.NVE`` with ``frames=[]``; frame 0 is the initial geometry).  The integrator runs on
+    the device; ``trajectory_output`` / ``energy_output`` (file names or file objects) receive plain
+    text tables (step, coordinates) / (step, E_pot, E_kin, E_tot) instead of PySCF's formats."""
+    if hermitian is not True:
+        raise NotImplementedError("hermitian=False is not implemented on the device")
+    from .md import DeviceNVE
+    from .mol import MolLite
+    if not isinstance(init_mol, MolLite):
+        raise TypeError("get_trajectory integrates on the device and needs an evcont_b200.mol.MolLite "
+                        "(use get_scanner with pyscf.md for a pyscf Mole)")
+    veloc = None if init_veloc is None else np.asarray(init_veloc, dtype=np.float64)[None]
+    nve = DeviceNVE(init_mol, one_rdm, two_rdm, overlap, init_mol.atom_coords()[None], veloc, dt=dt,
+                    max_frames=steps)
+    nve.run(steps - 1)
+    traj, epot, ekin = nve.frames()
+    if trajectory_output is not None:
+        np.savetxt(trajectory_output, np.column_stack([np.arange(len(traj)), traj[:, 0].reshape(len(traj), -1)]))
+    if energy_output is not None:
+        np.savetxt(energy_output, np.column_stack([np.arange(len(traj)), epot[:, 0], ekin[:, 0],
+                                                   epot[:, 0] + ekin[:, 0]]))
+    return traj[:, 0]

@@ -106,6 +106,10 @@ SIGNATURES = {
     "evc_sbasis_natm": (C.c_int, [C.c_void_p]),
     "evc_sbasis_aoslices": (C.c_void_p, [C.c_void_p]),
     "evc_ao_integrals_s": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9),
+    "evc_md_positions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p,
+                                   c_double_p]),
+    "evc_md_velocities": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int] + [c_double_p] * 8 +
+                          [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]),
 }
 
 _lib = None

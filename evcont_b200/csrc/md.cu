@@ -1,0 +1,90 @@
+// Device-resident velocity-Verlet integrator, batched over independent trajectories
+// (SURVEY.md section 8 row f3).  The reference drives pyscf.md.NVE from the host
+// (evcont/MD_utils.py:60-125: one scanner call, i.e. one get_energy_with_grad, per step);
+// here positions, velocities, accelerations and the recorded frames stay in HBM, so a step
+// is "positions kernel -> K9 integrals -> K3..K8 prediction -> velocities kernel" with no
+// host round trip and can be captured in a CUDA graph.
+//
+// pyscf.md.integrators.VelocityVerlet, restated:
+//   frame 0 = the initial geometry (only the acceleration is computed),
+//   x_{k+1} = x_k + dt v_k + dt^2/2 a_k ;  a_{k+1} = -grad(x_{k+1}) / m ;
+//   v_{k+1} = v_k + dt/2 (a_k + a_{k+1}) ;  E_kin = 1/2 sum m v^2.
+#include "common.cuh"
+
+namespace {
+
+// one thread per coordinate; frame_idx is a device counter so that a captured graph can be
+// replayed step after step
+__global__ void md_positions_kernel(int64_t ncoord, double dt, const double* __restrict__ v,
+                                    const double* __restrict__ a, double* __restrict__ x) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= ncoord) return;
+  x[k] = fma(dt, fma(0.5 * dt, a[k], v[k]), x[k]);
+}
+
+// a_new = -grad / m; if `first`: a = a_new only (frame 0), else v += dt/2 (a + a_new), a = a_new.
+// One warp per trajectory: also reduces the kinetic energy and records the frame.
+__global__ void md_velocities_kernel(int nbatch, int natm, double dt, int first, const double* __restrict__ inv_mass,
+                                     const double* __restrict__ mass, const double* __restrict__ grad,
+                                     const double* __restrict__ x, const double* __restrict__ epot,
+                                     double* __restrict__ v, double* __restrict__ a, double* __restrict__ ekin,
+                                     int* __restrict__ frame_idx, int max_frames, double* __restrict__ traj,
+                                     double* __restrict__ epot_log, double* __restrict__ ekin_log) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= nbatch) return;
+  const int nc = natm * 3;
+  const int64_t o = static_cast<int64_t>(g) * nc;
+  const int f = *frame_idx;
+  double ke = 0.0;
+  for (int k = lane; k < nc; k += 32) {
+    const int at = k / 3;
+    const double an = -grad[o + k] * inv_mass[at];
+    double vk = v[o + k];
+    if (!first) vk = fma(0.5 * dt, a[o + k] + an, vk);
+    v[o + k] = vk;
+    a[o + k] = an;
+    ke = fma(0.5 * mass[at] * vk, vk, ke);
+    if (traj && f < max_frames) traj[(static_cast<int64_t>(f) * nbatch + g) * nc + k] = x[o + k];
+  }
+  for (int s = 16; s > 0; s >>= 1) ke += __shfl_xor_sync(0xffffffffu, ke, s);
+  if (lane == 0) {
+    ekin[g] = ke;
+    if (f < max_frames) {
+      if (epot_log) epot_log[static_cast<int64_t>(f) * nbatch + g] = epot[g];
+      if (ekin_log) ekin_log[static_cast<int64_t>(f) * nbatch + g] = ke;
+    }
+  }
+}
+
+__global__ void md_advance_frame_kernel(int* frame_idx) { *frame_idx += 1; }
+
+}  // namespace
+
+extern "C" {
+
+int evc_md_positions(evc_ctx* ctx, int nbatch, int natm, double dt, const double* v, const double* a, double* x) {
+  EVC_REQUIRE(ctx && v && a && x, "evc_md_positions: NULL argument");
+  if (nbatch <= 0) return 0;
+  const int64_t nc = static_cast<int64_t>(nbatch) * natm * 3;
+  md_positions_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, ctx->stream>>>(nc, dt, v, a, x);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_md_velocities(evc_ctx* ctx, int nbatch, int natm, double dt, int first, const double* inv_mass,
+                      const double* mass, const double* grad, const double* x, const double* epot, double* v,
+                      double* a, double* ekin, int* frame_idx, int max_frames, double* traj, double* epot_log,
+                      double* ekin_log) {
+  EVC_REQUIRE(ctx && inv_mass && mass && grad && x && epot && v && a && ekin && frame_idx,
+              "evc_md_velocities: NULL argument");
+  if (nbatch <= 0) return 0;
+  md_velocities_kernel<<<(nbatch + 3) / 4, 128, 0, ctx->stream>>>(nbatch, natm, dt, first, inv_mass, mass, grad, x,
+                                                                   epot, v, a, ekin, frame_idx, max_frames, traj,
+                                                                   epot_log, ekin_log);
+  EVC_CHECK_LAUNCH();
+  md_advance_frame_kernel<<<1, 1, 0, ctx->stream>>>(frame_idx);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -280,6 +280,21 @@ class Engine:
         ao = self.ao_integrals(sbasis, coords, out=ao)
         return self.energy_with_grad(stack, ao, want_rdms=want_rdms, out=out)
 
+    # -- device-resident velocity Verlet ------------------------------------------------------
+    def md_positions(self, dt, x, v, a):
+        G, natm = x.shape[0], x.shape[1]
+        self._bind_stream()
+        check(self.lib.evc_md_positions(self._ctx, G, natm, float(dt), _ptr(v), _ptr(a), _ptr(x)))
+
+    def md_velocities(self, dt, first, inv_mass, mass, grad, x, epot, v, a, ekin, frame_idx, max_frames,
+                      traj=None, epot_log=None, ekin_log=None):
+        G, natm = x.shape[0], x.shape[1]
+        self._bind_stream()
+        check(self.lib.evc_md_velocities(self._ctx, G, natm, float(dt), 1 if first else 0, _ptr(inv_mass),
+                                         _ptr(mass), _ptr(grad), _ptr(x), _ptr(epot), _ptr(v), _ptr(a),
+                                         _ptr(ekin), _ptr(frame_idx), int(max_frames), _ptr(traj),
+                                         _ptr(epot_log), _ptr(ekin_log)))
+
     # -- fused step ------------------------------------------------------------------------
     def energy_with_grad(self, stack, ao, want_rdms=False, out=None, packed=None):
         """One prediction step for a batch of geometries resident on the device.

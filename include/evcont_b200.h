@@ -305,6 +305,25 @@ int evc_ao_integrals_s(evc_ctx *ctx, const evc_sbasis *basis, int nbatch, const 
                        double *ovlp, double *hcore, double *eri, double *ipovlp,
                        double *hcore_deriv, double *eri_ip1, double *e_nuc, double *grad_nuc);
 
+/* ---- device-resident velocity Verlet (batched over trajectories) ------------------
+ * Replaces the host loop of pyscf.md.NVE that get_trajectory drives
+ * (evcont/MD_utils.py:60-125; one scanner call per step): x, v, a: [nbatch][natm][3]
+ * stay on the device.  One MD step is
+ *   evc_md_positions  : x += dt v + dt^2/2 a
+ *   (evc_ao_integrals_s + evc_energy_with_grad[_packed] at the new x)
+ *   evc_md_velocities : a' = -grad / m;  v += dt/2 (a + a');  a = a';  E_kin; frame recording
+ * `first` != 0 is the start-up call (frame 0 = initial geometry: only a is set).
+ * frame_idx is a device counter (advanced by every evc_md_velocities call) so that a
+ * captured CUDA graph of one step can be replayed; traj [max_frames][nbatch][natm][3],
+ * epot_log / ekin_log [max_frames][nbatch] may be NULL. */
+int evc_md_positions(evc_ctx *ctx, int nbatch, int natm, double dt, const double *v,
+                     const double *a, double *x);
+int evc_md_velocities(evc_ctx *ctx, int nbatch, int natm, double dt, int first,
+                      const double *inv_mass /* [natm] */, const double *mass /* [natm] */,
+                      const double *grad, const double *x, const double *epot, double *v,
+                      double *a, double *ekin, int *frame_idx, int max_frames, double *traj,
+                      double *epot_log, double *ekin_log);
+
 #ifdef __cplusplus
 }
 #endif
