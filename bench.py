@@ -512,8 +512,15 @@ def run_b200(args):
         peak_src = "cuBLAS DGEMM 6144^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"
     else:
         ach, peak, unit, peak_src = wk["bytes"] / (per_call[top] * 1e-3) / 1e9, hbm_peak, "GB/s", hbm_src
+    # dram__bytes_read.sum + dram__bytes_write.sum per geometry from the ncu --set full capture of the
+    # same kernels at G = 4096 (profiles/r01b_packed_step_ncu_full.txt), scaled to this launch
+    ncu_bytes_per_geom = {"loewdin": 3.323e6 / 4096, "ao2oao": (191.717e6 + 162.234e6) / 4096,
+                          "grad": (172.879e6 + 68.772e6) / 4096, "grad_stream": (1172.312e6 + 5.484e6) / 4096}
+    traffic = ncu_bytes_per_geom[top] * G if (top in ncu_bytes_per_geom and n == 10 and N == 20) else None
     roofline = {"kernel": top, "bound": "tensor" if unit == "TFLOP/s" else "hbm", "achieved": ach,
-                "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
+                "traffic_source": "profiles/r01b_packed_step_ncu_full.txt (bytes per launch)" if traffic else None,
+                "algorithmic_bytes": wk["bytes"], "peak_source": peak_src,
                 "share_of_step": per_call[top] / max(1e-12, sum(per_call.values())),
                 "stage_ms_per_step": per_call}
     trdm = {"pairs_per_s": pairs_per_s, "pairs": len(pairs), "build_ms": build_ms,

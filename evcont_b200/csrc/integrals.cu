@@ -100,13 +100,11 @@ __device__ __forceinline__ void boys01(double T, const double* __restrict__ tab,
     const double d = t0 - T, tt = t0 + t0;
     const double2 fe = *reinterpret_cast<const double2*>(tab + 2 * i);
     const double r6 = fe.x, e = fe.y;
-    // r_{k-1} = (tt r_k + e) / (2k - 1), the division folded into both FMA operands so that
-    // the dependent chain is one FMA per step
-    const double r5 = fma(tt * (1.0 / 11.0), r6, e * (1.0 / 11.0));
-    const double r4 = fma(tt * (1.0 / 9.0), r5, e * (1.0 / 9.0));
-    const double r3 = fma(tt * (1.0 / 7.0), r4, e * (1.0 / 7.0));
-    const double r2 = fma(tt * (1.0 / 5.0), r3, e * (1.0 / 5.0));
-    const double r1 = fma(tt * (1.0 / 3.0), r2, e * (1.0 / 3.0));
+    const double r5 = fma(tt, r6, e) * (1.0 / 11.0);
+    const double r4 = fma(tt, r5, e) * (1.0 / 9.0);
+    const double r3 = fma(tt, r4, e) * (1.0 / 7.0);
+    const double r2 = fma(tt, r3, e) * (1.0 / 5.0);
+    const double r1 = fma(tt, r2, e) * (1.0 / 3.0);
     const double r0 = fma(tt, r1, e);
     const double d2 = d * 0.5, d3 = d * (1.0 / 3.0), d4 = d * 0.25, d5 = d * 0.2;
     f0 = fma(d, fma(d2, fma(d3, fma(d4, fma(d5, r5, r4), r3), r2), r1), r0);
