@@ -155,6 +155,11 @@ class Engine:
     def trans_rdm12_issued_flops(self):
         return self.lib.evc_trans_rdm12_last_issued_flops(self._ctx)
 
+    # -- FCI Hamiltonian action (training side) --------------------------------------------
+    def fci_hamiltonian(self, h1e, eri, norb, nelec):
+        """Device operator for ``H c`` and ``diag H`` of one geometry: :class:`FCIHamiltonian`."""
+        return FCIHamiltonian(self, h1e, eri, norb, nelec)
+
     # -- K3 ------------------------------------------------------------------------
     def loewdin(self, s_ao):
         """Batched Loewdin: ``s_ao`` (G, n, n) device -> (X, evals, evecs)."""
@@ -374,6 +379,58 @@ class Engine:
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
         return host_ao.E, host_ao.grad
+
+
+class FCIHamiltonian:
+    """``sigma = H c`` (``evc_fci_contract_2e``) and ``<K|H|K>`` (``evc_fci_hdiag``) for fixed
+    integrals ``h1e (n,n)``, ``eri (n,n,n,n)`` in an orthonormal basis -- the two things a Davidson
+    solver asks of the Hamiltonian (pyscf.fci.direct_spin1.contract_2e / make_hdiag)."""
+
+    def __init__(self, engine, h1e, eri, norb, nelec):
+        from . import cistring
+        self.engine, self.norb = engine, int(norb)
+        n = self.norb
+        self.nelec = (int(nelec[0]), int(nelec[1]))
+        self.na, self.nlink_a, self.link_a, _ = engine.link_tables(n, self.nelec[0])
+        self.nb, self.nlink_b, self.link_b, _ = engine.link_tables(n, self.nelec[1])
+        h1e = np.asarray(h1e, dtype=np.float64).reshape(n, n)
+        eri = np.asarray(eri, dtype=np.float64).reshape(n, n, n, n)
+        n2, n2p = n * n, (n * n + 1) & ~1
+        h1eff = np.zeros(n2p)
+        h1eff[:n2] = (h1e - 0.5 * np.einsum("pqqs->ps", eri)).reshape(-1)
+        w2 = np.zeros((n2p, n2p))
+        w2[:n2, :n2] = 0.5 * eri.reshape(n2, n2).T   # w2[(rs), (pq)] = 1/2 (pq|rs)
+        self.h1eff, self.w2 = engine.to_device(h1eff), engine.to_device(w2)
+        self.h1, self.eri = engine.to_device(h1e), engine.to_device(eri)
+        self.strs_a = torch.from_numpy(cistring.make_strings(range(n), self.nelec[0])).to(engine.device)
+        self.strs_b = torch.from_numpy(cistring.make_strings(range(n), self.nelec[1])).to(engine.device)
+        nbytes = C.c_size_t()
+        check(engine.lib.evc_fci_contract_workspace_bytes(n, self.na, self.nb, C.byref(nbytes)))
+        self._ws_bytes = nbytes.value
+
+    @property
+    def ndet(self):
+        return self.na * self.nb
+
+    def hdiag(self):
+        eng = self.engine
+        out = eng.empty(self.ndet)
+        eng._bind_stream()
+        check(eng.lib.evc_fci_hdiag(eng._ctx, self.norb, self.na, self.nb, _ptr(self.strs_a), _ptr(self.strs_b),
+                                    _ptr(self.h1), _ptr(self.eri), _ptr(out)))
+        return out
+
+    def contract(self, c, out=None):
+        """``H c`` for a device vector ``c`` of ``ndet`` doubles."""
+        eng = self.engine
+        c = c.reshape(-1)
+        out = eng.empty(self.ndet) if out is None else out
+        ws = eng.workspace(self._ws_bytes)
+        eng._bind_stream()
+        check(eng.lib.evc_fci_contract_2e(eng._ctx, self.norb, self.na, self.nb, _ptr(self.link_a), self.nlink_a,
+                                          _ptr(self.link_b), self.nlink_b, _ptr(self.h1eff), _ptr(self.w2),
+                                          _ptr(c), _ptr(out), _ptr(ws), ws.numel()))
+        return out
 
 
 class SBasis:

@@ -3,12 +3,93 @@
 The reference's default is ``pyscf.fci.direct_spin0.FCI()`` (evcont/FCI_EVCont.py:17);
 the two methods ``append_to_rdms`` calls on it are ``kernel`` (:70) and
 ``trans_rdm12`` (:121).  :class:`B200FCISolver` runs ``trans_rdm12`` on the GPU
-(K1+K2 of the C ABI) and delegates ``kernel`` to a wrapped PySCF solver when one
-is available.
+(K1+K2 of the C ABI); ``kernel`` is a Davidson solver over the device ``H c``
+(``csrc/fci.cu``) unless a PySCF solver is wrapped.
 """
 import numpy as np
 
 from .engine import get_engine
+
+
+def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False):
+    """Davidson-Liu for the lowest ``nroots`` eigenpairs of ``ham`` (:class:`FCIHamiltonian`).
+
+    Vectors live on the device as torch tensors (dot products and axpys are torch calls -- plumbing);
+    the small projected eigenproblem is solved on the host.  Diagonal preconditioner, two passes of
+    Gram-Schmidt, restart with the current Ritz vectors when the space exceeds
+    ``max_space * nroots``.  Converged when every residual norm is below ``tol``.
+    """
+    import torch
+    na, nb, nd = ham.na, ham.nb, ham.ndet
+    hdiag = ham.hdiag()
+
+    def sym(v):
+        if spin0 and na == nb:
+            m = v.reshape(na, nb)
+            return (0.5 * (m + m.T)).reshape(-1)
+        return v
+
+    def orth(v, basis):
+        for _ in range(2):
+            for b in basis:
+                v = v - torch.dot(b, v) * b
+        nrm = torch.linalg.vector_norm(v)
+        return v, float(nrm)
+
+    # initial guesses: unit vectors on the lowest diagonal elements (symmetrised)
+    order = torch.argsort(hdiag)[: max(4 * nroots, 8)].tolist()
+    V = []
+    for k in order:
+        g = torch.zeros(nd, dtype=torch.float64, device=hdiag.device)
+        g[k] = 1.0
+        g, nrm = orth(sym(g), V)
+        if nrm > 1e-8:
+            V.append(g / nrm)
+        if len(V) == nroots:
+            break
+    W = [ham.contract(v) for v in V]
+    theta, X = None, None
+    for _cycle in range(max_cycle):
+        m = len(V)
+        Vm, Wm = torch.stack(V), torch.stack(W)
+        hsub = (Vm @ Wm.T).cpu().numpy()
+        hsub = 0.5 * (hsub + hsub.T)
+        w, s = np.linalg.eigh(hsub)
+        theta = w[:nroots]
+        S = torch.from_numpy(np.ascontiguousarray(s[:, :nroots].T)).to(Vm.device)
+        X = S @ Vm            # Ritz vectors (nroots, nd)
+        HX = S @ Wm
+        R = HX - torch.from_numpy(theta).to(Vm.device)[:, None] * X
+        rn = torch.linalg.vector_norm(R, dim=1).cpu().numpy()
+        if rn.max() < tol:
+            break
+        if m + nroots > max_space * nroots:   # restart from the Ritz vectors
+            V, W = [], []
+            for k in range(nroots):
+                v, nrm = orth(X[k].clone(), V)
+                V.append(v / nrm)
+            W = [ham.contract(v) for v in V]
+        added = 0
+        for k in range(nroots):
+            if rn[k] < tol:
+                continue
+            den = theta[k] - hdiag
+            den = torch.where(den.abs() < 1e-8, torch.full_like(den, -1e-8), den)
+            t, nrm = orth(sym(R[k] / den), V)
+            if nrm < 1e-10:
+                continue
+            V.append(t / nrm)
+            W.append(ham.contract(V[-1]))
+            added += 1
+        if added == 0:
+            break
+    else:
+        raise RuntimeError(f"FCI Davidson did not converge in {max_cycle} cycles (residuals {rn})")
+    out = []
+    for k in range(nroots):
+        v = sym(X[k])
+        out.append(v / torch.linalg.vector_norm(v))
+    return np.asarray(theta, dtype=np.float64), out
 
 
 def _unpack_nelec(nelec):
@@ -25,20 +106,26 @@ class B200FCISolver:
         self._base = base_solver
         self._device = device
 
-    # -- the part the reference delegates to PySCF's Davidson --------------------
-    def kernel(self, h1e, eri, norb, nelec, nroots=1, **kwargs):
-        base = self._base
-        if base is None:
-            try:
-                from pyscf import fci
-            except ImportError as exc:
-                raise NotImplementedError(
-                    "B200FCISolver.kernel needs a wrapped FCI eigensolver (pass "
-                    "base_solver=pyscf.fci.direct_spin0.FCI()) -- PySCF is not importable. "
-                    "Training vectors obtained elsewhere can be added with "
-                    "FCI_EVCont_obj.append_civec().") from exc
-            base = self._base = fci.direct_spin0.FCI()
-        return base.kernel(h1e, eri, norb, nelec, nroots=nroots, **kwargs)
+    # -- the FCI eigensolver (PySCF's Davidson in the reference, evcont/FCI_EVCont.py:70) ----
+    def kernel(self, h1e, eri, norb, nelec, nroots=1, tol=1e-10, max_cycle=200, max_space=12,
+               **kwargs):
+        """Lowest ``nroots`` FCI states: ``(e, c)`` for one root, ``(list e, list c)`` otherwise, ``c``
+        of shape ``(na, nb)`` -- the return convention of ``pyscf.fci.direct_spin0.FCI().kernel``.
+        A wrapped ``base_solver`` is used when one was given; otherwise a Davidson iteration whose
+        ``H c`` and ``diag H`` run on the device (``evc_fci_contract_2e`` / ``evc_fci_hdiag``).  For
+        ``n_alpha == n_beta`` the vectors are kept symmetric under alpha <-> beta exchange, as
+        ``direct_spin0`` does."""
+        if self._base is not None:
+            return self._base.kernel(h1e, eri, norb, nelec, nroots=nroots, **kwargs)
+        nelec = _unpack_nelec(nelec)
+        eng = get_engine(self._device)
+        ham = eng.fci_hamiltonian(h1e, eri, norb, nelec)
+        e, vecs = davidson(ham, nroots=nroots, tol=tol, max_cycle=max_cycle, max_space=max_space,
+                           spin0=(nelec[0] == nelec[1]))
+        cs = [v.reshape(ham.na, ham.nb).cpu().numpy() for v in vecs]
+        if nroots == 1:
+            return float(e[0]), cs[0]
+        return [float(x) for x in e], cs
 
     # -- K1 + K2 -------------------------------------------------------------------
     def trans_rdm12(self, cibra, ciket, norb, nelec, link_index=None, reorder=True):

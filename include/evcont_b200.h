@@ -324,6 +324,26 @@ int evc_md_velocities(evc_ctx *ctx, int nbatch, int natm, double dt, int first,
                       double *a, double *ekin, int *frame_idx, int max_frames, double *traj,
                       double *epot_log, double *ekin_log);
 
+/* ---- FCI Hamiltonian action (training side) ------------------------------------------
+ * What cisolver.kernel (evcont/FCI_EVCont.py:70; PySCF direct_spin0 Davidson:
+ * contract_2e + make_hdiag) needs from the Hamiltonian, on the device with the K0 link
+ * tables (string-major packing for BOTH spins here).
+ * evc_fci_hdiag: <K|H|K> for all determinants from the occupation strings (int64 bit
+ *   strings as evc_make_strings_host returns them, device copies), h1 [n][n], eri [n^4].
+ * evc_fci_contract_2e: sigma = H c.  h1eff: [n2p], n2p = n^2 rounded up to even, holding
+ *   h'_ps = h_ps - 1/2 sum_q (pq|qs) row-major, zero padded; w2: [n2p][n2p] with
+ *   w2[(rs)][(pq)] = 1/2 (pq|rs); civec, sigma: [na*nb].  D[K,(rs)] = <K|E_rs|c> is
+ *   gathered through the links, G = D w2 runs on the FP64 tensor cores, sigma gathers G
+ *   back through the links; deterministic. */
+int evc_fci_hdiag(evc_ctx *ctx, int norb, int64_t na, int64_t nb, const int64_t *strs_a,
+                  const int64_t *strs_b, const double *h1, const double *eri, double *hdiag);
+int evc_fci_contract_workspace_bytes(int norb, int64_t na, int64_t nb, size_t *bytes);
+int evc_fci_contract_2e(evc_ctx *ctx, int norb, int64_t na, int64_t nb,
+                        const uint64_t *link_a /* string-major */, int nlink_a,
+                        const uint64_t *link_b /* string-major */, int nlink_b,
+                        const double *h1eff, const double *w2, const double *civec,
+                        double *sigma, void *workspace, size_t workspace_bytes);
+
 #ifdef __cplusplus
 }
 #endif
