@@ -114,6 +114,8 @@ SIGNATURES = {
                                       C.c_size_t]),
     "evc_md_positions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p,
                                    c_double_p]),
+    "evc_md_berendsen": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                   c_double_p, c_double_p]),
     "evc_md_velocities": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int] + [c_double_p] * 8 +
                           [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]),
 }

@@ -58,6 +58,23 @@ __global__ void md_velocities_kernel(int nbatch, int natm, double dt, int first,
 
 __global__ void md_advance_frame_kernel(int* frame_idx) { *frame_idx += 1; }
 
+// Berendsen thermostat as pyscf.md.integrators.NVTBerendson applies it before each step:
+// v *= clip(sqrt(1 + (T / T_inst - 1) dt / taut), 0.9, 1.1),  T_inst = 2 E_kin / (3 natm k_B)
+__global__ void md_berendsen_kernel(int nbatch, int natm, double dt, double taut, double temperature, double kb,
+                                    const double* __restrict__ ekin, double* __restrict__ v) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= nbatch) return;
+  const int nc = natm * 3;
+  const double tinst = 2.0 * ekin[g] / (static_cast<double>(nc) * kb);
+  double f = 1.1;  // T_inst == 0: the ratio diverges and the clip applies
+  if (tinst > 0.0) {
+    const double a = 1.0 + (temperature / tinst - 1.0) * dt / taut;
+    f = a > 0.0 ? sqrt(a) : 0.9;
+    f = fmin(1.1, fmax(0.9, f));
+  }
+  for (int k = lane; k < nc; k += 32) v[static_cast<int64_t>(g) * nc + k] *= f;
+}
+
 }  // namespace
 
 extern "C" {
@@ -67,6 +84,17 @@ int evc_md_positions(evc_ctx* ctx, int nbatch, int natm, double dt, const double
   if (nbatch <= 0) return 0;
   const int64_t nc = static_cast<int64_t>(nbatch) * natm * 3;
   md_positions_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, ctx->stream>>>(nc, dt, v, a, x);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_md_berendsen(evc_ctx* ctx, int nbatch, int natm, double dt, double taut, double temperature,
+                     const double* ekin, double* v) {
+  EVC_REQUIRE(ctx && ekin && v, "evc_md_berendsen: NULL argument");
+  EVC_REQUIRE(taut > 0.0 && temperature >= 0.0, "evc_md_berendsen: taut must be positive, T non-negative");
+  if (nbatch <= 0) return 0;
+  md_berendsen_kernel<<<(nbatch + 3) / 4, 128, 0, ctx->stream>>>(nbatch, natm, dt, taut, temperature,
+                                                                  3.166811563e-6 /* Hartree / K */, ekin, v);
   EVC_CHECK_LAUNCH();
   return 0;
 }

@@ -291,6 +291,12 @@ class Engine:
         self._bind_stream()
         check(self.lib.evc_md_positions(self._ctx, G, natm, float(dt), _ptr(v), _ptr(a), _ptr(x)))
 
+    def md_berendsen(self, dt, taut, temperature, ekin, v):
+        G, natm = v.shape[0], v.shape[1]
+        self._bind_stream()
+        check(self.lib.evc_md_berendsen(self._ctx, G, natm, float(dt), float(taut), float(temperature),
+                                        _ptr(ekin), _ptr(v)))
+
     def md_velocities(self, dt, first, inv_mass, mass, grad, x, epot, v, a, ekin, frame_idx, max_frames,
                       traj=None, epot_log=None, ekin_log=None):
         G, natm = x.shape[0], x.shape[1]

@@ -69,7 +69,11 @@ class DeviceNVE:
                           self.a, self.ekin, self.frame_idx, self.max_frames, self.traj, self.epot_log,
                           self.ekin_log)
 
+    def _thermostat(self):
+        """Hook called before the positions update (NVE: nothing)."""
+
     def _step(self):
+        self._thermostat()
         self.engine.md_positions(self.dt, self.x, self.v, self.a)
         self._force(first=False)
 
@@ -105,3 +109,17 @@ class DeviceNVE:
         torch.cuda.synchronize(self.engine.device)
         n = min(int(self.frame_idx.item()), self.max_frames)
         return (self.traj[:n].cpu().numpy(), self.epot_log[:n].cpu().numpy(), self.ekin_log[:n].cpu().numpy())
+
+
+class DeviceNVT(DeviceNVE):
+    """Berendsen-thermostatted trajectories (``pyscf.md.NVTBerendson(scanner, T=, taut=)``, as in the
+    reference's Zundel scripts): the velocities are rescaled by
+    ``clip(sqrt(1 + (T/T_inst - 1) dt/taut), 0.9, 1.1)`` before every step."""
+
+    def __init__(self, mol, one_rdm, two_rdm, overlap, coords0, veloc0=None, dt=10.0, T=298.15, taut=250.0,
+                 **kwargs):
+        self.T, self.taut = float(T), float(taut)
+        super().__init__(mol, one_rdm, two_rdm, overlap, coords0, veloc0, dt=dt, **kwargs)
+
+    def _thermostat(self):
+        self.engine.md_berendsen(self.dt, self.taut, self.T, self.ekin, self.v)

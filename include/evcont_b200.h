@@ -318,6 +318,11 @@ int evc_ao_integrals_s(evc_ctx *ctx, const evc_sbasis *basis, int nbatch, const 
  * epot_log / ekin_log [max_frames][nbatch] may be NULL. */
 int evc_md_positions(evc_ctx *ctx, int nbatch, int natm, double dt, const double *v,
                      const double *a, double *x);
+/* Berendsen velocity rescaling (pyscf.md.NVTBerendson, used by the reference's Zundel
+ * scripts with T = 298.15 K, taut = 250 a.u.): called before evc_md_positions;
+ * v *= clip(sqrt(1 + (T/T_inst - 1) dt/taut), 0.9, 1.1), T_inst from ekin [nbatch]. */
+int evc_md_berendsen(evc_ctx *ctx, int nbatch, int natm, double dt, double taut,
+                     double temperature, const double *ekin, double *v);
 int evc_md_velocities(evc_ctx *ctx, int nbatch, int natm, double dt, int first,
                       const double *inv_mass /* [natm] */, const double *mass /* [natm] */,
                       const double *grad, const double *x, const double *epot, double *v,

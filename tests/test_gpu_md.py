@@ -77,3 +77,19 @@ def test_energy_conservation_second_order():
         etot = epot[:, 0] + ekin[:, 0]
         drift.append(np.abs(etot - etot[0]).max())
     assert drift[0] < 1e-2 and drift[1] < 0.4 * drift[0] + 1e-12, drift
+
+
+def test_berendsen_thermostat_against_oracle():
+    from evcont_b200.md import DeviceNVT, atomic_masses
+    from oracle import md as omd
+    mol, ovlp, one, two = _setup()
+    rng = np.random.default_rng(5)
+    v0 = 3e-4 * rng.standard_normal((mol.natm, 3))
+    steps, dt = 10, 5.0
+    nvt = DeviceNVT(mol, one, two, ovlp, mol.atom_coords()[None], v0[None], dt=dt, T=298.15, taut=250.0,
+                    max_frames=steps).run(steps - 1)
+    traj, _, ekin = nvt.frames()
+    ref, _, ekin_ref = omd.velocity_verlet(mol.atom_coords(), v0, atomic_masses(mol), dt, steps,
+                                          _oracle_force(mol, one, two, ovlp), berendsen=(298.15, 250.0))
+    assert np.abs(traj[:, 0] - ref).max() < 1e-9
+    assert np.abs(ekin[:, 0] - ekin_ref).max() < 1e-11
