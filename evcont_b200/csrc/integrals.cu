@@ -45,7 +45,7 @@ constexpr int kMaxAtoms = 64;
 }  // namespace
 
 struct evc_sbasis {
-  int natm, nao, nprim, ndexp, npe, npc, maxpp;
+  int natm, nao, nprim, ndexp, npe, npc, maxpp, pairs_in_smem;
   // device tables
   int32_t* ao_atom;    // [nao]
   int32_t* ao_poff;    // [nao + 1]
@@ -136,35 +136,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// shared memory: boys table | pp table (if it fits) | atom coordinates | primitive pairs | bounds
-//   primitive pair record, two arrays of double2: (bh = a_j/p, mu) and (Kc, pe as an int in the
-//   low word) -- 16-byte stride keeps the lane-consecutive 16-byte loads conflict-free; the records
-//   of a contracted pair are sorted by their Schwarz bound sqrt([ij|ij]) (descending, in sb[])
-//   so that the significant primitive quartets of (ab|cd) form a leading rectangle.
-template <bool PP_IN_SMEM>
-__global__ void __launch_bounds__(kIntThreads, 2)
-sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
-  extern __shared__ __align__(16) double sm[];
-  const int n = bs.nao, natm = bs.natm, npe = bs.npe;
-  double* boys = sm;
-  double* ppt = boys + 2 * kBoysN + 2;                            // [npe][npe][2]
-  double* R = ppt + (PP_IN_SMEM ? 2 * npe * npe : 0);             // [natm][3]
-  double2* pra = reinterpret_cast<double2*>(R + ((3 * natm + 1) & ~1));  // [maxpp] (bh, mu)
-  double2* prb = pra + bs.maxpp;                                         // [maxpp] (Kc, pe)
-  float* sb = reinterpret_cast<float*>(prb + bs.maxpp);           // [maxpp] sorted bounds
-  // unsorted bounds (scratch of the pair build): in the Boys region, which is filled afterwards
-  float* su = (static_cast<size_t>(bs.maxpp) * sizeof(float) <= 2 * kBoysN * sizeof(double))
-                  ? reinterpret_cast<float*>(boys) : sb + bs.maxpp;
-  const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NW = kIntThreads / 32;
-  const double* Rg = coords + static_cast<int64_t>(g) * natm * 3;
-
-  if (PP_IN_SMEM)
-    for (int k = tid; k < 2 * npe * npe; k += kIntThreads) ppt[k] = __ldg(bs.pp + k);
-  for (int k = tid; k < 3 * natm; k += kIntThreads) R[k] = Rg[k];
-  __syncthreads();
-  // primitive pairs of every contracted pair a >= b (all ordered primitive combinations)
-  for (int I = warp; I < bs.npc; I += NW) {
+// Primitive pairs of the contracted pairs a >= b (all ordered primitive combinations) for the warps
+// [warp0, warp0 + nwarps) of the caller: records sorted by Schwarz bound sqrt([ij|ij]), descending.
+__device__ __forceinline__ void build_pairs(const BasisView& bs, const double* __restrict__ R, int warp, int nwarps,
+                                            int lane, double2* pra, double2* prb, float* sb, float* su) {
+  for (int I = warp; I < bs.npc; I += nwarps) {
     int a, b;
     tri_unrank(I, a, b);
     const int pa0 = bs.ao_poff[a], na = bs.ao_poff[a + 1] - pa0;
@@ -209,7 +185,68 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
       sb[off + rank] = bd;
     }
   }
+}
+
+// global-memory pair tables (systems whose tables exceed shared memory): per geometry
+//   [maxpp] double2 (bh, mu) | [maxpp] double2 (Kc, pe) | [maxpp] float bounds | [maxpp] float scratch
+__host__ __device__ inline size_t pair_table_bytes(int maxpp) {
+  return (static_cast<size_t>(maxpp) * (2 * sizeof(double2) + 2 * sizeof(float)) + 255) / 256 * 256;
+}
+
+__global__ void __launch_bounds__(kIntThreads)
+spairs_kernel(BasisView bs, const double* __restrict__ coords, char* __restrict__ tables) {
+  __shared__ double R[3 * kMaxAtoms];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  for (int k = tid; k < 3 * bs.natm; k += kIntThreads) R[k] = coords[static_cast<int64_t>(g) * bs.natm * 3 + k];
   __syncthreads();
+  char* base = tables + static_cast<size_t>(g) * pair_table_bytes(bs.maxpp);
+  double2* pra = reinterpret_cast<double2*>(base);
+  double2* prb = pra + bs.maxpp;
+  float* sb = reinterpret_cast<float*>(prb + bs.maxpp);
+  build_pairs(bs, R, tid >> 5, kIntThreads / 32, tid & 31, pra, prb, sb, sb + bs.maxpp);
+}
+
+// shared memory: boys table | pp table (if it fits) | atom coordinates | primitive pairs | bounds
+//   primitive pair record, two arrays of double2: (bh = a_j/p, mu) and (Kc, pe as an int in the
+//   low word) -- 16-byte stride keeps the lane-consecutive 16-byte loads conflict-free; the records
+//   of a contracted pair are sorted by their Schwarz bound sqrt([ij|ij]) (descending, in sb[])
+//   so that the significant primitive quartets of (ab|cd) form a leading rectangle.
+//   PAIRS_IN_SMEM == false: the tables were built by spairs_kernel in global memory (L2-resident).
+template <bool PP_IN_SMEM, bool PAIRS_IN_SMEM>
+__global__ void __launch_bounds__(kIntThreads, 2)
+sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out, const char* __restrict__ tables) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = bs.nao, natm = bs.natm, npe = bs.npe;
+  double* boys = sm;
+  double* ppt = boys + 2 * kBoysN + 2;                            // [npe][npe][2]
+  double* R = ppt + (PP_IN_SMEM ? 2 * npe * npe : 0);             // [natm][3]
+  const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = kIntThreads / 32;
+  const double* Rg = coords + static_cast<int64_t>(g) * natm * 3;
+  const double2* pra;
+  const double2* prb;
+  const float* sb;
+
+  if (PP_IN_SMEM)
+    for (int k = tid; k < 2 * npe * npe; k += kIntThreads) ppt[k] = __ldg(bs.pp + k);
+  for (int k = tid; k < 3 * natm; k += kIntThreads) R[k] = Rg[k];
+  __syncthreads();
+  if (PAIRS_IN_SMEM) {
+    double2* wa = reinterpret_cast<double2*>(R + ((3 * natm + 1) & ~1));  // [maxpp] (bh, mu)
+    double2* wb = wa + bs.maxpp;                                          // [maxpp] (Kc, pe)
+    float* ws = reinterpret_cast<float*>(wb + bs.maxpp);                  // [maxpp] sorted bounds
+    // unsorted bounds (scratch of the pair build): in the Boys region, which is filled afterwards
+    float* su = (static_cast<size_t>(bs.maxpp) * sizeof(float) <= 2 * kBoysN * sizeof(double))
+                    ? reinterpret_cast<float*>(boys) : ws + bs.maxpp;
+    build_pairs(bs, R, warp, NW, lane, wa, wb, ws, su);
+    pra = wa; prb = wb; sb = ws;
+    __syncthreads();
+  } else {
+    const char* base = tables + static_cast<size_t>(g) * pair_table_bytes(bs.maxpp);
+    pra = reinterpret_cast<const double2*>(base);
+    prb = pra + bs.maxpp;
+    sb = reinterpret_cast<const float*>(prb + bs.maxpp);
+  }
   for (int k = tid; k < 2 * kBoysN; k += kIntThreads) boys[k] = __ldg(bs.boys + k);
   __syncthreads();
 
@@ -456,11 +493,12 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out) {
   }
 }
 
-size_t sint_smem_bytes(const evc_sbasis* b, bool pp_in_smem) {
+size_t sint_smem_bytes(const evc_sbasis* b, bool pp_in_smem, bool pairs_in_smem) {
   size_t d = 2 * static_cast<size_t>(kBoysN) + 2 + (pp_in_smem ? 2 * static_cast<size_t>(b->npe) * b->npe : 0) +
              ((3 * static_cast<size_t>(b->natm) + 1) & ~static_cast<size_t>(1));
+  if (!pairs_in_smem) return d * sizeof(double);
   const bool su_in_boys = static_cast<size_t>(b->maxpp) * sizeof(float) <= 2 * kBoysN * sizeof(double);
-  return d * sizeof(double) + static_cast<size_t>(b->maxpp) * (sizeof(double4) + (su_in_boys ? 1 : 2) * sizeof(float));
+  return d * sizeof(double) + static_cast<size_t>(b->maxpp) * (2 * sizeof(double2) + (su_in_boys ? 1 : 2) * sizeof(float));
 }
 
 template <typename T>
@@ -565,8 +603,7 @@ int evc_sbasis_create(evc_ctx* ctx, int natm, const double* charges_host, int na
     delete b;
     return rc;
   }
-  EVC_REQUIRE(sint_smem_bytes(b, false) <= ctx->smem_optin,
-              "evc_sbasis_create: %d primitive pairs do not fit in shared memory", b->maxpp);
+  b->pairs_in_smem = sint_smem_bytes(b, false, true) <= 113 * 1024 ? 1 : 0;  // two CTAs per SM
   *out = b;
   return 0;
 }
@@ -585,12 +622,22 @@ int evc_sbasis_nao(const evc_sbasis* b) { return b ? b->nao : -1; }
 int evc_sbasis_natm(const evc_sbasis* b) { return b ? b->natm : -1; }
 const int32_t* evc_sbasis_aoslices(const evc_sbasis* b) { return b ? b->aoslices : nullptr; }
 
+int evc_ao_integrals_s_workspace_bytes(const evc_sbasis* b, int nbatch, size_t* bytes) {
+  EVC_REQUIRE(b && bytes && nbatch >= 0, "evc_ao_integrals_s_workspace_bytes: bad arguments");
+  *bytes = b->pairs_in_smem ? 256 : static_cast<size_t>(nbatch) * pair_table_bytes(b->maxpp) + 256;
+  return 0;
+}
+
 int evc_ao_integrals_s(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const double* coords, double* ovlp,
                        double* hcore, double* eri, double* ipovlp, double* hcore_deriv, double* eri_ip1,
-                       double* e_nuc, double* grad_nuc) {
+                       double* e_nuc, double* grad_nuc, void* workspace, size_t workspace_bytes) {
   EVC_REQUIRE(ctx && b && coords && ovlp && hcore && eri && ipovlp && hcore_deriv && eri_ip1 && e_nuc && grad_nuc,
               "evc_ao_integrals_s: NULL argument");
   if (nbatch <= 0) return 0;
+  size_t need = 0;
+  evc_ao_integrals_s_workspace_bytes(b, nbatch, &need);
+  EVC_REQUIRE(b->pairs_in_smem || (workspace && workspace_bytes >= need),
+              "evc_ao_integrals_s: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
   BasisView v;
   v.natm = b->natm; v.nao = b->nao; v.nprim = b->nprim; v.npe = b->npe; v.npc = b->npc; v.maxpp = b->maxpp;
   v.ao_atom = b->ao_atom; v.ao_poff = b->ao_poff; v.prim_de = b->prim_de; v.pc_off = b->pc_off;
@@ -599,20 +646,29 @@ int evc_ao_integrals_s(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const doub
   IntOut o{ovlp, hcore, eri, ipovlp, hcore_deriv, eri_ip1, e_nuc, grad_nuc};
   // few geometries: several CTAs per geometry so that the whole GPU works on them
   int split = 1;
-  const int nq = b->npc * (b->npc + 1) / 2, nw = kIntThreads / 32;
-  while (static_cast<long long>(nbatch) * split < 2LL * ctx->sm_count && split * nw * 4 <= nq) split *= 2;
-  const bool pp_in = sint_smem_bytes(b, true) <= 113 * 1024;  // two CTAs per SM
-  const size_t smem = sint_smem_bytes(b, pp_in);
-  dim3 grid(split, nbatch);
-  if (pp_in) {
-    EVC_CHECK_CUDA(cudaFuncSetAttribute(sint_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    sint_kernel<true><<<grid, kIntThreads, smem, ctx->stream>>>(v, coords, o);
-  } else {
-    EVC_CHECK_CUDA(cudaFuncSetAttribute(sint_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    sint_kernel<false><<<grid, kIntThreads, smem, ctx->stream>>>(v, coords, o);
+  const long long nq = static_cast<long long>(b->npc) * (b->npc + 1) / 2;
+  const int nw = kIntThreads / 32;
+  while (static_cast<long long>(nbatch) * split < 2LL * ctx->sm_count && static_cast<long long>(split) * nw * 4 <= nq &&
+         split < 1024)
+    split *= 2;
+  const bool pairs_in = b->pairs_in_smem != 0;
+  const bool pp_in = sint_smem_bytes(b, true, pairs_in) <= 113 * 1024;  // two CTAs per SM
+  const size_t smem = sint_smem_bytes(b, pp_in, pairs_in);
+  char* tables = static_cast<char*>(workspace);
+  if (!pairs_in) {
+    spairs_kernel<<<nbatch, kIntThreads, 0, ctx->stream>>>(v, coords, tables);
+    EVC_CHECK_LAUNCH();
   }
+  dim3 grid(split, nbatch);
+#define EVC_SINT(PP, PR)                                                                                     \
+  do {                                                                                                       \
+    EVC_CHECK_CUDA(cudaFuncSetAttribute(sint_kernel<PP, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                        static_cast<int>(smem)));                                            \
+    sint_kernel<PP, PR><<<grid, kIntThreads, smem, ctx->stream>>>(v, coords, o, tables);                     \
+  } while (0)
+  if (pairs_in) { if (pp_in) EVC_SINT(true, true); else EVC_SINT(false, true); }
+  else { if (pp_in) EVC_SINT(true, false); else EVC_SINT(false, false); }
+#undef EVC_SINT
   EVC_CHECK_LAUNCH();
   return 0;
 }

@@ -272,11 +272,14 @@ class Engine:
         ao = out if out is not None else DeviceAO(self, G, sbasis.nao, sbasis.natm, sbasis.aoslices_host)
         if ao.nbatch != G or ao.nao != sbasis.nao or ao.natm != sbasis.natm:
             raise ValueError("DeviceAO does not match the basis / batch size")
+        nbytes = C.c_size_t()
+        check(self.lib.evc_ao_integrals_s_workspace_bytes(sbasis.handle, G, C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
         self._bind_stream()
         check(self.lib.evc_ao_integrals_s(self._ctx, sbasis.handle, G, _ptr(coords), _ptr(ao.ovlp),
                                           _ptr(ao.hcore), _ptr(ao.eri), _ptr(ao.ipovlp),
                                           _ptr(ao.hcore_deriv), _ptr(ao.eri_ip1), _ptr(ao.e_nuc),
-                                          _ptr(ao.grad_nuc)))
+                                          _ptr(ao.grad_nuc), _ptr(ws), ws.numel()))
         return ao
 
     def energy_with_grad_coords(self, stack, sbasis, coords, ao=None, out=None, want_rdms=False):

@@ -291,7 +291,10 @@ int evc_energy_with_grad_packed_host(evc_ctx *ctx, int ntrain, int n, int natm, 
  *   during evc_ao_integrals_s).  natm <= 64, nao <= 64, <= 16 primitives per AO.
  * evc_ao_integrals_s: coords [nbatch][natm][3] (bohr, device) -> the evc_ao_bundle
  *   arrays of every geometry, in the layouts documented at evc_ao_bundle;
- *   aoslices for the bundle come from evc_sbasis_aoslices (device, [natm][2]). */
+ *   aoslices for the bundle come from evc_sbasis_aoslices (device, [natm][2]).  The
+ *   primitive-pair tables of a geometry live in shared memory when they fit (H10/STO-6G:
+ *   1980 pairs); larger systems (H30: 16 740 pairs) build them in `workspace` first
+ *   (evc_ao_integrals_s_workspace_bytes; 256 bytes otherwise). */
 typedef struct evc_sbasis evc_sbasis;
 int evc_sbasis_create(evc_ctx *ctx, int natm, const double *charges_host, int nao,
                       const int32_t *ao_atom_host, const int32_t *ao_nprim_host,
@@ -301,9 +304,11 @@ int evc_sbasis_destroy(evc_sbasis *basis);
 int evc_sbasis_nao(const evc_sbasis *basis);
 int evc_sbasis_natm(const evc_sbasis *basis);
 const int32_t *evc_sbasis_aoslices(const evc_sbasis *basis);
+int evc_ao_integrals_s_workspace_bytes(const evc_sbasis *basis, int nbatch, size_t *bytes);
 int evc_ao_integrals_s(evc_ctx *ctx, const evc_sbasis *basis, int nbatch, const double *coords,
                        double *ovlp, double *hcore, double *eri, double *ipovlp,
-                       double *hcore_deriv, double *eri_ip1, double *e_nuc, double *grad_nuc);
+                       double *hcore_deriv, double *eri_ip1, double *e_nuc, double *grad_nuc,
+                       void *workspace, size_t workspace_bytes);
 
 /* ---- device-resident velocity Verlet (batched over trajectories) ------------------
  * Replaces the host loop of pyscf.md.NVE that get_trajectory drives

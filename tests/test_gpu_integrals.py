@@ -55,6 +55,21 @@ def test_h10_batch_against_oracle_and_split_invariance():
             assert np.abs(got_big[k][g] - ref[k]).max() < TOL, k
 
 
+def test_large_system_global_pair_tables():
+    """14 hydrogens: 3780 primitive pairs do not fit the shared-memory budget, so the pair tables are
+    built in the caller's workspace (spairs_kernel) -- the path H30 (BASELINE configs[3]) takes."""
+    from oracle import integrals as oi
+    co = _chain(14, d=1.9, radius=0.2, seed=11)
+    got, _ = _device_arrays(["H"] * 14, "sto-6g", np.stack([co] * 3))
+    ref = oi.ao_arrays(oi.SBasis([("H", c) for c in co], "sto-6g"))
+    for k in FIELDS:
+        assert np.abs(got[k][0] - ref[k]).max() < TOL, k
+        assert np.array_equal(got[k][0], got[k][2]), k
+    big, _ = _device_arrays(["H"] * 14, "sto-6g", np.stack([co] * 600))   # no quartet split
+    for k in FIELDS:
+        assert np.array_equal(got[k][0], big[k][599]), k
+
+
 def test_symmetries_on_device():
     got, _ = _device_arrays(["H"] * 6, "sto-6g", _chain(6, seed=7)[None])
     eri, ip1 = got["eri"][0], got["eri_ip1"][0]
