@@ -1,7 +1,9 @@
 // K6, lowest root only: H c = E S c for the ground state of the subspace problem
 // (evcont/ab_initio_eigenvector_continuation.py:75-88: eigh(H, S), argmin).
 //
-// One WARP per geometry, no block-level barriers:
+// One TEAM of threads per geometry: a warp (no block-level barriers; large batches) or a whole
+// 256-thread CTA (few geometries: the O(N^3) products and the Householder updates are spread over
+// the CTA instead of 32 lanes -- 1.49 ms -> ~0.1 ms for one N = 100 problem):
 //   A = L^-1 H L^-T                        (S = L L^T factored once per stack)
 //   A = Q T Q^T                            Householder tridiagonalisation in shared memory
 //   lambda_min(T)                          32-way multisection on Sturm counts (LAPACK dstebz recurrence)
@@ -26,16 +28,35 @@ __host__ __device__ inline size_t lowest_warp_doubles(int N) {
   return 2 * static_cast<size_t>(N) * (N + 1) + 10 * static_cast<size_t>(N) + 2;
 }
 
-__global__ void __launch_bounds__(128)
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM)
 geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restrict__ H,
                      const double* __restrict__ Linv, double* __restrict__ E, double* __restrict__ C) {
   extern __shared__ __align__(16) double sm[];
+  __shared__ double tred[TEAM == 32 ? 1 : TEAM / 32];
+  __shared__ double pw[TEAM == 32 ? 1 : TEAM / 32][TEAM == 32 ? 1 : 112];  // N <= 112
   const int wpc = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * wpc + warp;
-  if (b >= nbatch) return;  // whole warp; no block barriers below
+  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  const int b = TEAM == 32 ? blockIdx.x * wpc + warp : blockIdx.x;
+  if (b >= nbatch) return;  // whole team
+  const int lane = TEAM == 32 ? wl : static_cast<int>(threadIdx.x);  // index inside the team
+  auto team_sync = [&]() {
+    if (TEAM == 32) __syncwarp(); else __syncthreads();
+  };
+  // fixed-order sum over the team, result in every thread
+  auto team_sum = [&](double v) {
+    v = warp_sum(v);
+    if (TEAM == 32) return v;
+    __syncthreads();
+    if (wl == 0) tred[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < (TEAM == 32 ? 1 : TEAM / 32); ++w) t += tred[w];
+    return t;
+  };
   const int ld = N + 1;
-  double* A = sm + static_cast<size_t>(warp) * lowest_warp_doubles(N);
+  double* A = sm + (TEAM == 32 ? static_cast<size_t>(warp) * lowest_warp_doubles(N) : 0);
   double* M = A + N * ld;
   double* d = M + N * ld;
   double* e = d + N;        // e[i] couples i and i+1
@@ -51,89 +72,152 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
   // ---- M <- lower triangle of H, mirrored ----
   if (packed_lower) {
     const double* Hb = H + static_cast<int64_t>(b) * (N * (N + 1) / 2);
-    for (int k = lane; k < N * N; k += 32) {
+    for (int k = lane; k < N * N; k += TEAM) {
       const int i = k / N, j = k - i * N;
       const int hi = i > j ? i : j, lo = i > j ? j : i;
       M[i * ld + j] = Hb[hi * (hi + 1) / 2 + lo];
     }
   } else {
     const double* Hb = H + static_cast<int64_t>(b) * N * N;
-    for (int k = lane; k < N * N; k += 32) {
+    for (int k = lane; k < N * N; k += TEAM) {
       const int i = k / N, j = k - i * N;
       M[i * ld + j] = (i >= j) ? Hb[i * N + j] : Hb[j * N + i];
     }
   }
-  __syncwarp();
-  // ---- A <- Linv M   (Linv lower triangular) ----
-  for (int k = lane; k < N * N; k += 32) {
-    const int i = k / N, j = k - i * N;
-    double acc = 0.0;
-    for (int r = 0; r <= i; ++r) acc += __ldg(Linv + i * N + r) * M[r * ld + j];
-    A[i * ld + j] = acc;
+  team_sync();
+  if (TEAM == 32) {
+    // ---- A <- Linv M   (Linv lower triangular) ----
+    for (int k = lane; k < N * N; k += TEAM) {
+      const int i = k / N, j = k - i * N;
+      double acc = 0.0;
+      for (int r = 0; r <= i; ++r) acc += __ldg(Linv + i * N + r) * M[r * ld + j];
+      A[i * ld + j] = acc;
+    }
+    team_sync();
+    // ---- M <- A Linv^T, lower triangle computed and mirrored ----
+    for (int k = lane; k < N * N; k += TEAM) {
+      const int i = k / N, j = k - i * N;
+      if (j > i) continue;
+      double acc = 0.0;
+      for (int r = 0; r <= j; ++r) acc += A[i * ld + r] * __ldg(Linv + j * N + r);
+      M[i * ld + j] = acc;
+      M[j * ld + i] = acc;
+    }
+    team_sync();
+  } else {
+    // CTA team: dst[i][:] = sum_{r <= i} Linv[i][r] src[r][:], one warp per row i, the row of Linv in
+    // registers (broadcast by shuffle), lanes over the columns.  Pass 1 writes A^T = (Linv M)^T, pass 2
+    // gives Linv A^T = (A Linv^T)^T = M (symmetric), N <= 128.
+    constexpr int NWT = TEAM / 32;
+    for (int pass = 0; pass < 2; ++pass) {
+      const double* src = pass == 0 ? M : A;
+      double* dst = pass == 0 ? A : M;
+      for (int i = warp; i < N; i += NWT) {
+        double lr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) lr[q] = (wl + 32 * q <= i) ? __ldg(Linv + i * N + wl + 32 * q) : 0.0;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r <= i; ++r) {
+          const double lv = __shfl_sync(0xffffffffu, lr[r >> 5], r & 31);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (wl + 32 * q < N) acc[q] = fma(lv, src[r * ld + wl + 32 * q], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (wl + 32 * q < N) {
+            if (pass == 0) dst[(wl + 32 * q) * ld + i] = acc[q];   // transposed
+            else dst[i * ld + wl + 32 * q] = acc[q];
+          }
+      }
+      __syncthreads();
+    }
   }
-  __syncwarp();
-  // ---- M <- A Linv^T, lower triangle computed and mirrored ----
-  for (int k = lane; k < N * N; k += 32) {
-    const int i = k / N, j = k - i * N;
-    if (j > i) continue;
-    double acc = 0.0;
-    for (int r = 0; r <= j; ++r) acc += A[i * ld + r] * __ldg(Linv + j * N + r);
-    M[i * ld + j] = acc;
-    M[j * ld + i] = acc;
-  }
-  __syncwarp();
 
   // ---- Householder tridiagonalisation of M (both triangles kept up to date) ----
   for (int k = 0; k + 2 < N; ++k) {
     const int m = N - k - 1;
     double* col = M + (k + 1) * ld + k;  // u_i lives at col[i * ld]
     double part = 0.0;
-    for (int i = 1 + lane; i < m; i += 32) {
+    for (int i = 1 + lane; i < m; i += TEAM) {
       const double xv = col[i * ld];
       part += xv * xv;
     }
-    const double sigma = warp_sum(part);
+    const double sigma = team_sum(part);
     const double x0 = col[0];
     if (sigma == 0.0) {  // already tridiagonal in this column (warp-uniform)
       if (lane == 0) { e[k] = x0; tau[k] = 0.0; }
-      __syncwarp();
+      team_sync();
       continue;
     }
     const double mu = sqrt(x0 * x0 + sigma);
     const double alpha = (x0 <= 0.0) ? mu : -mu;
     const double u0 = x0 - alpha;
     const double taup = 2.0 / (u0 * u0 + sigma);
-    __syncwarp();
+    team_sync();
     if (lane == 0) { col[0] = u0; e[k] = alpha; tau[k] = taup; }
-    __syncwarp();
+    team_sync();
     // p = taup * M22 u ;  pu = p . u
     double pu_part = 0.0;
-    for (int i = lane; i < m; i += 32) {
-      const double* row = M + (k + 1 + i) * ld + k + 1;
-      double acc = 0.0;
-      for (int j = 0; j < m; ++j) acc += row[j] * col[j * ld];
-      const double p = taup * acc;
-      w1[i] = p;
-      pu_part += p * col[i * ld];
+    if (TEAM == 32) {
+      for (int i = lane; i < m; i += TEAM) {
+        const double* row = M + (k + 1 + i) * ld + k + 1;
+        double acc = 0.0;
+        for (int j = 0; j < m; ++j) acc += row[j] * col[j * ld];
+        const double p = taup * acc;
+        w1[i] = p;
+        pu_part += p * col[i * ld];
+      }
+    } else {
+      // M22 is symmetric: p_j = sum_i M22[i][j] u_i as column sums -- lanes own columns, the warps
+      // split the rows, no shuffle reduction; the per-warp partials are combined in a fixed order
+      for (int c0 = 0; c0 < m; c0 += 32) {
+        const int j = c0 + wl;
+        if (j < m) {
+          double acc = 0.0;
+          for (int i = warp; i < m; i += TEAM / 32) acc = fma(M[(k + 1 + i) * ld + k + 1 + j], col[i * ld], acc);
+          pw[warp][j] = acc;
+        }
+      }
+      __syncthreads();
+      for (int j = lane; j < m; j += TEAM) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < TEAM / 32; ++w) t += pw[w][j];
+        w1[j] = taup * t;
+      }
+      __syncthreads();
+      for (int i = lane; i < m; i += TEAM) pu_part += w1[i] * col[i * ld];
     }
-    const double pu = warp_sum(pu_part);
-    __syncwarp();
+    const double pu = team_sum(pu_part);
+    team_sync();
     // q = p - (taup/2) (p.u) u
-    for (int i = lane; i < m; i += 32) w1[i] -= 0.5 * taup * pu * col[i * ld];
-    __syncwarp();
+    for (int i = lane; i < m; i += TEAM) w1[i] -= 0.5 * taup * pu * col[i * ld];
+    team_sync();
     // M22 <- M22 - u q^T - q u^T
-    for (int i = lane; i < m; i += 32) {
-      double* row = M + (k + 1 + i) * ld + k + 1;
-      const double ui = col[i * ld], qi = w1[i];
-      for (int j = 0; j < m; ++j) row[j] -= ui * w1[j] + qi * col[j * ld];
+    if (TEAM == 32) {
+      for (int i = lane; i < m; i += TEAM) {
+        double* row = M + (k + 1 + i) * ld + k + 1;
+        const double ui = col[i * ld], qi = w1[i];
+        for (int j = 0; j < m; ++j) row[j] -= ui * w1[j] + qi * col[j * ld];
+      }
+    } else {
+      for (int i = warp; i < m; i += TEAM / 32) {
+        double* row = M + (k + 1 + i) * ld + k + 1;
+        const double ui = col[i * ld], qi = w1[i];
+        for (int j = wl; j < m; j += 32) row[j] -= ui * w1[j] + qi * col[j * ld];
+      }
     }
-    __syncwarp();
+    team_sync();
   }
-  for (int i = lane; i < N; i += 32) d[i] = M[i * ld + i];
+  for (int i = lane; i < N; i += TEAM) d[i] = M[i * ld + i];
   if (lane == 0 && N >= 2) e[N - 2] = M[(N - 1) * ld + N - 2];
-  __syncwarp();
+  team_sync();
 
-  // ---- lowest eigenvalue of T = tridiag(e, d, e): multisection on Sturm counts ----
+  // ---- lowest eigenvalue of T = tridiag(e, d, e): multisection on Sturm counts (first warp) ----
+  double lam = 0.0, tnorm = 0.0;
+  if (TEAM == 32) {
+    const int lane = wl;
   double glo = DBL_MAX, ghi = -DBL_MAX, emax = 0.0;
   for (int i = lane; i < N; i += 32) {
     const double el = i > 0 ? fabs(e[i - 1]) : 0.0, er = i + 1 < N ? fabs(e[i]) : 0.0;
@@ -147,7 +231,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
     emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   }
-  const double tnorm = fmax(fabs(glo), fabs(ghi));
+  tnorm = fmax(fabs(glo), fabs(ghi));
   const double pivmin = DBL_MIN * fmax(1.0, emax);
   double lo = glo - 2.0 * DBL_EPSILON * tnorm * N - 2.0 * pivmin;
   double hi = ghi + 2.0 * DBL_EPSILON * tnorm * N + 2.0 * pivmin;
@@ -171,7 +255,56 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     hi = (f < 32) ? lo + (f + 1) * h : hi;
     lo = nlo;
   }
-  const double lam = 0.5 * (lo + hi);
+  lam = 0.5 * (lo + hi);
+
+  }
+  if (TEAM != 32) {
+    // CTA team: TEAM-way multisection (every thread one sample point per round)
+    double glo = DBL_MAX, ghi = -DBL_MAX, emax = 0.0;
+    for (int i = wl; i < N; i += 32) {   // every warp redundantly: identical values everywhere
+      const double el = i > 0 ? fabs(e[i - 1]) : 0.0, er = i + 1 < N ? fabs(e[i]) : 0.0;
+      glo = fmin(glo, d[i] - el - er);
+      ghi = fmax(ghi, d[i] + el + er);
+      emax = fmax(emax, er * er);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      glo = fmin(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+      ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+      emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    }
+    tnorm = fmax(fabs(glo), fabs(ghi));
+    const double pivmin = DBL_MIN * fmax(1.0, emax);
+    double lo = glo - 2.0 * DBL_EPSILON * tnorm * N - 2.0 * pivmin;
+    double hi = ghi + 2.0 * DBL_EPSILON * tnorm * N + 2.0 * pivmin;
+    for (int it = 0; it < 8; ++it) {
+      const double width = hi - lo;
+      if (width <= 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) break;  // team-uniform
+      const double h = width / (TEAM + 1);
+      const double xs = lo + (lane + 1) * h;
+      double q = d[0] - xs;
+      if (fabs(q) < pivmin) q = -pivmin;
+      int cnt = q < 0.0;
+      for (int i = 1; i < N; ++i) {
+        const double ei = e[i - 1];
+        q = d[i] - xs - ei * ei / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += q < 0.0;
+      }
+      const unsigned ball = __ballot_sync(0xffffffffu, cnt >= 1);
+      __syncthreads();
+      if (wl == 0) tred[warp] = static_cast<double>(ball ? warp * 32 + __ffs(ball) - 1 : TEAM);
+      __syncthreads();
+      double fmin_ = static_cast<double>(TEAM);
+#pragma unroll
+      for (int w = 0; w < TEAM / 32; ++w) fmin_ = fmin(fmin_, tred[w]);
+      const int f = static_cast<int>(fmin_);   // first sample point with an eigenvalue below it
+      const double nlo = lo + f * h;
+      hi = (f < TEAM) ? lo + (f + 1) * h : hi;
+      lo = nlo;
+    }
+    lam = 0.5 * (lo + hi);
+  }
 
   // ---- eigenvector of T by inverse iteration (lane 0; pivoted LU of T - lam I) ----
   if (lane == 0) {
@@ -236,7 +369,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     }
     E[b] = rq;
   }
-  __syncwarp();
+  team_sync();
 
   // ---- y = H_0 H_1 ... H_{N-3} z ----
   for (int k = N - 3; k >= 0; --k) {
@@ -245,14 +378,14 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     const int m = N - k - 1;
     const double* col = M + (k + 1) * ld + k;
     double part = 0.0;
-    for (int i = lane; i < m; i += 32) part += col[i * ld] * z[k + 1 + i];
-    const double s = taup * warp_sum(part);
-    for (int i = lane; i < m; i += 32) z[k + 1 + i] -= s * col[i * ld];
-    __syncwarp();
+    for (int i = lane; i < m; i += TEAM) part += col[i * ld] * z[k + 1 + i];
+    const double s = taup * team_sum(part);
+    for (int i = lane; i < m; i += TEAM) z[k + 1 + i] -= s * col[i * ld];
+    team_sync();
   }
   // ---- c = Linv^T y ----
   double* Cb = C + static_cast<int64_t>(b) * N;
-  for (int i = lane; i < N; i += 32) {
+  for (int i = lane; i < N; i += TEAM) {
     double acc = 0.0;
     for (int r = i; r < N; ++r) acc += __ldg(Linv + r * N + i) * z[r];
     Cb[i] = acc;
@@ -265,12 +398,21 @@ int evc_launch_geneig_lowest(evc_ctx* ctx, int nbatch, int N, int packed_lower, 
                              const double* Linv, double* E, double* C) {
   const size_t per_warp = lowest_warp_doubles(N) * sizeof(double);
   EVC_REQUIRE(per_warp <= ctx->smem_optin, "geneig: N=%d needs %zu bytes of shared memory", N, per_warp);
+  if (nbatch <= 2 * ctx->sm_count) {
+    // few geometries: one 256-thread CTA each
+    EVC_CHECK_CUDA(cudaFuncSetAttribute(geneig_lowest_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(per_warp)));
+    geneig_lowest_kernel<256><<<nbatch, 256, per_warp, ctx->stream>>>(N, packed_lower, nbatch, H, Linv, E, C);
+    EVC_CHECK_LAUNCH();
+    return 0;
+  }
   int wpc = 4;
   while (wpc > 1 && (wpc * per_warp > ctx->smem_optin || wpc * per_warp > 48 * 1024)) wpc >>= 1;
   const size_t smem = wpc * per_warp;
-  EVC_CHECK_CUDA(cudaFuncSetAttribute(geneig_lowest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  EVC_CHECK_CUDA(cudaFuncSetAttribute(geneig_lowest_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-  geneig_lowest_kernel<<<(nbatch + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(N, packed_lower, nbatch, H, Linv, E, C);
+  geneig_lowest_kernel<32><<<(nbatch + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(N, packed_lower, nbatch, H, Linv,
+                                                                                      E, C);
   EVC_CHECK_LAUNCH();
   return 0;
 }

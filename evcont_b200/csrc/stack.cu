@@ -134,28 +134,31 @@ __device__ __forceinline__ void tril_unrank(int64_t t, int& a, int& b) {
 }
 
 // H[g][a][b] = one_rdm[a][b] . h1[g] + scale * sum_chunks partial
-// partial element (g, p, c) lives at partial[g*sg + p*sp + c*sc]
+// partial element (g, p, c) lives at partial[g*sg + p*sp + c*sc].  One WARP per (a, b): the lanes
+// run over the n^2 one-body elements (coalesced) and over the chunks; fixed butterfly reduction.
 __global__ void assemble_H_kernel(int N, int n2, int tril, double scale, int P, int nchunk,
                                   int64_t sg, int64_t sp, int64_t sc,
                                   const double* __restrict__ one_rdm, const double* __restrict__ h1,
                                   const double* __restrict__ partial, double* __restrict__ H) {
-  const int g = blockIdx.y;
-  const int ab = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y, lane = threadIdx.x & 31;
+  const int ab = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ab >= N * N) return;
   const int a = ab / N, b = ab - a * N;
   const double* r1 = one_rdm + static_cast<int64_t>(ab) * n2;
   const double* hg = h1 + static_cast<int64_t>(g) * n2;
   double one = 0.0;
-  for (int k = 0; k < n2; ++k) one += r1[k] * hg[k];
+  for (int k = lane; k < n2; k += 32) one = fma(r1[k], hg[k], one);
   double two = 0.0;
   int p = -1;
   if (!tril) p = ab;
   else if (a >= b) p = a * (a + 1) / 2 + b;
   if (p >= 0) {
     const double* pp = partial + g * sg + p * sp;
-    for (int c = 0; c < nchunk; ++c) two += pp[c * sc];
+    for (int c = lane; c < nchunk; c += 32) two += pp[c * sc];
   }
-  H[static_cast<int64_t>(g) * N * N + ab] = one + scale * two;
+  double v = one + scale * two;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) H[static_cast<int64_t>(g) * N * N + ab] = v;
 }
 
 // w[g][P] from the ground-state vector: c_a c_b (full) or tril-weighted
@@ -177,21 +180,48 @@ __global__ void pair_weights_kernel(int N, int tril, int P, const double* __rest
   w[static_cast<int64_t>(g) * P + p] = v;
 }
 
-// gamma[g][pq] = sum_ab c_a c_b one_rdm[ab][pq]
-__global__ void gamma1_kernel(int N, int n2, const double* __restrict__ one_rdm,
-                              const double* __restrict__ C, int64_t c_stride,
-                              double* __restrict__ gamma) {
-  const int g = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n2) return;
+// gamma[g][pq] = sum_ab c_a c_b one_rdm[ab][pq].  One CTA per (32 columns, geometry): the 16 warps
+// walk the N^2 rows with stride 16 (coalesced 256-byte reads, 8 in flight per warp) and are combined
+// in a fixed order, so the one-body stack (62.7 MB at N = 100, n = 28) streams instead of being walked
+// by n^2 threads one row at a time.
+constexpr int kG1Warps = 16;
+__global__ void __launch_bounds__(kG1Warps * 32)
+gamma1_kernel(int N, int n2, const double* __restrict__ one_rdm, const double* __restrict__ C, int64_t c_stride,
+              double* __restrict__ gamma) {
+  __shared__ double red[kG1Warps][33];
+  extern __shared__ double cs[];  // c[N]
+  const int g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 32 + lane;
   const double* c = C + static_cast<int64_t>(g) * c_stride;
+  for (int a = threadIdx.x; a < N; a += kG1Warps * 32) cs[a] = c[a];
+  __syncthreads();
+  const int P = N * N;
+  const bool live = k < n2;
+  const double* col = one_rdm + (live ? k : 0);
   double acc = 0.0;
-  for (int a = 0; a < N; ++a) {
-    const double ca = c[a];
-    for (int b = 0; b < N; ++b)
-      acc += ca * c[b] * one_rdm[(static_cast<int64_t>(a) * N + b) * n2 + k];
+  int ab = warp;
+  for (; ab + 7 * kG1Warps < P; ab += 8 * kG1Warps) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(col + static_cast<int64_t>(ab + u * kG1Warps) * n2);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = ab + u * kG1Warps, a = r / N, b = r - a * N;
+      acc = fma(cs[a] * cs[b], v[u], acc);
+    }
   }
-  gamma[static_cast<int64_t>(g) * n2 + k] = acc;
+  for (; ab < P; ab += kG1Warps) {
+    const int a = ab / N, b = ab - a * N;
+    acc = fma(cs[a] * cs[b], __ldg(col + static_cast<int64_t>(ab) * n2), acc);
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && live) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kG1Warps; ++w) t += red[w][lane];
+    gamma[static_cast<int64_t>(g) * n2 + k] = t;
+  }
 }
 
 // K7 streaming form: part[split][g][l] = sum_{p in split} w[g][p] R2[p][l].
@@ -512,7 +542,7 @@ int evc_subspace_H(evc_ctx* ctx, int layout, int N, int n, const double* one_rdm
     EVC_CHECK_LAUNCH();
   }
   {
-    dim3 grid((N * N + 127) / 128, nbatch);
+    dim3 grid((N * N + 3) / 4, nbatch);  // 4 warps per CTA, one warp per (a, b)
     const int64_t sg = gemm ? P : static_cast<int64_t>(P) * nchunk;
     const int64_t sp = gemm ? 1 : nchunk;
     const int64_t sc = gemm ? static_cast<int64_t>(nbatch) * P : 1;
@@ -559,8 +589,9 @@ int evc_predict_rdm(evc_ctx* ctx, int layout, int N, int n, const double* one_rd
     EVC_CHECK_LAUNCH();
   }
   {
-    dim3 grid((n2 + 127) / 128, nbatch);
-    gamma1_kernel<<<grid, 128, 0, ctx->stream>>>(N, n2, one_rdm, C, c_stride, gamma);
+    dim3 grid((n2 + 31) / 32, nbatch);
+    gamma1_kernel<<<grid, kG1Warps * 32, static_cast<size_t>(N) * sizeof(double), ctx->stream>>>(N, n2, one_rdm, C,
+                                                                                              c_stride, gamma);
     EVC_CHECK_LAUNCH();
   }
   if (gemm) {
