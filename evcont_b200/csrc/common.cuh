@@ -64,12 +64,13 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
                     const double* out7, const double* ipovlp, const double* hcore_deriv,
                     const double* eri_ip1, const double* grad_nuc, double* Wg, double* OmS, double* Pao,
                     double* grad);
-// K8 on full (n^4) arrays with the nuclear gradient added (grad.cu)
+// K8 on full (n^4) arrays with the nuclear gradient added (grad.cu); sym8 != 0: Gamma carries the 8-fold
+// permutational symmetry of the integrals (packed step), which turns the symmetrising gathers into streams
 int evc_grad_elec_full(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices,
                        const double* evals, const double* evecs, const double* x, const double* hcore,
                        const double* t3, const double* gamma, const double* Gamma, const double* ipovlp,
                        const double* hcore_deriv, const double* eri_ip1, const double* grad_nuc,
-                       double* grad, void* workspace, size_t workspace_bytes);
+                       double* grad, void* workspace, size_t workspace_bytes, int sym8);
 int evc_packed_hvec_from_full(evc_ctx* ctx, int nbatch, int n, const double* h1, const double* h2, double* hvec);
 int evc_packed_unpack_rdms(evc_ctx* ctx, int nbatch, int n, const double* out7, double* gamma, double* Gamma8);
 int evc_packed_pair_weights(evc_ctx* ctx, int nbatch, int N, const double* C, int64_t c_stride, double* w);

@@ -65,6 +65,95 @@ y_contract_kernel(int n, const double* __restrict__ T3, const double* __restrict
   if (threadIdx.x == 0) Y[(static_cast<int64_t>(g) * n + a) * n + i] = tot;
 }
 
+// ---- forms for an 8-fold symmetric Gamma (the packed prediction step, n > 13) ----------------------
+// Gamma_s = 4 Gamma and GammaAO_s = 4 GammaAO when Gamma has the permutational symmetry of the
+// integrals, so the four-fold gathers above collapse to one stream each.
+
+// Gsp[i,l,k,j] = 4 Gamma[i,j,k,l]: per (i, k) a transpose of the (j, l) plane through shared memory
+__global__ void __launch_bounds__(256)
+gamma_perm4_kernel(int n, const double* __restrict__ Gamma, double* __restrict__ Gsp) {
+  extern __shared__ double tile[];  // [n][n + 1]
+  const int g = blockIdx.y, i = blockIdx.x / n, k = blockIdx.x - i * n;
+  const int64_t n2 = static_cast<int64_t>(n) * n, n4 = n2 * n2;
+  const double* G = Gamma + static_cast<int64_t>(g) * n4 + static_cast<int64_t>(i) * n2 * n + static_cast<int64_t>(k) * n;
+  double* O = Gsp + static_cast<int64_t>(g) * n4 + static_cast<int64_t>(i) * n2 * n + static_cast<int64_t>(k) * n;
+  for (int t = threadIdx.x; t < n * n; t += 256) {
+    const int j = t / n, l = t - j * n;
+    tile[j * (n + 1) + l] = G[j * n2 + l];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n * n; t += 256) {
+    const int l = t / n, j = t - l * n;
+    O[l * n2 + j] = 4.0 * tile[j * (n + 1) + l];
+  }
+}
+
+// Y[g][a][i] = sum_m T3[g][a][m] Gsp[g][i][m], m < n^3, as a (n x n^3)(n^3 x n) product on the FP64
+// tensor cores: CTA = (chunk of m, geometry); every warp owns the m = 4-element steps
+// warp, warp + 8, ... of the chunk for all (n/8)^2 output tiles, operands straight from global memory
+// (each element is read once); the eight warps are combined in a fixed order.  n <= 32.
+__global__ void __launch_bounds__(256)
+y_contract_mma_kernel(int n, int nchunk, const double* __restrict__ T3, const double* __restrict__ Gsp,
+                      double* __restrict__ part) {
+  extern __shared__ double red_dyn[];  // [8][32 * 33]
+  double (*red)[32 * 33] = reinterpret_cast<double (*)[32 * 33]>(red_dyn);
+  const int g = blockIdx.y, ch = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tg = lane & 3;
+  const int64_t n3 = static_cast<int64_t>(n) * n * n;
+  const int64_t steps = (n3 + 3) / 4;
+  const int64_t s0 = steps * ch / nchunk, s1 = steps * (ch + 1) / nchunk;
+  const double* A = T3 + static_cast<int64_t>(g) * n * n3;
+  const double* B = Gsp + static_cast<int64_t>(g) * n * n3;
+  const int nt8 = (n + 7) >> 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  for (int64_t s = s0 + warp; s < s1; s += 8) {
+    const int64_t m = 4 * s + tg;
+    const bool mok = m < n3;
+    double af[4], bf[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int r = t * 8 + gq;
+      const bool ok = mok && r < n && t < nt8;
+      af[t] = ok ? __ldg(A + static_cast<int64_t>(r) * n3 + m) : 0.0;
+      bf[t] = ok ? __ldg(B + static_cast<int64_t>(r) * n3 + m) : 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (a < nt8 && b < nt8) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      red[warp][(a * 8 + gq) * 33 + b * 8 + tg * 2] = acc[a][b][0];
+      red[warp][(a * 8 + gq) * 33 + b * 8 + tg * 2 + 1] = acc[a][b][1];
+    }
+  __syncthreads();
+  double* dst = part + (static_cast<int64_t>(g) * nchunk + ch) * n * n;
+  for (int t = threadIdx.x; t < n * n; t += 256) {
+    const int a = t / n, i = t - a * n;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][a * 33 + i];
+    dst[t] = v;
+  }
+}
+
+__global__ void y_reduce_kernel(int n2, int nchunk, const double* __restrict__ part, double* __restrict__ Y) {
+  const int g = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n2) return;
+  const double* p = part + static_cast<int64_t>(g) * nchunk * n2 + t;
+  double v = 0.0;
+  for (int c = 0; c < nchunk; ++c) v += p[static_cast<int64_t>(c) * n2];
+  Y[static_cast<int64_t>(g) * n2 + t] = v;
+}
+
 // per geometry: OmS = Omega + Omega^T, Pao = X gamma X^T
 __global__ void one_el_adjoint_kernel(int n, const double* __restrict__ evals,
                                       const double* __restrict__ evecs, const double* __restrict__ x,
@@ -150,7 +239,7 @@ __global__ void one_el_adjoint_kernel(int n, const double* __restrict__ evals,
 
 // T2[g][x][m] = sum_{bcd} ip1[g][x][m][bcd] * GAO_s[m][bcd]
 __global__ void __launch_bounds__(256)
-ip1_dot_kernel(int n, const double* __restrict__ ip1, const double* __restrict__ GAO,
+ip1_dot_kernel(int n, int sym8, const double* __restrict__ ip1, const double* __restrict__ GAO,
                double* __restrict__ T2) {
   __shared__ double scratch[8];
   const int g = blockIdx.y, m = blockIdx.x;
@@ -159,6 +248,16 @@ ip1_dot_kernel(int n, const double* __restrict__ ip1, const double* __restrict__
   const double* ip = ip1 + static_cast<int64_t>(g) * 3 * n4 + static_cast<int64_t>(m) * n3;
   auto at = [&](int a, int b, int c, int d) { return G[((static_cast<int64_t>(a) * n + b) * n + c) * n + d]; };
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  if (sym8) {  // GammaAO_s = 4 GammaAO: a pure stream, 8 loads in flight per thread
+    const double* Gm = G + static_cast<int64_t>(m) * n3;
+#pragma unroll 2
+    for (int64_t k = threadIdx.x; k < n3; k += 256) {
+      const double gs = 4.0 * __ldg(Gm + k);
+      a0 = fma(__ldg(ip + k), gs, a0);
+      a1 = fma(__ldg(ip + n4 + k), gs, a1);
+      a2 = fma(__ldg(ip + 2 * n4 + k), gs, a2);
+    }
+  } else
   for (int64_t k = threadIdx.x; k < n3; k += 256) {
     const int d = static_cast<int>(k % n);
     const int c = static_cast<int>((k / n) % n);
@@ -215,11 +314,22 @@ __global__ void add_enuc_kernel(int G, const double* __restrict__ e0, const doub
   if (g < G) E[g] = e0[g] + (e_nuc ? e_nuc[g] : 0.0);
 }
 
+// chunks of the n^3 contraction index per geometry in y_contract_mma_kernel: about two CTAs per SM
+// in all, at least 512 elements per chunk (independent of the device: it sizes the workspace)
+inline int y_nchunk(int n, int nbatch) {
+  const long long n3 = static_cast<long long>(n) * n * n;
+  long long c = (2 * 148 + nbatch - 1) / nbatch;
+  const long long cap = n3 / 512 > 0 ? n3 / 512 : 1;
+  if (c > cap) c = cap;
+  if (c < 1) c = 1;
+  return static_cast<int>(c);
+}
+
 int grad_elec_impl(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices,
                    const double* evals, const double* evecs, const double* x, const double* hcore,
                    const double* t3, const double* gamma, const double* Gamma, const double* ipovlp,
                    const double* hcore_deriv, const double* eri_ip1, const double* grad_nuc,
-                   double* grad, void* workspace, size_t workspace_bytes) {
+                   double* grad, void* workspace, size_t workspace_bytes, int sym8) {
   const size_t n2 = static_cast<size_t>(n) * n, n4 = n2 * n2;
   evc_arena ar(workspace, workspace_bytes);
   double* bufA = ar.take<double>(nbatch * n4);  // Gsp, then rot scratch
@@ -232,14 +342,29 @@ int grad_elec_impl(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aos
   EVC_REQUIRE(bufA && bufB && GAO && Y && OmS && Pao && T2, "evc_grad_elec: workspace too small (%zu bytes)",
               workspace_bytes);
   cudaStream_t st = ctx->stream;
-  {
+  if (sym8 && n <= 32) {
+    // Gamma is 8-fold symmetric (packed step): one transposing stream, Y on the tensor cores
+    const int nchunk = y_nchunk(n, nbatch);
+    double* ypart = ar.take<double>(static_cast<size_t>(nbatch) * nchunk * n2);
+    EVC_REQUIRE(ypart, "evc_grad_elec: workspace too small (%zu bytes)", workspace_bytes);
+    dim3 grid(n * n, nbatch);
+    gamma_perm4_kernel<<<grid, 256, static_cast<size_t>(n) * (n + 1) * sizeof(double), st>>>(n, Gamma, bufA);
+    EVC_CHECK_LAUNCH();
+    dim3 g2(nchunk, nbatch);
+    constexpr size_t kYSmem = 8 * 32 * 33 * sizeof(double);
+    EVC_CHECK_CUDA(cudaFuncSetAttribute(y_contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kYSmem)));
+    y_contract_mma_kernel<<<g2, 256, kYSmem, st>>>(n, nchunk, t3, bufA, ypart);
+    EVC_CHECK_LAUNCH();
+    dim3 g3(static_cast<unsigned>((n2 + 127) / 128), nbatch);
+    y_reduce_kernel<<<g3, 128, 0, st>>>(static_cast<int>(n2), nchunk, ypart, Y);
+    EVC_CHECK_LAUNCH();
+  } else {
     dim3 grid(static_cast<unsigned>((n4 + 255) / 256), nbatch);
     gamma_sym_perm_kernel<<<grid, 256, 0, st>>>(n, Gamma, bufA);
     EVC_CHECK_LAUNCH();
-  }
-  {
-    dim3 grid(n * n, nbatch);
-    y_contract_kernel<<<grid, 128, 0, st>>>(n, t3, bufA, Y);
+    dim3 g2(n * n, nbatch);
+    y_contract_kernel<<<g2, 128, 0, st>>>(n, t3, bufA, Y);
     EVC_CHECK_LAUNCH();
   }
   {
@@ -257,7 +382,7 @@ int grad_elec_impl(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aos
   if ((rc = evc_launch_rot_pass(st, nbatch, n, bufA, x, 1, GAO))) return rc;
   {
     dim3 grid(n, nbatch);
-    ip1_dot_kernel<<<grid, 256, 0, st>>>(n, eri_ip1, GAO, T2);
+    ip1_dot_kernel<<<grid, 256, 0, st>>>(n, sym8 ? 1 : 0, eri_ip1, GAO, T2);
     EVC_CHECK_LAUNCH();
   }
   {
@@ -272,7 +397,8 @@ size_t grad_ws_bytes(int n, int natm, int nbatch) {
   const size_t n2 = static_cast<size_t>(n) * n, n4 = n2 * n2;
   (void)natm;
   return 3 * evc_align_up(nbatch * n4 * 8, 256) + 3 * evc_align_up(nbatch * n2 * 8, 256) +
-         evc_align_up(static_cast<size_t>(nbatch) * 3 * n * 8, 256);
+         evc_align_up(static_cast<size_t>(nbatch) * 3 * n * 8, 256) +
+         evc_align_up(static_cast<size_t>(nbatch) * y_nchunk(n, nbatch) * n2 * 8, 256);
 }
 
 }  // namespace
@@ -281,9 +407,9 @@ int evc_grad_elec_full(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t*
                        const double* evals, const double* evecs, const double* x, const double* hcore,
                        const double* t3, const double* gamma, const double* Gamma, const double* ipovlp,
                        const double* hcore_deriv, const double* eri_ip1, const double* grad_nuc,
-                       double* grad, void* workspace, size_t workspace_bytes) {
+                       double* grad, void* workspace, size_t workspace_bytes, int sym8) {
   return grad_elec_impl(ctx, nbatch, n, natm, aoslices, evals, evecs, x, hcore, t3, gamma, Gamma, ipovlp,
-                        hcore_deriv, eri_ip1, grad_nuc, grad, workspace, workspace_bytes);
+                        hcore_deriv, eri_ip1, grad_nuc, grad, workspace, workspace_bytes, sym8);
 }
 
 extern "C" {
@@ -305,7 +431,7 @@ int evc_grad_elec(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aosl
   EVC_REQUIRE(n >= 1 && n <= 32 && natm >= 1, "evc_grad_elec: n=%d natm=%d unsupported", n, natm);
   if (nbatch <= 0) return 0;
   return grad_elec_impl(ctx, nbatch, n, natm, aoslices, evals, evecs, x, hcore, t3, gamma, Gamma, ipovlp,
-                        hcore_deriv, eri_ip1, nullptr, grad_elec, workspace, workspace_bytes);
+                        hcore_deriv, eri_ip1, nullptr, grad_elec, workspace, workspace_bytes, 0);
 }
 
 int evc_energy_with_grad_workspace_bytes(int layout, int N, int n, int natm, int nbatch, size_t* bytes) {
@@ -377,7 +503,7 @@ int evc_energy_with_grad(evc_ctx* ctx, int layout, int N, int n, int natm, const
   if ((rc = evc_predict_rdm(ctx, layout, N, n, one_rdm, two_rdm, nbatch, C, N, gamma, Gamma, pred_ws, pred_b))) return rc;
   if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD))) return rc;
   if ((rc = grad_elec_impl(ctx, nbatch, n, natm, ao->aoslices, evals, evecs, X, ao->hcore, t3, gamma, Gamma,
-                           ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b)))
+                           ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b, 0)))
     return rc;
   if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM))) return rc;
   add_enuc_kernel<<<(nbatch + 127) / 128, 128, 0, ctx->stream>>>(nbatch, E0, ao->e_nuc, E);

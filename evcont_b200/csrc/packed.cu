@@ -163,23 +163,25 @@ __global__ void hvec_from_full_kernel(int n, int64_t L8, const double* __restric
 }
 
 // gamma = out7[0:n^2]; Gamma8[ijkl] = s_I s_K s_IK out7[tri(I,K)] / 4: the totally
-// symmetric part of the predicted two-body RDM (all the gradient sees)
-__global__ void unpack_rdms_kernel(int n, int64_t L8, const double* __restrict__ out7,
-                                   double* __restrict__ gamma, double* __restrict__ Gamma8) {
-  const int g = blockIdx.y;
-  const int64_t k4 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+// symmetric part of the predicted two-body RDM (all the gradient sees).  One CTA per (i, j) and
+// geometry, threads over (k, l): the pair index of (i, j) is uniform and the writes are contiguous.
+__global__ void __launch_bounds__(256)
+unpack_rdms_kernel(int n, int64_t L8, const double* __restrict__ out7, double* __restrict__ gamma,
+                   double* __restrict__ Gamma8) {
+  const int g = blockIdx.y, ij = blockIdx.x;
+  const int i = ij / n, j = ij - i * n;
   const int n2 = n * n;
-  const int64_t n4 = static_cast<int64_t>(n2) * n2;
-  if (k4 >= n4) return;
   const double* o = out7 + static_cast<int64_t>(g) * L8;
-  if (k4 < n2) gamma[static_cast<int64_t>(g) * n2 + k4] = o[k4];
-  const int l = static_cast<int>(k4 % n), k = static_cast<int>((k4 / n) % n);
-  const int j = static_cast<int>((k4 / n2) % n), i = static_cast<int>(k4 / (static_cast<int64_t>(n2) * n));
   const int I = i >= j ? tri_idx(i, j) : tri_idx(j, i);
-  const int K = k >= l ? tri_idx(k, l) : tri_idx(l, k);
-  const int hi = I > K ? I : K, lo = I > K ? K : I;
-  const double s = (i == j ? 2.0 : 1.0) * (k == l ? 2.0 : 1.0);  // (the I == K factor is in RG)
-  Gamma8[static_cast<int64_t>(g) * n4 + k4] = 0.25 * s * o[n2 + tri_idx(hi, lo)];
+  const double si = (i == j) ? 0.5 : 0.25;  // s_I / 4 (the I == K factor is in RG)
+  double* dst = Gamma8 + (static_cast<int64_t>(g) * n2 + ij) * n2;
+  for (int t = threadIdx.x; t < n2; t += 256) {
+    const int k = t / n, l = t - k * n;
+    const int K = k >= l ? tri_idx(k, l) : tri_idx(l, k);
+    const int hi = I > K ? I : K, lo = I > K ? K : I;
+    dst[t] = (k == l ? 2.0 : 1.0) * si * __ldg(o + n2 + tri_idx(hi, lo));
+  }
+  if (threadIdx.x == 0) gamma[static_cast<int64_t>(g) * n2 + ij] = o[ij];
 }
 
 // w[g][p] = c_a^2 (a == b), 2 c_a c_b (a > b)      (ab_initio_gradients_loewdin.py:345-353)
@@ -972,8 +974,7 @@ int evc_packed_hvec_from_full(evc_ctx* ctx, int nbatch, int n, const double* h1,
 
 int evc_packed_unpack_rdms(evc_ctx* ctx, int nbatch, int n, const double* out7, double* gamma, double* Gamma8) {
   const int64_t L8 = packed_len(n);
-  const int64_t n4 = static_cast<int64_t>(n) * n * n * n;
-  dim3 grid(static_cast<unsigned>((n4 + 255) / 256), nbatch);
+  dim3 grid(n * n, nbatch);
   unpack_rdms_kernel<<<grid, 256, 0, ctx->stream>>>(n, L8, out7, gamma, Gamma8);
   EVC_CHECK_LAUNCH();
   return 0;
@@ -1134,7 +1135,7 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
   } else {
     if ((rc = evc_packed_unpack_rdms(ctx, nbatch, n, out7, gamma, Gamma8))) return rc;
     if ((rc = evc_grad_elec_full(ctx, nbatch, n, natm, ao->aoslices, evals, evecs, X, ao->hcore, t3, gamma, Gamma8,
-                                 ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b)))
+                                 ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b, 1)))
       return rc;
   }
   if (!small && (rc = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM))) return rc;
