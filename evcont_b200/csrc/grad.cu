@@ -110,22 +110,29 @@ y_contract_mma_kernel(int n, int nchunk, const double* __restrict__ T3, const do
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  for (int64_t s = s0 + warp; s < s1; s += 8) {
-    const int64_t m = 4 * s + tg;
-    const bool mok = m < n3;
-    double af[4], bf[4];
+  // two steps per iteration: 16 independent 8-byte loads in flight per lane before the 32 DMMAs
+  for (int64_t s = s0 + warp; s < s1; s += 16) {
+    double af[2][4], bf[2][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int r = t * 8 + gq;
-      const bool ok = mok && r < n && t < nt8;
-      af[t] = ok ? __ldg(A + static_cast<int64_t>(r) * n3 + m) : 0.0;
-      bf[t] = ok ? __ldg(B + static_cast<int64_t>(r) * n3 + m) : 0.0;
+    for (int u = 0; u < 2; ++u) {
+      const int64_t su = s + 8 * u;
+      const int64_t m = 4 * su + tg;
+      const bool mok = su < s1 && m < n3;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int r = t * 8 + gq;
+        const bool ok = mok && r < n && t < nt8;
+        af[u][t] = ok ? __ldg(A + static_cast<int64_t>(r) * n3 + m) : 0.0;
+        bf[u][t] = ok ? __ldg(B + static_cast<int64_t>(r) * n3 + m) : 0.0;
+      }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (a < nt8 && b < nt8) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (a < nt8 && b < nt8) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[u][a], bf[u][b]);
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)

@@ -370,7 +370,7 @@ constexpr int kRaBM = 64, kRaBN = 128;   // rows_axpy GEMM tile (G x L)
 
 evc_gemm::Plan rows_dot_plan(int G, int P, int64_t L) {
   const int tiles = ((G + kRdBM - 1) / kRdBM) * ((P + kRdBN - 1) / kRdBN);
-  return evc_gemm::plan_split(tiles, static_cast<int>(L), kPlanSms, 32);
+  return evc_gemm::plan_split(tiles, static_cast<int>(L), kPlanSms, 128);
 }
 
 }  // namespace
