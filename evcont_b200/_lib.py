@@ -108,6 +108,12 @@ SIGNATURES = {
     "evc_ao_integrals_s_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, c_sz_p]),
     "evc_ao_integrals_s": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9 +
                            [C.c_void_p, C.c_size_t]),
+    "evc_gbasis_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "evc_gbasis_destroy": (C.c_int, [C.c_void_p]),
+    "evc_ao_integrals_sp_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, c_sz_p]),
+    "evc_ao_integrals_sp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9 +
+                            [C.c_void_p, C.c_size_t]),
     "evc_fci_hdiag": (C.c_int, [C.c_void_p, C.c_int, c_i64, c_i64, C.c_void_p, C.c_void_p, c_double_p,
                                 c_double_p, c_double_p]),
     "evc_fci_contract_workspace_bytes": (C.c_int, [C.c_int, c_i64, c_i64, c_sz_p]),

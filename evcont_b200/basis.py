@@ -1,9 +1,9 @@
 """Gaussian basis-set data for the device integral engine (K9, ``csrc/integrals.cu``).
 
-Only s shells in this version: H and He in STO-3G / STO-6G / 6-31G, which covers the
-hydrogen-chain configurations of the reference (examples/H6_continuation.py,
-H10_continuation_3D_replacements.py, md_H30_evcont_from_DMRG.py build their ``Mole``
-with ``basis="sto-6g"``).  Exponents and contraction coefficients are the EMSL / Basis
+s shells (H and He in STO-3G / STO-6G / 6-31G: the hydrogen-chain configurations of the reference,
+built there with ``basis="sto-6g"``) go through the specialised s kernel; molecules with p shells
+(oxygen in 6-31G: scripts/MD/md_H2O_6_31G_FCI.py, the Zundel scripts) through the general s+p kernel
+(``csrc/integrals_sp.cu``).  Exponents and contraction coefficients are the EMSL / Basis
 Set Exchange values (coefficients refer to normalised primitives); like ``pyscf.gto``
 the contracted function is renormalised to unit self-overlap.
 """
@@ -11,7 +11,15 @@ import math
 
 import numpy as np
 
-CHARGES = {"H": 1, "He": 2}
+CHARGES = {"H": 1, "He": 2, "O": 8}
+
+#: (element, basis) -> p shells (exponents, coefficients); "sp" shells of Pople bases are split
+P_SHELLS = {
+    ("O", "6-31g"): [
+        ((15.539616, 3.5999336, 1.0137618), (0.0708743, 0.3397528, 0.7271586)),
+        ((0.2700058,), (1.0,)),
+    ],
+}
 
 #: (element, basis) -> list of s shells, each (exponents, contraction coefficients)
 S_SHELLS = {
@@ -36,6 +44,12 @@ S_SHELLS = {
     ("He", "6-31g"): [
         ((38.4216340, 5.7780300, 1.2417740), (0.0237660, 0.1546790, 0.4696300)),
         ((0.2979640,), (1.0,)),
+    ],
+    ("O", "6-31g"): [
+        ((5484.6717, 825.23495, 188.04696, 52.9645, 16.89757, 5.7996353),
+         (0.0018311, 0.0139501, 0.0684451, 0.2327143, 0.470193, 0.3585209)),
+        ((15.539616, 3.5999336, 1.0137618), (-0.1107775, -0.1480263, 1.130767)),
+        ((0.2700058,), (1.0,)),
     ],
 }
 
@@ -73,3 +87,45 @@ def s_basis_tables(symbols, basis):
                 ao_nprim=np.asarray(ao_nprim, dtype=np.int32),
                 prim_exp=np.asarray(prim_exp, dtype=np.float64),
                 prim_wt=np.asarray(prim_wt, dtype=np.float64))
+
+
+def normalised_p_shell(exps, coefs):
+    """Weights of one Cartesian component of a contracted p function:
+    ``c_k (2 a_k / pi)^(3/4) 2 sqrt(a_k) / sqrt(<phi|phi>)``."""
+    e = np.asarray(exps, dtype=np.float64)
+    c = np.asarray(coefs, dtype=np.float64) * (2.0 * e / np.pi) ** 0.75 * 2.0 * np.sqrt(e)
+    pp = e[:, None] + e[None, :]
+    ss = (c[:, None] * c[None, :] * (np.pi / pp) ** 1.5 / (2.0 * pp)).sum()
+    return e, c / math.sqrt(ss)
+
+
+def has_p_shells(symbols, basis):
+    key = basis.lower().replace("_", "-")
+    return any((s.capitalize(), key) in P_SHELLS for s in symbols)
+
+
+def sp_basis_tables(symbols, basis):
+    """Host tables for ``evc_gbasis_create``: contracted Cartesian AOs in pyscf.gto order (per atom the
+    s shells, then the p shells with components x, y, z).  Returns ``dict(charges, ao_atom, ao_pow
+    [nao, 3], ao_nprim, prim_exp, prim_wt)``."""
+    key = basis.lower().replace("_", "-")
+    charges, ao_atom, ao_pow, ao_nprim, prim_exp, prim_wt = [], [], [], [], [], []
+    for ia, sym in enumerate(symbols):
+        sym = sym.capitalize()
+        if (sym, key) not in S_SHELLS:
+            raise NotImplementedError(f"no basis data for element {sym!r} in basis {basis!r}")
+        charges.append(CHARGES[sym])
+        for exps, coefs in S_SHELLS[(sym, key)]:
+            e, w = normalised_s_shell(exps, coefs)
+            ao_atom.append(ia); ao_pow.append((0, 0, 0)); ao_nprim.append(len(e))
+            prim_exp.extend(e); prim_wt.extend(w)
+        for exps, coefs in P_SHELLS.get((sym, key), []):
+            e, w = normalised_p_shell(exps, coefs)
+            for comp in range(3):
+                pw = [0, 0, 0]
+                pw[comp] = 1
+                ao_atom.append(ia); ao_pow.append(tuple(pw)); ao_nprim.append(len(e))
+                prim_exp.extend(e); prim_wt.extend(w)
+    return dict(charges=np.asarray(charges, dtype=np.float64), ao_atom=np.asarray(ao_atom, dtype=np.int32),
+                ao_pow=np.ascontiguousarray(ao_pow, dtype=np.int32), ao_nprim=np.asarray(ao_nprim, dtype=np.int32),
+                prim_exp=np.asarray(prim_exp, dtype=np.float64), prim_wt=np.asarray(prim_wt, dtype=np.float64))

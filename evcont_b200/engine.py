@@ -273,13 +273,14 @@ class Engine:
         if ao.nbatch != G or ao.nao != sbasis.nao or ao.natm != sbasis.natm:
             raise ValueError("DeviceAO does not match the basis / batch size")
         nbytes = C.c_size_t()
-        check(self.lib.evc_ao_integrals_s_workspace_bytes(sbasis.handle, G, C.byref(nbytes)))
+        ws_fn, fn = ((self.lib.evc_ao_integrals_sp_workspace_bytes, self.lib.evc_ao_integrals_sp) if sbasis.general
+                     else (self.lib.evc_ao_integrals_s_workspace_bytes, self.lib.evc_ao_integrals_s))
+        check(ws_fn(sbasis.handle, G, C.byref(nbytes)))
         ws = self.workspace(nbytes.value)
         self._bind_stream()
-        check(self.lib.evc_ao_integrals_s(self._ctx, sbasis.handle, G, _ptr(coords), _ptr(ao.ovlp),
-                                          _ptr(ao.hcore), _ptr(ao.eri), _ptr(ao.ipovlp),
-                                          _ptr(ao.hcore_deriv), _ptr(ao.eri_ip1), _ptr(ao.e_nuc),
-                                          _ptr(ao.grad_nuc), _ptr(ws), ws.numel()))
+        check(fn(self._ctx, sbasis.handle, G, _ptr(coords), _ptr(ao.ovlp), _ptr(ao.hcore), _ptr(ao.eri),
+                 _ptr(ao.ipovlp), _ptr(ao.hcore_deriv), _ptr(ao.eri_ip1), _ptr(ao.e_nuc), _ptr(ao.grad_nuc),
+                 _ptr(ws), ws.numel()))
         return ao
 
     def energy_with_grad_coords(self, stack, sbasis, coords, ao=None, out=None, want_rdms=False):
@@ -443,22 +444,30 @@ class FCIHamiltonian:
 
 
 class SBasis:
-    """Device tables of an s-shell Gaussian basis (``evc_sbasis``) for a fixed list of atoms."""
+    """Device tables of a Gaussian basis for a fixed list of atoms: ``evc_sbasis`` (s shells only, the
+    specialised kernel K9) or ``evc_gbasis`` (s and p shells, the general kernel K9g)."""
 
     def __init__(self, engine, symbols, basis):
-        from .basis import s_basis_tables
+        from .basis import has_p_shells, s_basis_tables, sp_basis_tables
         self.engine = engine
         self.symbols = tuple(s.capitalize() for s in symbols)
         self.basis = basis.lower()
-        t = s_basis_tables(self.symbols, self.basis)
+        self.general = has_p_shells(self.symbols, self.basis)
+        t = sp_basis_tables(self.symbols, self.basis) if self.general else s_basis_tables(self.symbols, self.basis)
         self.tables = t
         self.natm, self.nao = len(self.symbols), len(t["ao_atom"])
         handle = C.c_void_p()
         with torch.cuda.device(engine.device):
-            check(engine.lib.evc_sbasis_create(
-                engine._ctx, self.natm, t["charges"].ctypes.data, self.nao, t["ao_atom"].ctypes.data,
-                t["ao_nprim"].ctypes.data, t["prim_exp"].ctypes.data, t["prim_wt"].ctypes.data,
-                C.byref(handle)))
+            if self.general:
+                check(engine.lib.evc_gbasis_create(
+                    engine._ctx, self.natm, t["charges"].ctypes.data, self.nao, t["ao_atom"].ctypes.data,
+                    t["ao_pow"].ctypes.data, t["ao_nprim"].ctypes.data, t["prim_exp"].ctypes.data,
+                    t["prim_wt"].ctypes.data, C.byref(handle)))
+            else:
+                check(engine.lib.evc_sbasis_create(
+                    engine._ctx, self.natm, t["charges"].ctypes.data, self.nao, t["ao_atom"].ctypes.data,
+                    t["ao_nprim"].ctypes.data, t["prim_exp"].ctypes.data, t["prim_wt"].ctypes.data,
+                    C.byref(handle)))
         self.handle = handle
         sl = np.zeros((self.natm, 2), dtype=np.int32)
         for A in range(self.natm):
@@ -470,7 +479,10 @@ class SBasis:
     def __del__(self):
         try:
             if self.handle:
-                self.engine.lib.evc_sbasis_destroy(self.handle)
+                if self.general:
+                    self.engine.lib.evc_gbasis_destroy(self.handle)
+                else:
+                    self.engine.lib.evc_sbasis_destroy(self.handle)
                 self.handle = None
         except Exception:  # interpreter shutdown
             pass

@@ -18,7 +18,7 @@ import torch
 from .stackcache import as_device_stack
 
 AMU2AU = 1822.888486209  # pyscf.data.nist.AMU2AU
-COMMON_ISOTOPE_MASSES = {"H": 1.00782503223, "He": 4.00260325413}
+COMMON_ISOTOPE_MASSES = {"H": 1.00782503223, "He": 4.00260325413, "O": 15.99491461957}
 
 
 def atomic_masses(mol):

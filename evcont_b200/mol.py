@@ -96,7 +96,7 @@ class MolLite:
     Covers what the reference touches on the prediction path ("mol duck
     type"): ``nao, natm, nelec, atom_coords(), set_geom_(), copy(), energy_nuc(),
     intor(name, comp=), aoslice_by_atom()`` and, as methods, the PySCF free functions
-    ``get_hcore / hcore_generator / grad_nuc``.  s shells only (``evcont_b200.basis``).
+    ``get_hcore / hcore_generator / grad_nuc``.  s and p shells (``evcont_b200.basis``: H, He, O).
     The reference scripts build their molecules as
     ``gto.Mole().build(atom=[("H", (x, 0, 0)), ...], basis="sto-6g", unit="Bohr")``
     (examples/H10_continuation_3D_replacements.py:84-102); ``MolLite(atom, basis, unit)``
@@ -109,8 +109,9 @@ class MolLite:
         scale = 1.0 if unit.lower().startswith(("b", "au")) else 1.0 / BOHR
         self._coords = np.array([a[1] for a in atoms], dtype=np.float64).reshape(-1, 3) * scale
         self.basis, self.charge, self.spin, self.unit = basis, charge, spin, unit
-        from .basis import CHARGES, s_basis_tables
-        self._tables = s_basis_tables(self._symbols, basis)
+        from .basis import CHARGES, has_p_shells, s_basis_tables, sp_basis_tables
+        self._tables = (sp_basis_tables if has_p_shells(self._symbols, basis) else s_basis_tables)(
+            self._symbols, basis)
         self.natm = len(atoms)
         self.nao = int(len(self._tables["ao_atom"]))
         nel = int(sum(CHARGES[s] for s in self._symbols)) - int(charge)

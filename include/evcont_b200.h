@@ -334,6 +334,27 @@ int evc_md_velocities(evc_ctx *ctx, int nbatch, int natm, double dt, int first,
                       double *a, double *ekin, int *frame_idx, int max_frames, double *traj,
                       double *epot_log, double *ekin_log);
 
+/* ---- K9g: AO integrals over contracted Cartesian s AND p Gaussians ---------------------
+ * The same arrays as evc_ao_integrals_s for molecules with p shells (6-31G oxygen: the H2O
+ * and Zundel configurations of the reference, scripts/MD/md_H2O_6_31G_FCI.py,
+ * scripts/MD/Zundel_thermodynamics), McMurchie-Davidson scheme.  AOs are contracted
+ * Cartesian functions in pyscf.gto order (per atom: s shells, then p shells, components
+ * x, y, z); ao_pow_host [nao][3] holds the Cartesian powers (all zero: s; one 1: p); the
+ * three components of a p shell repeat its primitives.  prim_wt = contraction coefficient x
+ * primitive norm ((2a/pi)^(3/4), times 2 sqrt(a) for p) x contracted normalisation.
+ * natm <= 16, nao <= 64.  Workspace: evc_ao_integrals_sp_workspace_bytes. */
+typedef struct evc_gbasis evc_gbasis;
+int evc_gbasis_create(evc_ctx *ctx, int natm, const double *charges_host, int nao,
+                      const int32_t *ao_atom_host, const int32_t *ao_pow_host,
+                      const int32_t *ao_nprim_host, const double *prim_exp_host,
+                      const double *prim_wt_host, evc_gbasis **out);
+int evc_gbasis_destroy(evc_gbasis *basis);
+int evc_ao_integrals_sp_workspace_bytes(const evc_gbasis *basis, int nbatch, size_t *bytes);
+int evc_ao_integrals_sp(evc_ctx *ctx, const evc_gbasis *basis, int nbatch, const double *coords,
+                        double *ovlp, double *hcore, double *eri, double *ipovlp,
+                        double *hcore_deriv, double *eri_ip1, double *e_nuc, double *grad_nuc,
+                        void *workspace, size_t workspace_bytes);
+
 /* ---- FCI Hamiltonian action (training side) ------------------------------------------
  * What cisolver.kernel (evcont/FCI_EVCont.py:70; PySCF direct_spin0 Davidson:
  * contract_2e + make_hdiag) needs from the Hamiltonian, on the device with the K0 link

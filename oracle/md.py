@@ -10,7 +10,7 @@ conservation and time reversibility (tests/test_gpu_md.py).
 import numpy as np
 
 AMU2AU = 1822.888486209
-COMMON_ISOTOPE_MASSES = {"H": 1.00782503223, "He": 4.00260325413}
+COMMON_ISOTOPE_MASSES = {"H": 1.00782503223, "He": 4.00260325413, "O": 15.99491461957}
 
 
 KB_HARTREE = 3.166811563e-6

@@ -124,4 +124,4 @@ def test_angstrom_units_and_unknown_element():
     m = MolLite("H 0 0 0; H 0 0 0.74", basis="sto-3g", unit="Angstrom")
     assert abs(m.atom_coords()[1, 2] - 0.74 / BOHR) < 1e-14
     with pytest.raises(NotImplementedError):
-        MolLite("O 0 0 0; H 0 0 1", basis="6-31g")
+        MolLite("N 0 0 0; H 0 0 1", basis="6-31g")
