@@ -10,11 +10,12 @@
 //     R^n_000 = (-2 rho)^n F_n(rho |PQ|^2),  R^n_{t+1,u,v} = t R^{n+1}_{t-1,u,v} + X_PQ R^{n+1}_{tuv}
 //   d/dA_x of a Cartesian Gaussian: 2a G_{l+1} - l G_{l-1};  (nabla a b|cd) = -d/dA (ab|cd).
 //
-// One warp per contracted quartet (ab|cd), (ab) >= (cd); lanes over the primitive quartets; per
+// One lane group (1..32 lanes, sized to the number of primitive quartets) per contracted quartet (ab|cd),
+// (ab) >= (cd); lanes over the primitive quartets; per
 // primitive quartet the value and the derivatives with respect to the centres of a, b and c (the
 // fourth follows from translational invariance) are evaluated from shifted angular momenta over one
-// shared R table; fixed butterfly reduction; lanes 0..7 write the eight index permutations.  First
-// correct version: no shared-memory pair tables, no screening beyond a weight cut-off.
+// shared R table, with the ket side contracted first (staged Hermite contraction); fixed butterfly
+// reduction; the eight index permutations are written by the lanes of the group.
 #include "common.cuh"
 
 #include <algorithm>
@@ -34,16 +35,17 @@ constexpr int kGMaxL = 6;            // highest Boys order: (pp|pp) with one der
 }  // namespace
 
 struct evc_gbasis {
-  int natm, nao, nprim;
+  int natm, nao, nprim, nunits;
   int32_t *ao_atom, *ao_pow, *ao_poff, *aoslices;  // ao_pow: [nao][3]
+  int32_t *qsorted, *units;                        // quartet work list (see evc_gbasis_create)
   double *prim_exp, *prim_wt, *charges, *boys;
 };
 
 namespace {
 
 struct GView {
-  int natm, nao;
-  const int32_t *ao_atom, *ao_pow, *ao_poff;
+  int natm, nao, nunits;
+  const int32_t *ao_atom, *ao_pow, *ao_poff, *qsorted, *units;
   const double *prim_exp, *prim_wt, *charges, *boys;
 };
 
@@ -123,14 +125,10 @@ __device__ __forceinline__ void herm_E(int i, int j, double xpa, double xpb, dou
   }
 }
 
-// compact index of (t, u, v), t + u + v <= 6: offsets by t then u
-__device__ __forceinline__ int ridx(int t, int u, int v) {
-  // number of (t', u', v') with t' < t: sum_{t'<t} (7-t')(8-t')/2 ; then u' < u: sum (7 - t - u')
-  const int a = 7 - t;
-  const int before_t = 84 - a * (a + 1) * (a + 2) / 6;       // C(9,3) = 84 total for order <= 6
-  const int before_u = u * (7 - t) - u * (u - 1) / 2;
-  return before_t + before_u + v;
-}
+// compact index of (t, u, v), t + u + v <= 6 (84 entries, ordered by t, then u, then v).  All lanes of a
+// warp walk the same (t, u, v) at the same time, so the table sits in constant memory (one broadcast).
+__constant__ unsigned char c_ridx[7][7][7];
+__device__ __forceinline__ int ridx(int t, int u, int v) { return c_ridx[t][u][v]; }
 
 // R^0_{tuv}(alpha, X) for t + u + v <= L (L <= 6) into R (84 entries), with scratch S (84)
 __device__ void build_R(int L, double alpha, double X, double Y, double Z, const double* F, double* R, double* S) {
@@ -162,8 +160,9 @@ struct PrimFn {
   int l[3];
 };
 
+// (reference form of the primitive contraction, kept for documentation of the staged version below)
 // sum_{tuv} E^{ab}_{tuv} sum_{t'u'v'} (-1)^{t'+u'+v'} E^{cd}_{t'u'v'} R_{t+t',u+u',v+v'} for the given powers
-__device__ double herm_contract(const int* la, const int* lb, const int* lc, const int* ld, const double* xpa,
+[[maybe_unused]] __device__ double herm_contract(const int* la, const int* lb, const int* lc, const int* ld, const double* xpa,
                                 const double* xpb, double hp, const double* xqc, const double* xqd, double hq,
                                 const double* R) {
   double Eb[3][8], Ek[3][8];
@@ -206,9 +205,15 @@ gint2e_kernel(GView bs, const double* __restrict__ coords, GOut out) {
   const int64_t n2 = static_cast<int64_t>(n) * n, n3 = n2 * n, n4 = n2 * n2;
   double* eri = out.eri + static_cast<int64_t>(g) * n4;
   double* ip1 = out.eri_ip1 + static_cast<int64_t>(g) * 3 * n4;
-  const int npc = n * (n + 1) / 2;
-  const int nq = npc * (npc + 1) / 2;
-  for (int q = blockIdx.x * NW + warp; q < nq; q += gridDim.x * NW) {
+  // Work units (built once per basis): contracted quartets with the same Cartesian powers and the same
+  // lane-group size gs = 2^k >= min(#primitive quartets, 32) are packed 32/gs to a warp, so quartets of
+  // the single-primitive outer shells do not leave 31 lanes idle and every lane runs the same loops.
+  for (int un = blockIdx.x * NW + warp; un < bs.nunits; un += gridDim.x * NW) {
+    const int ustart = bs.units[2 * un], uinfo = bs.units[2 * un + 1];
+    const int gs = 1 << (uinfo & 0xff), ucount = uinfo >> 8;
+    const int grp = lane / gs, lig = lane - grp * gs;
+    const bool live = grp < ucount;
+    const int q = bs.qsorted[ustart + (live ? grp : 0)];
     int I, K, ao[4];
     gtri_unrank(q, I, K);
     gtri_unrank(I, ao[0], ao[1]);
@@ -237,8 +242,8 @@ gint2e_kernel(GView bs, const double* __restrict__ coords, GOut out) {
     for (int f = 0; f < 3; ++f)
 #pragma unroll
       for (int d = 0; d < 3; ++d) dv[f][d] = 0.0;
-    const int tot = np_[0] * np_[1] * np_[2] * np_[3];
-    for (int t = lane; t < tot; t += 32) {
+    const int tot = live ? np_[0] * np_[1] * np_[2] * np_[3] : 0;
+    for (int t = lig; t < tot; t += gs) {
       int r = t;
       const int il = r % np_[3]; r /= np_[3];
       const int ik = r % np_[2]; r /= np_[2];
@@ -265,37 +270,91 @@ gint2e_kernel(GView bs, const double* __restrict__ coords, GOut out) {
       boys_upto(L, rho * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]), boys, F);
       build_R(L, rho, pq[0], pq[1], pq[2], F, R, S);
       const double hp = 0.5 / p, hq = 0.5 / qq;
-      val = fma(pref, herm_contract(l[0], l[1], l[2], l[3], xpa, xpb, hp, xqc, xqd, hq, R), val);
-      // derivatives with respect to the centres of a, b, c: 2 alpha (l + 1_x) - l_x (l - 1_x)
-      const double ex3[3] = {ea, eb, ec};
+      // 1-D Hermite tables: bra for (la + sa, lb + sb) with one of the shifts in {-1, 0, +1}, ket for
+      // (lc + sc, ld); index 0: base, 1: first function up, 2: first function down, 3: second up, 4: second down
+      double Eb[3][5][6], Ek[3][3][6];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        herm_E(l[0][d], l[1][d], xpa[d], xpb[d], hp, Eb[d][0]);
+        herm_E(l[0][d] + 1, l[1][d], xpa[d], xpb[d], hp, Eb[d][1]);
+        if (l[0][d] > 0) herm_E(l[0][d] - 1, l[1][d], xpa[d], xpb[d], hp, Eb[d][2]);
+        herm_E(l[0][d], l[1][d] + 1, xpa[d], xpb[d], hp, Eb[d][3]);
+        if (l[1][d] > 0) herm_E(l[0][d], l[1][d] - 1, xpa[d], xpb[d], hp, Eb[d][4]);
+        herm_E(l[2][d], l[3][d], xqc[d], xqd[d], hq, Ek[d][0]);
+        herm_E(l[2][d] + 1, l[3][d], xqc[d], xqd[d], hq, Ek[d][1]);
+        if (l[2][d] > 0) herm_E(l[2][d] - 1, l[3][d], xqc[d], xqd[d], hq, Ek[d][2]);
+      }
+      const int nb[3] = {l[0][0] + l[1][0], l[0][1] + l[1][1], l[0][2] + l[1][2]};   // bra Hermite ranges
+      const int nk[3] = {l[2][0] + l[3][0], l[2][1] + l[3][1], l[2][2] + l[3][2]};
+      // ket-contracted intermediate G_{tuv} = sum_{t'u'v'} (-1)^{t'+u'+v'} E^{cd}_{t'u'v'} R_{t+t',u+u',v+v'}
+      // kx/ky/kz: ket table index per dimension, dk: ket range shift per dimension; bra range (bt,bu,bv)
+      auto ket_G = [&](int kx, int ky, int kz, int dkx, int dky, int dkz, int bt, int bu, int bv, double* G) {
+        for (int t = 0; t <= bt; ++t)
+          for (int u = 0; u <= bu; ++u)
+            for (int v = 0; v <= bv; ++v) {
+              // at most one direction beyond the base bra range (one shifted function at a time)
+              if ((t > nb[0]) + (u > nb[1]) + (v > nb[2]) > 1) continue;
+              double acc = 0.0;
+              for (int t2 = 0; t2 <= nk[0] + dkx; ++t2)
+                for (int u2 = 0; u2 <= nk[1] + dky; ++u2)
+                  for (int v2 = 0; v2 <= nk[2] + dkz; ++v2) {
+                    const double ek = Ek[0][kx][t2] * Ek[1][ky][u2] * Ek[2][kz][v2];
+                    acc = fma(((t2 + u2 + v2) & 1) ? -ek : ek, R[ridx(t + t2, u + u2, v + v2)], acc);
+                  }
+              G[(t * 4 + u) * 4 + v] = acc;
+            }
+      };
+      // sum_{tuv} E^{ab}_{tuv} G_{tuv} with bra table indices (bx, by, bz) and range shifts
+      auto bra_dot = [&](int bx, int by, int bz, int dbx, int dby, int dbz, const double* G) {
+        double acc = 0.0;
+        for (int t = 0; t <= nb[0] + dbx; ++t)
+          for (int u = 0; u <= nb[1] + dby; ++u)
+            for (int v = 0; v <= nb[2] + dbz; ++v)
+              acc = fma(Eb[0][bx][t] * Eb[1][by][u] * Eb[2][bz][v], G[(t * 4 + u) * 4 + v], acc);
+        return acc;
+      };
+      double G0[64];
+      // base ket, bra range one wider in every direction (serves all bra up-shifts)
+      ket_G(0, 0, 0, 0, 0, 0, nb[0] + 1, nb[1] + 1, nb[2] + 1, G0);
+      val = fma(pref, bra_dot(0, 0, 0, 0, 0, 0, G0), val);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int ux = d == 0, uy = d == 1, uz = d == 2;
+        // d/dA_d and d/dB_d
+        double sa = 2.0 * ea * bra_dot(ux ? 1 : 0, uy ? 1 : 0, uz ? 1 : 0, ux, uy, uz, G0);
+        if (l[0][d] > 0) sa -= static_cast<double>(l[0][d]) * bra_dot(ux ? 2 : 0, uy ? 2 : 0, uz ? 2 : 0, -ux, -uy, -uz, G0);
+        double sb = 2.0 * eb * bra_dot(ux ? 3 : 0, uy ? 3 : 0, uz ? 3 : 0, ux, uy, uz, G0);
+        if (l[1][d] > 0) sb -= static_cast<double>(l[1][d]) * bra_dot(ux ? 4 : 0, uy ? 4 : 0, uz ? 4 : 0, -ux, -uy, -uz, G0);
+        dv[0][d] = fma(pref, sa, dv[0][d]);
+        dv[1][d] = fma(pref, sb, dv[1][d]);
+        // d/dC_d: shifted ket tables against the base bra
+        double G1[64];
+        ket_G(ux ? 1 : 0, uy ? 1 : 0, uz ? 1 : 0, ux, uy, uz, nb[0], nb[1], nb[2], G1);
+        double sc = 2.0 * ec * bra_dot(0, 0, 0, 0, 0, 0, G1);
+        if (l[2][d] > 0) {
+          ket_G(ux ? 2 : 0, uy ? 2 : 0, uz ? 2 : 0, -ux, -uy, -uz, nb[0], nb[1], nb[2], G1);
+          sc -= static_cast<double>(l[2][d]) * bra_dot(0, 0, 0, 0, 0, 0, G1);
+        }
+        dv[2][d] = fma(pref, sc, dv[2][d]);
+      }
+    }
+    // butterfly inside the lane group (fixed order)
+    for (int o = gs >> 1; o > 0; o >>= 1) {
+      val += __shfl_xor_sync(0xffffffffu, val, o);
 #pragma unroll
       for (int f = 0; f < 3; ++f)
-        for (int d = 0; d < 3; ++d) {
-          int ls[4][3];
-          for (int f2 = 0; f2 < 4; ++f2)
-            for (int d2 = 0; d2 < 3; ++d2) ls[f2][d2] = l[f2][d2];
-          ls[f][d] += 1;
-          double s = 2.0 * ex3[f] * herm_contract(ls[0], ls[1], ls[2], ls[3], xpa, xpb, hp, xqc, xqd, hq, R);
-          if (l[f][d] > 0) {
-            ls[f][d] -= 2;
-            s -= static_cast<double>(l[f][d]) * herm_contract(ls[0], ls[1], ls[2], ls[3], xpa, xpb, hp, xqc, xqd, hq, R);
-          }
-          dv[f][d] = fma(pref, s, dv[f][d]);
-        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dv[f][d] += __shfl_xor_sync(0xffffffffu, dv[f][d], o);
     }
-    val = gwarp_sum(val);
-#pragma unroll
-    for (int f = 0; f < 3; ++f)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) dv[f][d] = gwarp_sum(dv[f][d]);
-    if (lane < 8) {
-      const int who = lane >> 1;
+    if (!live) continue;
+    for (int r = lig; r < 8; r += gs) {   // the eight index permutations, dealt to the lanes of the group
+      const int who = r >> 1;
       const int a = ao[0], b = ao[1], c = ao[2], d = ao[3];
       int i0, i1, i2, i3;
-      if (who == 0) { i0 = a; i1 = b; i2 = (lane & 1) ? d : c; i3 = (lane & 1) ? c : d; }
-      else if (who == 1) { i0 = b; i1 = a; i2 = (lane & 1) ? d : c; i3 = (lane & 1) ? c : d; }
-      else if (who == 2) { i0 = c; i1 = d; i2 = (lane & 1) ? b : a; i3 = (lane & 1) ? a : b; }
-      else { i0 = d; i1 = c; i2 = (lane & 1) ? b : a; i3 = (lane & 1) ? a : b; }
+      if (who == 0) { i0 = a; i1 = b; i2 = (r & 1) ? d : c; i3 = (r & 1) ? c : d; }
+      else if (who == 1) { i0 = b; i1 = a; i2 = (r & 1) ? d : c; i3 = (r & 1) ? c : d; }
+      else if (who == 2) { i0 = c; i1 = d; i2 = (r & 1) ? b : a; i3 = (r & 1) ? a : b; }
+      else { i0 = d; i1 = c; i2 = (r & 1) ? b : a; i3 = (r & 1) ? a : b; }
       int eff = who;  // duplicates carry bit-identical values
       if (eff == 1 && a == b) eff = 0;
       if (eff == 3 && c == d) eff = 2;
@@ -540,12 +599,59 @@ int evc_gbasis_create(evc_ctx* ctx, int natm, const double* charges_host, int na
     boys[2 * static_cast<size_t>(i)] = static_cast<double>(f[kGTop]);
     boys[2 * static_cast<size_t>(i) + 1] = static_cast<double>(expl(-t0));
   }
+  {
+    unsigned char tab[7][7][7];
+    for (int t = 0; t < 7; ++t)
+      for (int u = 0; u < 7; ++u)
+        for (int v = 0; v < 7; ++v) {
+          const int a = 7 - t;
+          const int idx = 84 - a * (a + 1) * (a + 2) / 6 + u * (7 - t) - u * (u - 1) / 2 + v;
+          tab[t][u][v] = static_cast<unsigned char>((t + u + v <= 6) ? idx : 0);
+        }
+    EVC_CHECK_CUDA(cudaMemcpyToSymbol(c_ridx, tab, sizeof(tab)));
+  }
+  // quartet work list: sort the contracted quartets (ab) >= (cd) by (lane-group size, Cartesian powers)
+  std::vector<int32_t> qsorted, units;
+  {
+    const int npc = nao * (nao + 1) / 2;
+    const long long nq = static_cast<long long>(npc) * (npc + 1) / 2;
+    std::vector<int> pa(npc), pb(npc);
+    for (int a = 0, I = 0; a < nao; ++a)
+      for (int bq = 0; bq <= a; ++bq, ++I) { pa[I] = a; pb[I] = bq; }
+    auto code = [&](int a) { return pw[3 * a] ? 1 : pw[3 * a + 1] ? 2 : pw[3 * a + 2] ? 3 : 0; };
+    std::vector<std::pair<int, int32_t>> keyed;
+    keyed.reserve(static_cast<size_t>(nq));
+    int32_t q = 0;
+    for (int I = 0; I < npc; ++I)
+      for (int K = 0; K <= I; ++K, ++q) {
+        const long long tot = static_cast<long long>(ao_nprim_host[pa[I]]) * ao_nprim_host[pb[I]] * ao_nprim_host[pa[K]] *
+                              ao_nprim_host[pb[K]];
+        int lg = 0;
+        while ((1 << lg) < 32 && (1LL << lg) < tot) ++lg;
+        const int pat = (code(pa[I]) << 6) | (code(pb[I]) << 4) | (code(pa[K]) << 2) | code(pb[K]);
+        keyed.emplace_back((lg << 8) | pat, q);
+      }
+    std::stable_sort(keyed.begin(), keyed.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    qsorted.resize(keyed.size());
+    for (size_t k = 0; k < keyed.size(); ++k) qsorted[k] = keyed[k].second;
+    size_t k = 0;
+    while (k < keyed.size()) {
+      const int key = keyed[k].first, lg = key >> 8, per = 32 >> lg;
+      size_t e = k;
+      while (e < keyed.size() && keyed[e].first == key && e - k < static_cast<size_t>(per)) ++e;
+      units.push_back(static_cast<int32_t>(k));
+      units.push_back(static_cast<int32_t>(((e - k) << 8) | lg));
+      k = e;
+    }
+  }
   evc_gbasis* b = new evc_gbasis();
   b->natm = natm; b->nao = nao; b->nprim = nprim;
+  b->nunits = static_cast<int>(units.size() / 2);
   int rc = 0;
   if ((rc = gupload(&b->ao_atom, ao_atom)) || (rc = gupload(&b->ao_pow, pw)) || (rc = gupload(&b->ao_poff, poff)) ||
       (rc = gupload(&b->aoslices, slices)) || (rc = gupload(&b->prim_exp, ex)) || (rc = gupload(&b->prim_wt, wt)) ||
-      (rc = gupload(&b->charges, ch)) || (rc = gupload(&b->boys, boys))) {
+      (rc = gupload(&b->charges, ch)) || (rc = gupload(&b->boys, boys)) || (rc = gupload(&b->qsorted, qsorted)) ||
+      (rc = gupload(&b->units, units))) {
     delete b;
     return rc;
   }
@@ -556,7 +662,7 @@ int evc_gbasis_create(evc_ctx* ctx, int natm, const double* charges_host, int na
 int evc_gbasis_destroy(evc_gbasis* b) {
   if (b) {
     cudaFree(b->ao_atom); cudaFree(b->ao_pow); cudaFree(b->ao_poff); cudaFree(b->aoslices); cudaFree(b->prim_exp);
-    cudaFree(b->prim_wt); cudaFree(b->charges); cudaFree(b->boys);
+    cudaFree(b->prim_wt); cudaFree(b->charges); cudaFree(b->boys); cudaFree(b->qsorted); cudaFree(b->units);
   }
   delete b;
   return 0;
@@ -578,15 +684,16 @@ int evc_ao_integrals_sp(evc_ctx* ctx, const evc_gbasis* b, int nbatch, const dou
   size_t need = 0;
   evc_ao_integrals_sp_workspace_bytes(b, nbatch, &need);
   EVC_REQUIRE(workspace_bytes >= need, "evc_ao_integrals_sp: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-  GView v{b->natm, b->nao, b->ao_atom, b->ao_pow, b->ao_poff, b->prim_exp, b->prim_wt, b->charges, b->boys};
+  GView v{b->natm, b->nao, b->nunits, b->ao_atom, b->ao_pow, b->ao_poff, b->qsorted, b->units,
+          b->prim_exp, b->prim_wt, b->charges, b->boys};
   GOut o{ovlp, hcore, eri, ipovlp, static_cast<double*>(workspace), eri_ip1, e_nuc, grad_nuc};
   const size_t smem = (2 * static_cast<size_t>(kGBoysN) + 2 + 3 * kGMaxAtoms) * sizeof(double);
   EVC_CHECK_CUDA(cudaFuncSetAttribute(gint2e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   EVC_CHECK_CUDA(cudaFuncSetAttribute(gint1e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int nw = kGThreads / 32;
-  const long long npc = static_cast<long long>(b->nao) * (b->nao + 1) / 2, nq = npc * (npc + 1) / 2;
   int split = 1;
-  while (static_cast<long long>(nbatch) * split < 4LL * ctx->sm_count && static_cast<long long>(split) * nw * 2 <= nq && split < 2048)
+  while (static_cast<long long>(nbatch) * split < 4LL * ctx->sm_count && static_cast<long long>(split) * nw * 2 <= b->nunits &&
+         split < 2048)
     split *= 2;
   gint2e_kernel<<<dim3(split, nbatch), kGThreads, smem, ctx->stream>>>(v, coords, o);
   EVC_CHECK_LAUNCH();

@@ -150,10 +150,40 @@ def probe_ints(args):
                       "step_from_coords_ms": ms_s, "steps_per_s": G / ms_s * 1e3}), flush=True)
 
 
+def probe_ints_sp(args):
+    """K9g: device AO integrals of water (--natm 3) or the Zundel cation (--natm 7) in 6-31G + the step."""
+    import torch
+    from evcont_b200.engine import DeviceAO, DeviceStack, get_engine
+    eng = get_engine()
+    G, N = args.batch, args.ntrain
+    rng = np.random.default_rng(1)
+    ang = 1.0 / 0.52917721092
+    if args.natm == 3:
+        r, th = 0.9572 * ang, np.deg2rad(104.52)
+        base = np.array([[0, 0, 0], [r * np.sin(th / 2), 0, r * np.cos(th / 2)], [-r * np.sin(th / 2), 0, r * np.cos(th / 2)]])
+        sym = ["O", "H", "H"]
+    else:
+        base = np.array([[-2.25, 0, 0], [2.25, 0, 0], [0, 0.1, 0], [-2.9, 1.45, 0.3], [-2.9, -1.45, -0.3],
+                         [2.9, 0.3, 1.45], [2.9, -0.3, -1.45]], dtype=float)
+        sym = ["O", "O", "H", "H", "H", "H", "H"]
+    co = base[None] + 0.05 * rng.standard_normal((G,) + base.shape)
+    sb = eng.sbasis(sym, "6-31g")
+    cd = eng.to_device(co)
+    ao = DeviceAO(eng, G, sb.nao, len(sym), sb.aoslices_host)
+    ms_i = timed(torch, lambda: eng.ao_integrals(sb, cd, out=ao), args.reps)
+    S, one, two = synthetic_stack_dev(eng, torch, sb.nao, N, args.layout)
+    stack = DeviceStack(S, one, two, engine=eng, norb=sb.nao)
+    out = (eng.empty(G), eng.empty(G, len(sym), 3), eng.empty(G, N))
+    ms_s = timed(torch, lambda: eng.energy_with_grad_coords(stack, sb, cd, ao=ao, out=out), args.reps)
+    print(json.dumps({"probe": "ints_sp", "natm": len(sym), "nao": sb.nao, "batch": G, "ntrain": N,
+                      "integrals_ms": ms_i, "geoms_per_s": G / ms_i * 1e3,
+                      "step_from_coords_ms": ms_s, "steps_per_s": G / ms_s * 1e3}), flush=True)
+
+
 def main():
     _peaks()
     ap = argparse.ArgumentParser()
-    ap.add_argument("probe", choices=["trdm", "stack", "step", "ints"])
+    ap.add_argument("probe", choices=["trdm", "stack", "step", "ints", "ints_sp"])
     ap.add_argument("--norb", type=int, default=10)
     ap.add_argument("--nocc", type=int, default=5)
     ap.add_argument("--nvec", type=int, default=20)
@@ -164,7 +194,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--basis", default="sto-6g")
     args = ap.parse_args()
-    {"trdm": probe_trdm, "stack": probe_stack, "step": probe_step, "ints": probe_ints}[args.probe](args)
+    {"trdm": probe_trdm, "stack": probe_stack, "step": probe_step, "ints": probe_ints, "ints_sp": probe_ints_sp}[args.probe](args)
 
 
 if __name__ == "__main__":
