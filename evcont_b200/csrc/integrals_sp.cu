@@ -78,7 +78,7 @@ __device__ __forceinline__ void gtri_unrank(int t, int& a, int& b) {
 // F_0 .. F_L at T.  T < Tmax: F_L..F_{L+5} at the grid point by downward recursion from the tabulated
 // F_11, 5th-order Taylor series for F_L(T), exp(-T) = exp(-T0) exp(T0 - T), downward recursion in T.
 // T >= Tmax: F_0 = sqrt(pi / T) / 2 and the upward recursion with exp(-T) (stable for T > m).
-__device__ void boys_upto(int L, double T, const double* __restrict__ tab, double* F) {
+__device__ __noinline__ void boys_upto(int L, double T, const double* __restrict__ tab, double* F) {
   if (T < static_cast<double>(kGTmax)) {
     const double r = fma(T, static_cast<double>(kGPerUnit), 6755399441055744.0);
     const int i = __double2loint(r);
@@ -108,7 +108,7 @@ __device__ void boys_upto(int L, double T, const double* __restrict__ tab, doubl
 }
 
 // Hermite coefficients E^{ij}_t, t = 0..i+j (without the exp(-mu X_AB^2) factor); E has room for 8
-__device__ __forceinline__ void herm_E(int i, int j, double xpa, double xpb, double h, double* E) {
+__device__ __noinline__ void herm_E(int i, int j, double xpa, double xpb, double h, double* E) {
   E[0] = 1.0;
   int deg = 0;
   for (int s = 0; s < i + j; ++s) {
@@ -131,7 +131,7 @@ __constant__ unsigned char c_ridx[7][7][7];
 __device__ __forceinline__ int ridx(int t, int u, int v) { return c_ridx[t][u][v]; }
 
 // R^0_{tuv}(alpha, X) for t + u + v <= L (L <= 6) into R (84 entries), with scratch S (84)
-__device__ void build_R(int L, double alpha, double X, double Y, double Z, const double* F, double* R, double* S) {
+__device__ __noinline__ void build_R(int L, double alpha, double X, double Y, double Z, const double* F, double* R, double* S) {
   double* A = S;   // level n + 1
   double* B = R;   // level n
   // make sure the final level lands in R: levels L, L-1, ..., 0 alternate; start so that n = 0 writes R
@@ -184,6 +184,52 @@ struct PrimFn {
               acc = fma(sgn * eb * ek, R[ridx(t + t2, u + u2, v + v2)], acc);
             }
       }
+  return acc;
+}
+
+// Staged Hermite contraction of one primitive quartet (real functions: the fully inlined form made the
+// kernel instruction-fetch bound).  Eb: [3][5][6] bra tables (0 base, 1 / 2 first function up / down,
+// 3 / 4 second function up / down), Ek: [3][3][6] ket tables (0 base, 1 / 2 first function up / down).
+struct GTabs {
+  const double* Eb;
+  const double* Ek;
+  const double* R;
+  int nb[3], nk[3];
+};
+
+// G_{tuv} = sum_{t'u'v'} (-1)^{t'+u'+v'} E^{cd}_{t'u'v'} R_{t+t',u+u',v+v'} for the bra range (bt, bu, bv);
+// (kx, ky, kz): ket table per dimension, (dkx, dky, dkz): change of the ket range per dimension
+__device__ __noinline__ void ket_G(const GTabs& tb, int kx, int ky, int kz, int dkx, int dky, int dkz, int bt, int bu,
+                                   int bv, double* G) {
+  const double* ex = tb.Ek + (0 * 3 + kx) * 6;
+  const double* ey = tb.Ek + (1 * 3 + ky) * 6;
+  const double* ez = tb.Ek + (2 * 3 + kz) * 6;
+  for (int t = 0; t <= bt; ++t)
+    for (int u = 0; u <= bu; ++u)
+      for (int v = 0; v <= bv; ++v) {
+        // at most one direction beyond the base bra range (one shifted function at a time)
+        if ((t > tb.nb[0]) + (u > tb.nb[1]) + (v > tb.nb[2]) > 1) continue;
+        double acc = 0.0;
+        for (int t2 = 0; t2 <= tb.nk[0] + dkx; ++t2)
+          for (int u2 = 0; u2 <= tb.nk[1] + dky; ++u2)
+            for (int v2 = 0; v2 <= tb.nk[2] + dkz; ++v2) {
+              const double ek = ex[t2] * ey[u2] * ez[v2];
+              acc = fma(((t2 + u2 + v2) & 1) ? -ek : ek, tb.R[ridx(t + t2, u + u2, v + v2)], acc);
+            }
+        G[(t * 4 + u) * 4 + v] = acc;
+      }
+}
+
+// sum_{tuv} E^{ab}_{tuv} G_{tuv}; (bx, by, bz): bra table per dimension, (dbx, dby, dbz): range change
+__device__ __noinline__ double bra_dot(const GTabs& tb, int bx, int by, int bz, int dbx, int dby, int dbz,
+                                       const double* G) {
+  const double* ex = tb.Eb + (0 * 5 + bx) * 6;
+  const double* ey = tb.Eb + (1 * 5 + by) * 6;
+  const double* ez = tb.Eb + (2 * 5 + bz) * 6;
+  double acc = 0.0;
+  for (int t = 0; t <= tb.nb[0] + dbx; ++t)
+    for (int u = 0; u <= tb.nb[1] + dby; ++u)
+      for (int v = 0; v <= tb.nb[2] + dbz; ++v) acc = fma(ex[t] * ey[u] * ez[v], G[(t * 4 + u) * 4 + v], acc);
   return acc;
 }
 
@@ -273,7 +319,7 @@ gint2e_kernel(GView bs, const double* __restrict__ coords, GOut out) {
       // 1-D Hermite tables: bra for (la + sa, lb + sb) with one of the shifts in {-1, 0, +1}, ket for
       // (lc + sc, ld); index 0: base, 1: first function up, 2: first function down, 3: second up, 4: second down
       double Eb[3][5][6], Ek[3][3][6];
-#pragma unroll
+#pragma unroll 1
       for (int d = 0; d < 3; ++d) {
         herm_E(l[0][d], l[1][d], xpa[d], xpb[d], hp, Eb[d][0]);
         herm_E(l[0][d] + 1, l[1][d], xpa[d], xpb[d], hp, Eb[d][1]);
@@ -286,54 +332,28 @@ gint2e_kernel(GView bs, const double* __restrict__ coords, GOut out) {
       }
       const int nb[3] = {l[0][0] + l[1][0], l[0][1] + l[1][1], l[0][2] + l[1][2]};   // bra Hermite ranges
       const int nk[3] = {l[2][0] + l[3][0], l[2][1] + l[3][1], l[2][2] + l[3][2]};
-      // ket-contracted intermediate G_{tuv} = sum_{t'u'v'} (-1)^{t'+u'+v'} E^{cd}_{t'u'v'} R_{t+t',u+u',v+v'}
-      // kx/ky/kz: ket table index per dimension, dk: ket range shift per dimension; bra range (bt,bu,bv)
-      auto ket_G = [&](int kx, int ky, int kz, int dkx, int dky, int dkz, int bt, int bu, int bv, double* G) {
-        for (int t = 0; t <= bt; ++t)
-          for (int u = 0; u <= bu; ++u)
-            for (int v = 0; v <= bv; ++v) {
-              // at most one direction beyond the base bra range (one shifted function at a time)
-              if ((t > nb[0]) + (u > nb[1]) + (v > nb[2]) > 1) continue;
-              double acc = 0.0;
-              for (int t2 = 0; t2 <= nk[0] + dkx; ++t2)
-                for (int u2 = 0; u2 <= nk[1] + dky; ++u2)
-                  for (int v2 = 0; v2 <= nk[2] + dkz; ++v2) {
-                    const double ek = Ek[0][kx][t2] * Ek[1][ky][u2] * Ek[2][kz][v2];
-                    acc = fma(((t2 + u2 + v2) & 1) ? -ek : ek, R[ridx(t + t2, u + u2, v + v2)], acc);
-                  }
-              G[(t * 4 + u) * 4 + v] = acc;
-            }
-      };
-      // sum_{tuv} E^{ab}_{tuv} G_{tuv} with bra table indices (bx, by, bz) and range shifts
-      auto bra_dot = [&](int bx, int by, int bz, int dbx, int dby, int dbz, const double* G) {
-        double acc = 0.0;
-        for (int t = 0; t <= nb[0] + dbx; ++t)
-          for (int u = 0; u <= nb[1] + dby; ++u)
-            for (int v = 0; v <= nb[2] + dbz; ++v)
-              acc = fma(Eb[0][bx][t] * Eb[1][by][u] * Eb[2][bz][v], G[(t * 4 + u) * 4 + v], acc);
-        return acc;
-      };
+      const GTabs tb{&Eb[0][0][0], &Ek[0][0][0], R, {nb[0], nb[1], nb[2]}, {nk[0], nk[1], nk[2]}};
       double G0[64];
       // base ket, bra range one wider in every direction (serves all bra up-shifts)
-      ket_G(0, 0, 0, 0, 0, 0, nb[0] + 1, nb[1] + 1, nb[2] + 1, G0);
-      val = fma(pref, bra_dot(0, 0, 0, 0, 0, 0, G0), val);
-#pragma unroll
+      ket_G(tb, 0, 0, 0, 0, 0, 0, nb[0] + 1, nb[1] + 1, nb[2] + 1, G0);
+      val = fma(pref, bra_dot(tb, 0, 0, 0, 0, 0, 0, G0), val);
+#pragma unroll 1
       for (int d = 0; d < 3; ++d) {
         const int ux = d == 0, uy = d == 1, uz = d == 2;
         // d/dA_d and d/dB_d
-        double sa = 2.0 * ea * bra_dot(ux ? 1 : 0, uy ? 1 : 0, uz ? 1 : 0, ux, uy, uz, G0);
-        if (l[0][d] > 0) sa -= static_cast<double>(l[0][d]) * bra_dot(ux ? 2 : 0, uy ? 2 : 0, uz ? 2 : 0, -ux, -uy, -uz, G0);
-        double sb = 2.0 * eb * bra_dot(ux ? 3 : 0, uy ? 3 : 0, uz ? 3 : 0, ux, uy, uz, G0);
-        if (l[1][d] > 0) sb -= static_cast<double>(l[1][d]) * bra_dot(ux ? 4 : 0, uy ? 4 : 0, uz ? 4 : 0, -ux, -uy, -uz, G0);
+        double sa = 2.0 * ea * bra_dot(tb, ux ? 1 : 0, uy ? 1 : 0, uz ? 1 : 0, ux, uy, uz, G0);
+        if (l[0][d] > 0) sa -= static_cast<double>(l[0][d]) * bra_dot(tb, ux ? 2 : 0, uy ? 2 : 0, uz ? 2 : 0, -ux, -uy, -uz, G0);
+        double sb = 2.0 * eb * bra_dot(tb, ux ? 3 : 0, uy ? 3 : 0, uz ? 3 : 0, ux, uy, uz, G0);
+        if (l[1][d] > 0) sb -= static_cast<double>(l[1][d]) * bra_dot(tb, ux ? 4 : 0, uy ? 4 : 0, uz ? 4 : 0, -ux, -uy, -uz, G0);
         dv[0][d] = fma(pref, sa, dv[0][d]);
         dv[1][d] = fma(pref, sb, dv[1][d]);
         // d/dC_d: shifted ket tables against the base bra
         double G1[64];
-        ket_G(ux ? 1 : 0, uy ? 1 : 0, uz ? 1 : 0, ux, uy, uz, nb[0], nb[1], nb[2], G1);
-        double sc = 2.0 * ec * bra_dot(0, 0, 0, 0, 0, 0, G1);
+        ket_G(tb, ux ? 1 : 0, uy ? 1 : 0, uz ? 1 : 0, ux, uy, uz, nb[0], nb[1], nb[2], G1);
+        double sc = 2.0 * ec * bra_dot(tb, 0, 0, 0, 0, 0, 0, G1);
         if (l[2][d] > 0) {
-          ket_G(ux ? 2 : 0, uy ? 2 : 0, uz ? 2 : 0, -ux, -uy, -uz, nb[0], nb[1], nb[2], G1);
-          sc -= static_cast<double>(l[2][d]) * bra_dot(0, 0, 0, 0, 0, 0, G1);
+          ket_G(tb, ux ? 2 : 0, uy ? 2 : 0, uz ? 2 : 0, -ux, -uy, -uz, nb[0], nb[1], nb[2], G1);
+          sc -= static_cast<double>(l[2][d]) * bra_dot(tb, 0, 0, 0, 0, 0, 0, G1);
         }
         dv[2][d] = fma(pref, sc, dv[2][d]);
       }
