@@ -7,7 +7,9 @@ behind the same surface:
   the GPU as ONE batched launch over the pair list;
 * link tables are cached instead of being rebuilt per call;
 * :meth:`append_civec` feeds a CI vector directly (synthetic vectors, vectors
-  from another solver), bypassing the PySCF-dependent ``kernel``/``transform_ci``.
+  from another solver);
+* ``kernel`` (device Davidson), ``transform_ci`` (device) and the canonical basis
+  (``evcont_b200.scf.rhf``) are built in, so ``append_to_rdms(MolLite)`` needs no PySCF.
 
 Reference quirks kept on purpose: mirror blocks
 ``[i, -1]`` hold the *untransposed* RDMs (:125,127); ``mol_index`` is not pruned.
@@ -47,7 +49,7 @@ class FCI_EVCont_obj:
         if nroots_train == 1:
             e_all, fcivec_all = [e_all], [fcivec_all]
         if self.cibasis != "OAO":
-            from pyscf.fci.addons import transform_ci  # needs PySCF
+            from .fci import transform_ci  # device minors + DMMA products
             S = mol.intor("int1e_ovlp")
             u = np.einsum("ji,jk,kl->il", basis, S, get_basis(mol))
             fcivec_all = [transform_ci(c, mol.nelec, u) for c in fcivec_all]

@@ -120,6 +120,10 @@ SIGNATURES = {
     "evc_fci_contract_2e": (C.c_int, [C.c_void_p, C.c_int, c_i64, c_i64, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_void_p,
                                       C.c_size_t]),
+    "evc_transform_ci_workspace_bytes": (C.c_int, [C.c_int, c_i64, c_i64, c_sz_p]),
+    "evc_transform_ci": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_i64, c_i64, C.c_void_p, C.c_void_p,
+                                   c_double_p, c_double_p, c_double_p, C.c_void_p, C.c_size_t]),
+    "evc_fock_rhf": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "evc_md_positions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p,
                                    c_double_p]),
     "evc_md_berendsen": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,

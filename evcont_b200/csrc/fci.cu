@@ -97,6 +97,66 @@ __global__ void fci_hdiag_kernel(int n, int64_t na, int64_t nb, const int64_t* _
   hdiag[K] = e;
 }
 
+
+// ---- transform_ci: the same state in a rotated one-particle basis -------------------------
+// pyscf.fci.addons.transform_ci, called at evcont/FCI_EVCont.py:79-85:
+//   ci_new = Ta^T ci Tb,   T[I][J] = det(u[occ(I), occ(J)])   (rows: old strings, columns: new strings)
+// One thread per minor: the k x k sub-matrix is gathered from u (shared memory) and eliminated with
+// partial pivoting.  transpose != 0 stores T^T (element (r, c) of the output is T[c][r]).
+constexpr int kMaxOcc = 12;
+
+__global__ void __launch_bounds__(128)
+fci_minors_kernel(int n, int k, int64_t ns, const int64_t* __restrict__ strs, const double* __restrict__ u,
+                  int transpose, double* __restrict__ out, int64_t ld) {
+  extern __shared__ double us[];
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) us[t] = u[t];
+  __syncthreads();
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (c >= ns) return;
+  const int64_t sI = strs[transpose ? c : r], sJ = strs[transpose ? r : c];
+  unsigned char oi[kMaxOcc], oj[kMaxOcc];
+  int ki = 0, kj = 0;
+  for (int o = 0; o < n; ++o) {
+    if ((sI >> o) & 1) oi[ki++] = static_cast<unsigned char>(o);
+    if ((sJ >> o) & 1) oj[kj++] = static_cast<unsigned char>(o);
+  }
+  double a[kMaxOcc * kMaxOcc];
+  for (int x = 0; x < k; ++x)
+    for (int y = 0; y < k; ++y) a[x * kMaxOcc + y] = us[oi[x] * n + oj[y]];
+  double det = 1.0;
+  for (int p = 0; p < k; ++p) {
+    int piv = p;
+    double best = fabs(a[p * kMaxOcc + p]);
+    for (int x = p + 1; x < k; ++x) {
+      const double v = fabs(a[x * kMaxOcc + p]);
+      if (v > best) { best = v; piv = x; }
+    }
+    if (best == 0.0) { det = 0.0; break; }
+    if (piv != p) {
+      for (int y = p; y < k; ++y) {
+        const double t = a[p * kMaxOcc + y];
+        a[p * kMaxOcc + y] = a[piv * kMaxOcc + y];
+        a[piv * kMaxOcc + y] = t;
+      }
+      det = -det;
+    }
+    const double d = a[p * kMaxOcc + p], inv = 1.0 / d;
+    det *= d;
+    for (int x = p + 1; x < k; ++x) {
+      const double f = a[x * kMaxOcc + p] * inv;
+      for (int y = p + 1; y < k; ++y) a[x * kMaxOcc + y] = fma(-f, a[p * kMaxOcc + y], a[x * kMaxOcc + y]);
+    }
+  }
+  out[r * ld + c] = det;
+}
+
+__global__ void fci_zero_pad_kernel(int64_t rows, int64_t cols, int64_t ld, double* __restrict__ m) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  for (int64_t c = cols; c < ld; ++c) m[r * ld + c] = 0.0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -145,6 +205,65 @@ int evc_fci_contract_2e(evc_ctx* ctx, int norb, int64_t na, int64_t nb, const ui
   fci_sigma_kernel<<<blocks, 256, 0, ctx->stream>>>(norb, n2p, na, nb, link_a, nlink_a, link_b, nlink_b, h1eff, D, G,
                                                      sigma);
   EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_transform_ci_workspace_bytes(int norb, int64_t na, int64_t nb, size_t* bytes) {
+  EVC_REQUIRE(bytes && norb >= 1 && na >= 1 && nb >= 1, "evc_transform_ci_workspace_bytes: bad arguments");
+  const int64_t ldb = (nb + 1) & ~static_cast<int64_t>(1);
+  size_t tot = evc_align_up(static_cast<size_t>(na) * na * sizeof(double), 256);        // Ta^T
+  tot += evc_align_up(static_cast<size_t>(nb) * ldb * sizeof(double), 256);              // Tb
+  tot += 2 * evc_align_up(static_cast<size_t>(na) * ldb * sizeof(double), 256);          // ci Tb, result
+  tot += evc_align_up(evc_rows_axpy_ws_bytes(ldb, static_cast<int>(nb), static_cast<int>(na)), 256);
+  tot += evc_align_up(evc_rows_axpy_ws_bytes(ldb, static_cast<int>(na), static_cast<int>(na)), 256);
+  *bytes = tot + 256;
+  return 0;
+}
+
+// u: [norb][norb] row-major, rows = old orbitals, columns = new orbitals; strs_a / strs_b: occupation
+// strings (device int64, ascending); ci_in / ci_out: [na][nb] contiguous.
+int evc_transform_ci(evc_ctx* ctx, int norb, int nelec_a, int nelec_b, int64_t na, int64_t nb, const int64_t* strs_a,
+                     const int64_t* strs_b, const double* u, const double* ci_in, double* ci_out, void* workspace,
+                     size_t workspace_bytes) {
+  EVC_REQUIRE(ctx && strs_a && strs_b && u && ci_in && ci_out && workspace, "evc_transform_ci: NULL argument");
+  EVC_REQUIRE(norb >= 1 && norb <= 62 && nelec_a >= 0 && nelec_b >= 0 && nelec_a <= kMaxOcc && nelec_b <= kMaxOcc &&
+                  nelec_a <= norb && nelec_b <= norb,
+              "evc_transform_ci: norb=%d nelec=(%d,%d) unsupported (at most %d electrons per spin)", norb, nelec_a,
+              nelec_b, kMaxOcc);
+  EVC_REQUIRE(na < (int64_t(1) << 31) / (nb > 0 ? nb : 1) && na <= 65535 && nb <= 65535,
+              "evc_transform_ci: %lld x %lld strings unsupported", (long long)na, (long long)nb);
+  size_t need = 0;
+  int rc = evc_transform_ci_workspace_bytes(norb, na, nb, &need);
+  if (rc) return rc;
+  EVC_REQUIRE(workspace_bytes >= need, "evc_transform_ci: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+  const int64_t ldb = (nb + 1) & ~static_cast<int64_t>(1);
+  evc_arena ar(workspace, workspace_bytes);
+  double* TaT = ar.take<double>(static_cast<size_t>(na) * na);
+  double* Tb = ar.take<double>(static_cast<size_t>(nb) * ldb);
+  double* tmp = ar.take<double>(static_cast<size_t>(na) * ldb);
+  double* res = ar.take<double>(static_cast<size_t>(na) * ldb);
+  const size_t w1 = evc_rows_axpy_ws_bytes(ldb, static_cast<int>(nb), static_cast<int>(na));
+  const size_t w2 = evc_rows_axpy_ws_bytes(ldb, static_cast<int>(na), static_cast<int>(na));
+  char* ws1 = ar.take<char>(w1);
+  char* ws2 = ar.take<char>(w2);
+  EVC_REQUIRE(TaT && Tb && tmp && res && ws1 && ws2, "evc_transform_ci: workspace too small");
+  const size_t smem = static_cast<size_t>(norb) * norb * sizeof(double);
+  fci_minors_kernel<<<dim3(static_cast<unsigned>((na + 127) / 128), static_cast<unsigned>(na)), 128, smem, ctx->stream>>>(
+      norb, nelec_a, na, strs_a, u, 1, TaT, na);
+  EVC_CHECK_LAUNCH();
+  fci_minors_kernel<<<dim3(static_cast<unsigned>((nb + 127) / 128), static_cast<unsigned>(nb)), 128, smem, ctx->stream>>>(
+      norb, nelec_b, nb, strs_b, u, 0, Tb, ldb);
+  EVC_CHECK_LAUNCH();
+  if (ldb != nb) {
+    fci_zero_pad_kernel<<<static_cast<unsigned>((nb + 127) / 128), 128, 0, ctx->stream>>>(nb, nb, ldb, Tb);
+    EVC_CHECK_LAUNCH();
+  }
+  // tmp[Ia][Jb] = sum_Ib ci[Ia][Ib] Tb[Ib][Jb];  res[Ja][Jb] = sum_Ia TaT[Ja][Ia] tmp[Ia][Jb]
+  if ((rc = evc_rows_axpy(ctx, Tb, ldb, static_cast<int>(nb), ci_in, static_cast<int>(na), tmp, ws1, w1))) return rc;
+  if ((rc = evc_rows_axpy(ctx, tmp, ldb, static_cast<int>(na), TaT, static_cast<int>(na), res, ws2, w2))) return rc;
+  EVC_CHECK_CUDA(cudaMemcpy2DAsync(ci_out, static_cast<size_t>(nb) * sizeof(double), res,
+                                   static_cast<size_t>(ldb) * sizeof(double), static_cast<size_t>(nb) * sizeof(double),
+                                   static_cast<size_t>(na), cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 

@@ -67,15 +67,20 @@ def restore_electron_exchange_symmetry(h2, norb):
 
 def get_basis(mol, basis_type="OAO"):
     """Orthogonal basis as AO coefficients (evcont/electron_integral_utils.py:91-119).
-    ``"OAO"`` runs on the GPU; ``"canonical"``/``"split"`` need PySCF's RHF / Boys."""
+    ``"OAO"``: Loewdin on the GPU (K3).  ``"canonical"``: RHF orbitals -- PySCF's RHF for a PySCF
+    ``Mole``, otherwise :func:`evcont_b200.scf.rhf` (Fock builds on the device).  ``"split"``
+    (Boys-localised occupied / virtual blocks) needs PySCF's localiser."""
     if basis_type == "OAO":
         return get_loewdin_trafo(mol.intor("int1e_ovlp"))
+    if basis_type == "canonical" and not type(mol).__module__.startswith("pyscf."):
+        from .scf import rhf
+        return rhf(mol).mo_coeff
     try:
         from pyscf import lo, scf
     except ImportError as exc:
         raise NotImplementedError(
-            f"basis_type={basis_type!r} needs PySCF (RHF / Boys localisation); only 'OAO' is "
-            "built in") from exc
+            f"basis_type={basis_type!r} needs PySCF (Boys localisation); 'OAO' and 'canonical' "
+            "are built in") from exc
     myhf = scf.RHF(mol)
     myhf.scf()
     basis = myhf.mo_coeff

@@ -160,6 +160,31 @@ class Engine:
         """Device operator for ``H c`` and ``diag H`` of one geometry: :class:`FCIHamiltonian`."""
         return FCIHamiltonian(self, h1e, eri, norb, nelec)
 
+    def transform_ci(self, ci, nelec, u):
+        """``pyscf.fci.addons.transform_ci``: ``ci`` (na, nb) in the old orbitals -> device tensor
+        (na, nb) in the new ones, ``u[old, new]`` (``evc_transform_ci``)."""
+        from . import cistring
+        u = self.to_device(np.asarray(u, dtype=np.float64))
+        n = u.shape[0]
+        if u.shape != (n, n):
+            raise NotImplementedError("transform_ci: only square rotations (dimension conserved)")
+        nea, neb = int(nelec[0]), int(nelec[1])
+        key = ("strs", n, nea, neb)
+        if key not in self._links:
+            self._links[key] = tuple(torch.from_numpy(cistring.make_strings(range(n), k)).to(self.device)
+                                     for k in (nea, neb))
+        sa, sb = self._links[key]
+        na, nb = sa.numel(), sb.numel()
+        ci = self.to_device(ci).reshape(na, nb)
+        out = self.empty(na, nb)
+        nbytes = C.c_size_t()
+        check(self.lib.evc_transform_ci_workspace_bytes(n, na, nb, C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        check(self.lib.evc_transform_ci(self._ctx, n, nea, neb, na, nb, _ptr(sa), _ptr(sb), _ptr(u), _ptr(ci),
+                                        _ptr(out), _ptr(ws), ws.numel()))
+        return out
+
     # -- K3 ------------------------------------------------------------------------
     def loewdin(self, s_ao):
         """Batched Loewdin: ``s_ao`` (G, n, n) device -> (X, evals, evecs)."""

@@ -99,6 +99,17 @@ def _unpack_nelec(nelec):
     return int(nelec[0]), int(nelec[1])
 
 
+def transform_ci(ci, nelec, u):
+    """Drop-in for ``pyscf.fci.addons.transform_ci`` as the reference uses it
+    (evcont/FCI_EVCont.py:79-85): the CI vector ``ci`` (na, nb), solved in an orthonormal basis,
+    expressed in the basis reached by the rotation ``u[old, new]``.  Runs on the device
+    (``evc_transform_ci``: minors of ``u`` per string pair, two DMMA products)."""
+    u = np.asarray(u, dtype=np.float64)
+    if u.ndim != 2:
+        raise NotImplementedError("transform_ci: one rotation for both spins only")
+    return get_engine().transform_ci(ci, _unpack_nelec(nelec), u).cpu().numpy()
+
+
 class B200FCISolver:
     """FCI solver facade whose transition RDMs run on the B200."""
 

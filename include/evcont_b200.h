@@ -375,6 +375,27 @@ int evc_fci_contract_2e(evc_ctx *ctx, int norb, int64_t na, int64_t nb,
                         const double *h1eff, const double *w2, const double *civec,
                         double *sigma, void *workspace, size_t workspace_bytes);
 
+/* ---- transform_ci: CI vector in a rotated one-particle basis --------------------------
+ * Replaces pyscf.fci.addons.transform_ci(ci, nelec, u), called at evcont/FCI_EVCont.py:79-85
+ * with u = basis^T S basis_oao (rows: old orbitals, columns: new orbitals, [norb][norb]
+ * row-major, device):  ci_new = Ta^T ci Tb,  T[I][J] = det(u[occ(I), occ(J)]) over the
+ * occupation strings of each spin (device int64, ascending, as evc_make_strings_host
+ * returns them).  One thread per minor (partial-pivoting elimination), the two products on
+ * the FP64 tensor cores.  ci_in / ci_out: [na][nb] contiguous; at most 12 electrons per spin. */
+int evc_transform_ci_workspace_bytes(int norb, int64_t na, int64_t nb, size_t *bytes);
+int evc_transform_ci(evc_ctx *ctx, int norb, int nelec_a, int nelec_b, int64_t na, int64_t nb,
+                     const int64_t *strs_a, const int64_t *strs_b, const double *u,
+                     const double *ci_in, double *ci_out, void *workspace,
+                     size_t workspace_bytes);
+
+/* ---- closed-shell Fock matrix ------------------------------------------------------------
+ * The device part of the RHF behind get_basis(mol, "canonical")
+ * (evcont/electron_integral_utils.py:103-106: scf.RHF(mol).scf() -> mo_coeff; the reference's
+ * default cibasis):  F = hcore + J - K/2 with J[p,q] = sum_rs (pq|rs) D[r,s] and
+ * K[p,s] = sum_qr (pq|rs) D[q,r]; hcore, dm, fock: [n][n]; eri: [n^4] chemists' notation. */
+int evc_fock_rhf(evc_ctx *ctx, int n, const double *hcore, const double *eri, const double *dm,
+                 double *fock);
+
 #ifdef __cplusplus
 }
 #endif
