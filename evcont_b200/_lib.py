@@ -123,6 +123,7 @@ SIGNATURES = {
     "evc_transform_ci_workspace_bytes": (C.c_int, [C.c_int, c_i64, c_i64, c_sz_p]),
     "evc_transform_ci": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_i64, c_i64, C.c_void_p, C.c_void_p,
                                    c_double_p, c_double_p, c_double_p, C.c_void_p, C.c_size_t]),
+    "evc_min_sqdist": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i64, c_i64, c_double_p, c_double_p, c_double_p]),
     "evc_fock_rhf": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "evc_md_positions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p,
                                    c_double_p]),

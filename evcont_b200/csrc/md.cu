@@ -77,6 +77,41 @@ __global__ void md_berendsen_kernel(int nbatch, int natm, double dt, double taut
 
 }  // namespace
 
+
+// Farthest-point selection in Hamiltonian space (evcont/MD_utils.py:363-405, data_addition =
+// "farthest_point_ham"): for every trajectory frame g the smallest weighted squared distance
+//   d[g][t] = sum_{k < L1} (x[g][k] - y[t][k])^2 + 1/2 sum_{L1 <= k < L} (x[g][k] - y[t][k])^2
+// to the T training rows (x, y: [.][L] rows holding h1 (L1 = n^2) followed by h2 (n^4) in the OAO
+// basis).  One CTA per frame; differences are formed before squaring (no cancellation), fixed
+// reduction order.
+__global__ void __launch_bounds__(256)
+md_min_sqdist_kernel(int T, int64_t L1, int64_t L, const double* __restrict__ x, const double* __restrict__ y,
+                     double* __restrict__ dmin) {
+  __shared__ double red[8];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const double* xr = x + static_cast<int64_t>(g) * L;
+  double best = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const double* yr = y + static_cast<int64_t>(t) * L;
+    double a1 = 0.0, a2 = 0.0;
+    for (int64_t k = tid; k < L; k += 256) {
+      const double d = xr[k] - yr[k];
+      if (k < L1) a1 = fma(d, d, a1); else a2 = fma(d, d, a2);
+    }
+    double a = a1 + 0.5 * a2;
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = a;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      if (t == 0 || s < best) best = s;
+    }
+  }
+  if (tid == 0) dmin[g] = best;
+}
+
 extern "C" {
 
 int evc_md_positions(evc_ctx* ctx, int nbatch, int natm, double dt, const double* v, const double* a, double* x) {
@@ -111,6 +146,16 @@ int evc_md_velocities(evc_ctx* ctx, int nbatch, int natm, double dt, int first, 
                                                                    epot_log, ekin_log);
   EVC_CHECK_LAUNCH();
   md_advance_frame_kernel<<<1, 1, 0, ctx->stream>>>(frame_idx);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_min_sqdist(evc_ctx* ctx, int nframes, int ntrain, int64_t len_one, int64_t len_total, const double* frames,
+                   const double* train, double* dmin) {
+  EVC_REQUIRE(ctx && frames && train && dmin, "evc_min_sqdist: NULL argument");
+  EVC_REQUIRE(ntrain >= 1 && len_one >= 0 && len_total >= len_one, "evc_min_sqdist: bad sizes");
+  if (nframes <= 0) return 0;
+  md_min_sqdist_kernel<<<nframes, 256, 0, ctx->stream>>>(ntrain, len_one, len_total, frames, train, dmin);
   EVC_CHECK_LAUNCH();
   return 0;
 }

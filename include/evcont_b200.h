@@ -396,6 +396,14 @@ int evc_transform_ci(evc_ctx *ctx, int norb, int nelec_a, int nelec_b, int64_t n
 int evc_fock_rhf(evc_ctx *ctx, int n, const double *hcore, const double *eri, const double *dm,
                  double *fock);
 
+/* ---- farthest-point selection in Hamiltonian space ----------------------------------------
+ * converge_EVCont_MD(..., data_addition="farthest_point_ham") (evcont/MD_utils.py:363-405):
+ * dmin[g] = min_t ( |h1_g - h1_t|^2 + 1/2 |h2_g - h2_t|^2 ) over the training rows;
+ * frames: [nframes][len_total], train: [ntrain][len_total], each row h1 (len_one doubles)
+ * followed by h2, OAO basis, device. */
+int evc_min_sqdist(evc_ctx *ctx, int nframes, int ntrain, int64_t len_one, int64_t len_total,
+                   const double *frames, const double *train, double *dmin);
+
 #ifdef __cplusplus
 }
 #endif
