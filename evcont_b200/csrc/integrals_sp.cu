@@ -10,44 +10,21 @@
 //     R^n_000 = (-2 rho)^n F_n(rho |PQ|^2),  R^n_{t+1,u,v} = t R^{n+1}_{t-1,u,v} + X_PQ R^{n+1}_{tuv}
 //   d/dA_x of a Cartesian Gaussian: 2a G_{l+1} - l G_{l-1};  (nabla a b|cd) = -d/dA (ab|cd).
 //
-// One lane group (1..32 lanes, sized to the number of primitive quartets) per contracted quartet (ab|cd),
-// (ab) >= (cd); lanes over the primitive quartets; per
-// primitive quartet the value and the derivatives with respect to the centres of a, b and c (the
-// fourth follows from translational invariance) are evaluated from shifted angular momenta over one
-// shared R table, with the ket side contracted first (staged Hermite contraction); fixed butterfly
-// reduction; the eight index permutations are written by the lanes of the group.
+// Two-electron part: gclass.cu (class kernels over contracted SHELL quartets, everything in registers;
+// one lane group of 1..32 lanes, sized to the number of primitive quartets, per shell quartet; value and
+// the derivatives with respect to the centres of a, b and c from shifted angular momenta over one R table,
+// the fourth centre from translational invariance; fixed butterfly reduction; the eight index permutations
+// written by the lanes of the group).  This file: tables, work lists, the one-electron kernel, the C ABI.
 #include "common.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <vector>
 
-namespace {
-
-constexpr int kGTop = 11;            // Boys table: F_11(T0) and exp(-T0) on the grid T0 = i / 64
-constexpr int kGPerUnit = 64;
-constexpr int kGTmax = 32;
-constexpr int kGBoysN = kGTmax * kGPerUnit + 1;
-constexpr int kGThreads = 256;
-constexpr int kGMaxAtoms = 16;
-constexpr int kGMaxL = 6;            // highest Boys order: (pp|pp) with one derivative = 5 (+1 spare)
-
-}  // namespace
-
-struct evc_gbasis {
-  int natm, nao, nprim, nunits;
-  int32_t *ao_atom, *ao_pow, *ao_poff, *aoslices;  // ao_pow: [nao][3]
-  int32_t *qsorted, *units;                        // quartet work list (see evc_gbasis_create)
-  double *prim_exp, *prim_wt, *charges, *boys;
-};
+#include "integrals_sp.cuh"
 
 namespace {
-
-struct GView {
-  int natm, nao, nunits;
-  const int32_t *ao_atom, *ao_pow, *ao_poff, *qsorted, *units;
-  const double *prim_exp, *prim_wt, *charges, *boys;
-};
+using namespace evc_gint;
 
 void boys_host_g(int mmax, long double t, long double* out) {
   const long double et = expl(-t);
@@ -65,14 +42,6 @@ __device__ __forceinline__ double gwarp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-
-__device__ __forceinline__ void gtri_unrank(int t, int& a, int& b) {
-  int x = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f);
-  while (x * (x + 1) / 2 > t) --x;
-  while ((x + 1) * (x + 2) / 2 <= t) ++x;
-  a = x;
-  b = t - x * (x + 1) / 2;
 }
 
 // F_0 .. F_L at T.  T < Tmax: F_L..F_{L+5} at the grid point by downward recursion from the tabulated
@@ -152,245 +121,6 @@ __device__ __noinline__ void build_R(int L, double alpha, double X, double Y, do
           B[ridx(t, u, v)] = val;
         }
     double* tmp = A; A = B; B = tmp;
-  }
-}
-
-struct PrimFn {
-  double a, x, y, z;
-  int l[3];
-};
-
-// (reference form of the primitive contraction, kept for documentation of the staged version below)
-// sum_{tuv} E^{ab}_{tuv} sum_{t'u'v'} (-1)^{t'+u'+v'} E^{cd}_{t'u'v'} R_{t+t',u+u',v+v'} for the given powers
-[[maybe_unused]] __device__ double herm_contract(const int* la, const int* lb, const int* lc, const int* ld, const double* xpa,
-                                const double* xpb, double hp, const double* xqc, const double* xqd, double hq,
-                                const double* R) {
-  double Eb[3][8], Ek[3][8];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    herm_E(la[d], lb[d], xpa[d], xpb[d], hp, Eb[d]);
-    herm_E(lc[d], ld[d], xqc[d], xqd[d], hq, Ek[d]);
-  }
-  double acc = 0.0;
-  for (int t = 0; t <= la[0] + lb[0]; ++t)
-    for (int u = 0; u <= la[1] + lb[1]; ++u)
-      for (int v = 0; v <= la[2] + lb[2]; ++v) {
-        const double eb = Eb[0][t] * Eb[1][u] * Eb[2][v];
-        for (int t2 = 0; t2 <= lc[0] + ld[0]; ++t2)
-          for (int u2 = 0; u2 <= lc[1] + ld[1]; ++u2)
-            for (int v2 = 0; v2 <= lc[2] + ld[2]; ++v2) {
-              const double ek = Ek[0][t2] * Ek[1][u2] * Ek[2][v2];
-              const double sgn = ((t2 + u2 + v2) & 1) ? -1.0 : 1.0;
-              acc = fma(sgn * eb * ek, R[ridx(t + t2, u + u2, v + v2)], acc);
-            }
-      }
-  return acc;
-}
-
-// Staged Hermite contraction of one primitive quartet (real functions: the fully inlined form made the
-// kernel instruction-fetch bound).  Eb: [3][5][6] bra tables (0 base, 1 / 2 first function up / down,
-// 3 / 4 second function up / down), Ek: [3][3][6] ket tables (0 base, 1 / 2 first function up / down).
-struct GTabs {
-  const double* Eb;
-  const double* Ek;
-  const double* R;
-  int nb[3], nk[3];
-};
-
-// G_{tuv} = sum_{t'u'v'} (-1)^{t'+u'+v'} E^{cd}_{t'u'v'} R_{t+t',u+u',v+v'} for the bra range (bt, bu, bv);
-// (kx, ky, kz): ket table per dimension, (dkx, dky, dkz): change of the ket range per dimension
-__device__ __noinline__ void ket_G(const GTabs& tb, int kx, int ky, int kz, int dkx, int dky, int dkz, int bt, int bu,
-                                   int bv, double* G) {
-  const double* ex = tb.Ek + (0 * 3 + kx) * 6;
-  const double* ey = tb.Ek + (1 * 3 + ky) * 6;
-  const double* ez = tb.Ek + (2 * 3 + kz) * 6;
-  for (int t = 0; t <= bt; ++t)
-    for (int u = 0; u <= bu; ++u)
-      for (int v = 0; v <= bv; ++v) {
-        // at most one direction beyond the base bra range (one shifted function at a time)
-        if ((t > tb.nb[0]) + (u > tb.nb[1]) + (v > tb.nb[2]) > 1) continue;
-        double acc = 0.0;
-        for (int t2 = 0; t2 <= tb.nk[0] + dkx; ++t2)
-          for (int u2 = 0; u2 <= tb.nk[1] + dky; ++u2)
-            for (int v2 = 0; v2 <= tb.nk[2] + dkz; ++v2) {
-              const double ek = ex[t2] * ey[u2] * ez[v2];
-              acc = fma(((t2 + u2 + v2) & 1) ? -ek : ek, tb.R[ridx(t + t2, u + u2, v + v2)], acc);
-            }
-        G[(t * 4 + u) * 4 + v] = acc;
-      }
-}
-
-// sum_{tuv} E^{ab}_{tuv} G_{tuv}; (bx, by, bz): bra table per dimension, (dbx, dby, dbz): range change
-__device__ __noinline__ double bra_dot(const GTabs& tb, int bx, int by, int bz, int dbx, int dby, int dbz,
-                                       const double* G) {
-  const double* ex = tb.Eb + (0 * 5 + bx) * 6;
-  const double* ey = tb.Eb + (1 * 5 + by) * 6;
-  const double* ez = tb.Eb + (2 * 5 + bz) * 6;
-  double acc = 0.0;
-  for (int t = 0; t <= tb.nb[0] + dbx; ++t)
-    for (int u = 0; u <= tb.nb[1] + dby; ++u)
-      for (int v = 0; v <= tb.nb[2] + dbz; ++v) acc = fma(ex[t] * ey[u] * ez[v], G[(t * 4 + u) * 4 + v], acc);
-  return acc;
-}
-
-struct GOut {
-  double *ovlp, *hcore, *eri, *ipovlp, *vtmp, *eri_ip1, *e_nuc, *grad_nuc;
-};
-
-__global__ void __launch_bounds__(kGThreads)
-gint2e_kernel(GView bs, const double* __restrict__ coords, GOut out) {
-  extern __shared__ __align__(16) double sm[];
-  double* boys = sm;                      // [kGBoysN][2]
-  double* Rc = boys + 2 * kGBoysN + 2;    // [natm][3]
-  const int n = bs.nao, natm = bs.natm;
-  const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NW = kGThreads / 32;
-  for (int k = tid; k < 2 * kGBoysN; k += kGThreads) boys[k] = __ldg(bs.boys + k);
-  for (int k = tid; k < 3 * natm; k += kGThreads) Rc[k] = coords[static_cast<int64_t>(g) * natm * 3 + k];
-  __syncthreads();
-  const int64_t n2 = static_cast<int64_t>(n) * n, n3 = n2 * n, n4 = n2 * n2;
-  double* eri = out.eri + static_cast<int64_t>(g) * n4;
-  double* ip1 = out.eri_ip1 + static_cast<int64_t>(g) * 3 * n4;
-  // Work units (built once per basis): contracted quartets with the same Cartesian powers and the same
-  // lane-group size gs = 2^k >= min(#primitive quartets, 32) are packed 32/gs to a warp, so quartets of
-  // the single-primitive outer shells do not leave 31 lanes idle and every lane runs the same loops.
-  for (int un = blockIdx.x * NW + warp; un < bs.nunits; un += gridDim.x * NW) {
-    const int ustart = bs.units[2 * un], uinfo = bs.units[2 * un + 1];
-    const int gs = 1 << (uinfo & 0xff), ucount = uinfo >> 8;
-    const int grp = lane / gs, lig = lane - grp * gs;
-    const bool live = grp < ucount;
-    const int q = bs.qsorted[ustart + (live ? grp : 0)];
-    int I, K, ao[4];
-    gtri_unrank(q, I, K);
-    gtri_unrank(I, ao[0], ao[1]);
-    gtri_unrank(K, ao[2], ao[3]);
-    int l[4][3], p0[4], np_[4];
-    double ctr[4][3];
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      p0[f] = bs.ao_poff[ao[f]];
-      np_[f] = bs.ao_poff[ao[f] + 1] - p0[f];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        l[f][d] = bs.ao_pow[3 * ao[f] + d];
-        ctr[f][d] = Rc[3 * bs.ao_atom[ao[f]] + d];
-      }
-    }
-    const int ltot = l[0][0] + l[0][1] + l[0][2] + l[1][0] + l[1][1] + l[1][2] + l[2][0] + l[2][1] + l[2][2] +
-                     l[3][0] + l[3][1] + l[3][2];
-    const double ab2 = (ctr[0][0] - ctr[1][0]) * (ctr[0][0] - ctr[1][0]) + (ctr[0][1] - ctr[1][1]) * (ctr[0][1] - ctr[1][1]) +
-                       (ctr[0][2] - ctr[1][2]) * (ctr[0][2] - ctr[1][2]);
-    const double cd2 = (ctr[2][0] - ctr[3][0]) * (ctr[2][0] - ctr[3][0]) + (ctr[2][1] - ctr[3][1]) * (ctr[2][1] - ctr[3][1]) +
-                       (ctr[2][2] - ctr[3][2]) * (ctr[2][2] - ctr[3][2]);
-    // accumulators: value, d/d(centre of a), d/d(centre of b), d/d(centre of c)
-    double val = 0.0, dv[3][3];
-#pragma unroll
-    for (int f = 0; f < 3; ++f)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) dv[f][d] = 0.0;
-    const int tot = live ? np_[0] * np_[1] * np_[2] * np_[3] : 0;
-    for (int t = lig; t < tot; t += gs) {
-      int r = t;
-      const int il = r % np_[3]; r /= np_[3];
-      const int ik = r % np_[2]; r /= np_[2];
-      const int ij = r % np_[1]; r /= np_[1];
-      const int ii = r;
-      const double ea = bs.prim_exp[p0[0] + ii], eb = bs.prim_exp[p0[1] + ij], ec = bs.prim_exp[p0[2] + ik],
-                   ed = bs.prim_exp[p0[3] + il];
-      const double w4 = bs.prim_wt[p0[0] + ii] * bs.prim_wt[p0[1] + ij] * bs.prim_wt[p0[2] + ik] * bs.prim_wt[p0[3] + il];
-      const double p = ea + eb, qq = ec + ed;
-      const double kk = exp(-(ea * eb / p) * ab2 - (ec * ed / qq) * cd2);
-      const double pref = w4 * kk * 34.986836655249725 / (p * qq * sqrt(p + qq));  // 2 pi^2.5
-      if (fabs(pref) < 1.0e-18) continue;
-      double xpa[3], xpb[3], xqc[3], xqd[3], pq[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double P = (ea * ctr[0][d] + eb * ctr[1][d]) / p, Q = (ec * ctr[2][d] + ed * ctr[3][d]) / qq;
-        xpa[d] = P - ctr[0][d]; xpb[d] = P - ctr[1][d];
-        xqc[d] = Q - ctr[2][d]; xqd[d] = Q - ctr[3][d];
-        pq[d] = P - Q;
-      }
-      const double rho = p * qq / (p + qq);
-      const int L = ltot + 1;
-      double F[kGMaxL + 2], R[84], S[84];
-      boys_upto(L, rho * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]), boys, F);
-      build_R(L, rho, pq[0], pq[1], pq[2], F, R, S);
-      const double hp = 0.5 / p, hq = 0.5 / qq;
-      // 1-D Hermite tables: bra for (la + sa, lb + sb) with one of the shifts in {-1, 0, +1}, ket for
-      // (lc + sc, ld); index 0: base, 1: first function up, 2: first function down, 3: second up, 4: second down
-      double Eb[3][5][6], Ek[3][3][6];
-#pragma unroll 1
-      for (int d = 0; d < 3; ++d) {
-        herm_E(l[0][d], l[1][d], xpa[d], xpb[d], hp, Eb[d][0]);
-        herm_E(l[0][d] + 1, l[1][d], xpa[d], xpb[d], hp, Eb[d][1]);
-        if (l[0][d] > 0) herm_E(l[0][d] - 1, l[1][d], xpa[d], xpb[d], hp, Eb[d][2]);
-        herm_E(l[0][d], l[1][d] + 1, xpa[d], xpb[d], hp, Eb[d][3]);
-        if (l[1][d] > 0) herm_E(l[0][d], l[1][d] - 1, xpa[d], xpb[d], hp, Eb[d][4]);
-        herm_E(l[2][d], l[3][d], xqc[d], xqd[d], hq, Ek[d][0]);
-        herm_E(l[2][d] + 1, l[3][d], xqc[d], xqd[d], hq, Ek[d][1]);
-        if (l[2][d] > 0) herm_E(l[2][d] - 1, l[3][d], xqc[d], xqd[d], hq, Ek[d][2]);
-      }
-      const int nb[3] = {l[0][0] + l[1][0], l[0][1] + l[1][1], l[0][2] + l[1][2]};   // bra Hermite ranges
-      const int nk[3] = {l[2][0] + l[3][0], l[2][1] + l[3][1], l[2][2] + l[3][2]};
-      const GTabs tb{&Eb[0][0][0], &Ek[0][0][0], R, {nb[0], nb[1], nb[2]}, {nk[0], nk[1], nk[2]}};
-      double G0[64];
-      // base ket, bra range one wider in every direction (serves all bra up-shifts)
-      ket_G(tb, 0, 0, 0, 0, 0, 0, nb[0] + 1, nb[1] + 1, nb[2] + 1, G0);
-      val = fma(pref, bra_dot(tb, 0, 0, 0, 0, 0, 0, G0), val);
-#pragma unroll 1
-      for (int d = 0; d < 3; ++d) {
-        const int ux = d == 0, uy = d == 1, uz = d == 2;
-        // d/dA_d and d/dB_d
-        double sa = 2.0 * ea * bra_dot(tb, ux ? 1 : 0, uy ? 1 : 0, uz ? 1 : 0, ux, uy, uz, G0);
-        if (l[0][d] > 0) sa -= static_cast<double>(l[0][d]) * bra_dot(tb, ux ? 2 : 0, uy ? 2 : 0, uz ? 2 : 0, -ux, -uy, -uz, G0);
-        double sb = 2.0 * eb * bra_dot(tb, ux ? 3 : 0, uy ? 3 : 0, uz ? 3 : 0, ux, uy, uz, G0);
-        if (l[1][d] > 0) sb -= static_cast<double>(l[1][d]) * bra_dot(tb, ux ? 4 : 0, uy ? 4 : 0, uz ? 4 : 0, -ux, -uy, -uz, G0);
-        dv[0][d] = fma(pref, sa, dv[0][d]);
-        dv[1][d] = fma(pref, sb, dv[1][d]);
-        // d/dC_d: shifted ket tables against the base bra
-        double G1[64];
-        ket_G(tb, ux ? 1 : 0, uy ? 1 : 0, uz ? 1 : 0, ux, uy, uz, nb[0], nb[1], nb[2], G1);
-        double sc = 2.0 * ec * bra_dot(tb, 0, 0, 0, 0, 0, 0, G1);
-        if (l[2][d] > 0) {
-          ket_G(tb, ux ? 2 : 0, uy ? 2 : 0, uz ? 2 : 0, -ux, -uy, -uz, nb[0], nb[1], nb[2], G1);
-          sc -= static_cast<double>(l[2][d]) * bra_dot(tb, 0, 0, 0, 0, 0, 0, G1);
-        }
-        dv[2][d] = fma(pref, sc, dv[2][d]);
-      }
-    }
-    // butterfly inside the lane group (fixed order)
-    for (int o = gs >> 1; o > 0; o >>= 1) {
-      val += __shfl_xor_sync(0xffffffffu, val, o);
-#pragma unroll
-      for (int f = 0; f < 3; ++f)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) dv[f][d] += __shfl_xor_sync(0xffffffffu, dv[f][d], o);
-    }
-    if (!live) continue;
-    for (int r = lig; r < 8; r += gs) {   // the eight index permutations, dealt to the lanes of the group
-      const int who = r >> 1;
-      const int a = ao[0], b = ao[1], c = ao[2], d = ao[3];
-      int i0, i1, i2, i3;
-      if (who == 0) { i0 = a; i1 = b; i2 = (r & 1) ? d : c; i3 = (r & 1) ? c : d; }
-      else if (who == 1) { i0 = b; i1 = a; i2 = (r & 1) ? d : c; i3 = (r & 1) ? c : d; }
-      else if (who == 2) { i0 = c; i1 = d; i2 = (r & 1) ? b : a; i3 = (r & 1) ? a : b; }
-      else { i0 = d; i1 = c; i2 = (r & 1) ? b : a; i3 = (r & 1) ? a : b; }
-      int eff = who;  // duplicates carry bit-identical values
-      if (eff == 1 && a == b) eff = 0;
-      if (eff == 3 && c == d) eff = 2;
-      if (I == K) eff -= (eff >= 2) ? 2 : 0;
-      double gx, gy, gz;
-      if (eff < 3) { gx = dv[eff][0]; gy = dv[eff][1]; gz = dv[eff][2]; }
-      else {  // translational invariance: d/dD = -(d/dA + d/dB + d/dC)
-        gx = -(dv[0][0] + dv[1][0] + dv[2][0]); gy = -(dv[0][1] + dv[1][1] + dv[2][1]);
-        gz = -(dv[0][2] + dv[1][2] + dv[2][2]);
-      }
-      const int64_t idx = i0 * n3 + i1 * n2 + i2 * n + i3;
-      eri[idx] = val;
-      ip1[idx] = -gx;
-      ip1[n4 + idx] = -gy;
-      ip1[2 * n4 + idx] = -gz;
-    }
   }
 }
 
@@ -630,48 +360,75 @@ int evc_gbasis_create(evc_ctx* ctx, int natm, const double* charges_host, int na
         }
     EVC_CHECK_CUDA(cudaMemcpyToSymbol(c_ridx, tab, sizeof(tab)));
   }
-  // quartet work list: sort the contracted quartets (ab) >= (cd) by (lane-group size, Cartesian powers)
-  std::vector<int32_t> qsorted, units;
-  {
-    const int npc = nao * (nao + 1) / 2;
-    const long long nq = static_cast<long long>(npc) * (npc + 1) / 2;
-    std::vector<int> pa(npc), pb(npc);
-    for (int a = 0, I = 0; a < nao; ++a)
-      for (int bq = 0; bq <= a; ++bq, ++I) { pa[I] = a; pb[I] = bq; }
-    auto code = [&](int a) { return pw[3 * a] ? 1 : pw[3 * a + 1] ? 2 : pw[3 * a + 2] ? 3 : 0; };
-    std::vector<std::pair<int, int32_t>> keyed;
-    keyed.reserve(static_cast<size_t>(nq));
-    int32_t q = 0;
-    for (int I = 0; I < npc; ++I)
-      for (int K = 0; K <= I; ++K, ++q) {
-        const long long tot = static_cast<long long>(ao_nprim_host[pa[I]]) * ao_nprim_host[pb[I]] * ao_nprim_host[pa[K]] *
-                              ao_nprim_host[pb[K]];
-        int lg = 0;
-        while ((1 << lg) < 32 && (1LL << lg) < tot) ++lg;
-        const int pat = (code(pa[I]) << 6) | (code(pb[I]) << 4) | (code(pa[K]) << 2) | code(pb[K]);
-        keyed.emplace_back((lg << 8) | pat, q);
-      }
-    std::stable_sort(keyed.begin(), keyed.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-    qsorted.resize(keyed.size());
-    for (size_t k = 0; k < keyed.size(); ++k) qsorted[k] = keyed[k].second;
-    size_t k = 0;
-    while (k < keyed.size()) {
-      const int key = keyed[k].first, lg = key >> 8, per = 32 >> lg;
-      size_t e = k;
-      while (e < keyed.size() && keyed[e].first == key && e - k < static_cast<size_t>(per)) ++e;
-      units.push_back(static_cast<int32_t>(k));
-      units.push_back(static_cast<int32_t>(((e - k) << 8) | lg));
-      k = e;
+  // shells: an s AO, or the three consecutive components x, y, z of a p shell
+  std::vector<int32_t> sh_atom, sh_ao0, sh_p0, sh_np, sh_l;
+  for (int a = 0; a < nao;) {
+    const int l = pw[3 * a] + pw[3 * a + 1] + pw[3 * a + 2];
+    if (l == 1) {
+      EVC_REQUIRE(a + 2 < nao && pw[3 * a] == 1 && pw[3 * (a + 1) + 1] == 1 && pw[3 * (a + 2) + 2] == 1 &&
+                      ao_atom[a + 1] == ao_atom[a] && ao_atom[a + 2] == ao_atom[a] &&
+                      ao_nprim_host[a + 1] == ao_nprim_host[a] && ao_nprim_host[a + 2] == ao_nprim_host[a],
+                  "evc_gbasis_create: p functions must come as consecutive x, y, z components of one shell (AO %d)", a);
+      for (int k = 0; k < ao_nprim_host[a]; ++k)
+        EVC_REQUIRE(ex[poff[a] + k] == ex[poff[a + 1] + k] && ex[poff[a] + k] == ex[poff[a + 2] + k] &&
+                        wt[poff[a] + k] == wt[poff[a + 1] + k] && wt[poff[a] + k] == wt[poff[a + 2] + k],
+                    "evc_gbasis_create: the components of p shell at AO %d differ in their primitives", a);
     }
+    sh_atom.push_back(ao_atom[a]); sh_ao0.push_back(a); sh_p0.push_back(poff[a]); sh_np.push_back(ao_nprim_host[a]);
+    sh_l.push_back(l);
+    a += l == 1 ? 3 : 1;
+  }
+  const int nshell = static_cast<int>(sh_atom.size());
+  EVC_REQUIRE(nshell <= 255, "evc_gbasis_create: too many shells (%d)", nshell);
+  // shell-quartet work lists per class: canonical order (p first inside bra and ket, heavier pair as bra),
+  // sorted by lane-group size, packed 32 / gs quartets to a warp
+  std::vector<int32_t> cq, cunits;
+  int cq_off[kGClasses + 1] = {0}, cunit_off[kGClasses + 1] = {0};
+  {
+    std::vector<std::vector<std::pair<int, int32_t>>> per(kGClasses);
+    for (int I = 0; I < nshell; ++I)
+      for (int J = 0; J <= I; ++J)
+        for (int K = 0; K <= I; ++K)
+          for (int Lq = 0; Lq <= (K == I ? J : K); ++Lq) {
+            int A = I, B = J, Cc = K, D = Lq;
+            if (sh_l[A] < sh_l[B]) std::swap(A, B);
+            if (sh_l[Cc] < sh_l[D]) std::swap(Cc, D);
+            if (sh_l[Cc] + sh_l[D] > sh_l[A] + sh_l[B]) { std::swap(A, Cc); std::swap(B, D); }
+            const int npf = sh_l[A] + sh_l[B] + sh_l[Cc] + sh_l[D];
+            const int cls = npf <= 1 ? npf : npf == 2 ? (sh_l[B] ? 2 : 3) : npf + 1;
+            const long long tot = static_cast<long long>(sh_np[A]) * sh_np[B] * sh_np[Cc] * sh_np[D];
+            int lg = 0;
+            while ((1 << lg) < 32 && (1LL << lg) < tot) ++lg;
+            per[cls].emplace_back(lg, static_cast<int32_t>(A | (B << 8) | (Cc << 16) | (D << 24)));
+          }
+    for (int c = 0; c < kGClasses; ++c) {
+      std::stable_sort(per[c].begin(), per[c].end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+      cq_off[c] = static_cast<int>(cq.size());
+      cunit_off[c] = static_cast<int>(cunits.size() / 2);
+      size_t k = 0;
+      while (k < per[c].size()) {
+        const int lg = per[c][k].first, perw = 32 >> lg;
+        size_t e = k;
+        while (e < per[c].size() && per[c][e].first == lg && e - k < static_cast<size_t>(perw)) ++e;
+        cunits.push_back(static_cast<int32_t>(cq.size() + 0));
+        cunits.push_back(static_cast<int32_t>(((e - k) << 8) | lg));
+        for (size_t x = k; x < e; ++x) cq.push_back(per[c][x].second);
+        k = e;
+      }
+    }
+    cq_off[kGClasses] = static_cast<int>(cq.size());
+    cunit_off[kGClasses] = static_cast<int>(cunits.size() / 2);
   }
   evc_gbasis* b = new evc_gbasis();
-  b->natm = natm; b->nao = nao; b->nprim = nprim;
-  b->nunits = static_cast<int>(units.size() / 2);
+  b->natm = natm; b->nao = nao; b->nprim = nprim; b->nshell = nshell;
+  for (int c = 0; c <= kGClasses; ++c) { b->cq_off[c] = cq_off[c]; b->cunit_off[c] = cunit_off[c]; }
   int rc = 0;
   if ((rc = gupload(&b->ao_atom, ao_atom)) || (rc = gupload(&b->ao_pow, pw)) || (rc = gupload(&b->ao_poff, poff)) ||
       (rc = gupload(&b->aoslices, slices)) || (rc = gupload(&b->prim_exp, ex)) || (rc = gupload(&b->prim_wt, wt)) ||
-      (rc = gupload(&b->charges, ch)) || (rc = gupload(&b->boys, boys)) || (rc = gupload(&b->qsorted, qsorted)) ||
-      (rc = gupload(&b->units, units))) {
+      (rc = gupload(&b->charges, ch)) || (rc = gupload(&b->boys, boys)) ||
+      (rc = gupload(&b->sh_atom, sh_atom)) || (rc = gupload(&b->sh_ao0, sh_ao0)) ||
+      (rc = gupload(&b->sh_p0, sh_p0)) || (rc = gupload(&b->sh_np, sh_np)) || (rc = gupload(&b->cq, cq)) ||
+      (rc = gupload(&b->cunits, cunits))) {
     delete b;
     return rc;
   }
@@ -682,7 +439,8 @@ int evc_gbasis_create(evc_ctx* ctx, int natm, const double* charges_host, int na
 int evc_gbasis_destroy(evc_gbasis* b) {
   if (b) {
     cudaFree(b->ao_atom); cudaFree(b->ao_pow); cudaFree(b->ao_poff); cudaFree(b->aoslices); cudaFree(b->prim_exp);
-    cudaFree(b->prim_wt); cudaFree(b->charges); cudaFree(b->boys); cudaFree(b->qsorted); cudaFree(b->units);
+    cudaFree(b->prim_wt); cudaFree(b->charges); cudaFree(b->boys);
+    cudaFree(b->sh_atom); cudaFree(b->sh_ao0); cudaFree(b->sh_p0); cudaFree(b->sh_np); cudaFree(b->cq); cudaFree(b->cunits);
   }
   delete b;
   return 0;
@@ -704,19 +462,20 @@ int evc_ao_integrals_sp(evc_ctx* ctx, const evc_gbasis* b, int nbatch, const dou
   size_t need = 0;
   evc_ao_integrals_sp_workspace_bytes(b, nbatch, &need);
   EVC_REQUIRE(workspace_bytes >= need, "evc_ao_integrals_sp: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-  GView v{b->natm, b->nao, b->nunits, b->ao_atom, b->ao_pow, b->ao_poff, b->qsorted, b->units,
-          b->prim_exp, b->prim_wt, b->charges, b->boys};
+  GView v{b->natm, b->nao, b->ao_atom, b->ao_pow, b->ao_poff,
+          b->sh_atom, b->sh_ao0, b->sh_p0, b->sh_np, b->prim_exp, b->prim_wt, b->charges, b->boys};
   GOut o{ovlp, hcore, eri, ipovlp, static_cast<double*>(workspace), eri_ip1, e_nuc, grad_nuc};
   const size_t smem = (2 * static_cast<size_t>(kGBoysN) + 2 + 3 * kGMaxAtoms) * sizeof(double);
-  EVC_CHECK_CUDA(cudaFuncSetAttribute(gint2e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   EVC_CHECK_CUDA(cudaFuncSetAttribute(gint1e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int nw = kGThreads / 32;
-  int split = 1;
-  while (static_cast<long long>(nbatch) * split < 4LL * ctx->sm_count && static_cast<long long>(split) * nw * 2 <= b->nunits &&
-         split < 2048)
-    split *= 2;
-  gint2e_kernel<<<dim3(split, nbatch), kGThreads, smem, ctx->stream>>>(v, coords, o);
-  EVC_CHECK_LAUNCH();
+  {
+    int rc;
+    if ((rc = launch_gclass_part0(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+    if ((rc = launch_gclass_part1(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+    if ((rc = launch_gclass_part2(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+    if ((rc = launch_gclass_part3(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+    if ((rc = launch_gclass_part4(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+  }
   int split1 = 1;
   while (static_cast<long long>(nbatch) * split1 < 2LL * ctx->sm_count && split1 * nw < b->nao * b->nao) split1 *= 2;
   gint1e_kernel<<<dim3(split1, nbatch), kGThreads, smem, ctx->stream>>>(v, coords, o);

@@ -1,0 +1,53 @@
+// Shared declarations of the s+p AO-integral engine K9g (integrals_sp.cu: tables, one-electron part, C ABI;
+// gclass.cu: the two-electron class kernels, compiled in several parts).
+#pragma once
+#include "common.cuh"
+
+namespace evc_gint {
+
+constexpr int kGTop = 11;            // Boys table: F_11(T0) and exp(-T0) on the grid T0 = i / 64
+constexpr int kGPerUnit = 64;
+constexpr int kGTmax = 32;
+constexpr int kGBoysN = kGTmax * kGPerUnit + 1;
+constexpr int kGThreads = 256;
+constexpr int kGMaxAtoms = 16;
+constexpr int kGMaxL = 6;            // highest Boys order: (pp|pp) with one derivative = 5 (+1 spare)
+
+constexpr int kGClasses = 6;   // ssss, psss, ppss, psps, ppps, pppp (canonical shell-quartet classes)
+
+struct GView {
+  int natm, nao;
+  const int32_t *ao_atom, *ao_pow, *ao_poff;
+  const int32_t *sh_atom, *sh_ao0, *sh_p0, *sh_np;
+  const double *prim_exp, *prim_wt, *charges, *boys;
+};
+
+
+struct GOut {
+  double *ovlp, *hcore, *eri, *ipovlp, *vtmp, *eri_ip1, *e_nuc, *grad_nuc;
+};
+
+// launches the two-electron class kernels of compilation part `part` (0: ssss, psss, ppss, psps; 1: ppps;
+// 2..4: pppp with the component of the second function fixed) for the unit lists of the basis
+int launch_gclass_part0(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+                        const int* cunit_off, const double* coords, const GOut& o);
+int launch_gclass_part1(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+                        const int* cunit_off, const double* coords, const GOut& o);
+int launch_gclass_part2(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+                        const int* cunit_off, const double* coords, const GOut& o);
+int launch_gclass_part3(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+                        const int* cunit_off, const double* coords, const GOut& o);
+int launch_gclass_part4(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+                        const int* cunit_off, const double* coords, const GOut& o);
+
+}  // namespace evc_gint
+
+struct evc_gbasis {
+  int natm, nao, nprim, nshell;
+  int32_t *ao_atom, *ao_pow, *ao_poff, *aoslices;  // ao_pow: [nao][3]
+  int32_t *sh_atom, *sh_ao0, *sh_p0, *sh_np;       // shells (s: one AO, p: three consecutive AOs)
+  int32_t *cq, *cunits;                            // shell-quartet work lists of the class kernels
+  int cq_off[evc_gint::kGClasses + 1], cunit_off[evc_gint::kGClasses + 1];
+  double *prim_exp, *prim_wt, *charges, *boys;
+};
+
