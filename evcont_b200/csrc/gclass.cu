@@ -1,11 +1,12 @@
 // K9g two-electron class kernels (see integrals_sp.cuh / integrals_sp.cu).  Compiled once per
-// EVC_GCLASS_PART (Makefile): 0 = ssss, psss, ppss, psps; 1 = ppps; 2, 3, 4 = pppp with JB = 0, 1, 2.
+// EVC_GCLASS_PART (Makefile): 0 = ssss, psss, ppss, psps; 1 = ppps; 2, 3, 4 = pppp with JB = 0, 1, 2;
+// 5 = the one-electron class kernels.
 #include "integrals_sp.cuh"
 
 #include <algorithm>
 
 #ifndef EVC_GCLASS_PART
-#error "compile with -DEVC_GCLASS_PART=0..4"
+#error "compile with -DEVC_GCLASS_PART=0..5"
 #endif
 
 namespace evc_gint {
@@ -418,6 +419,262 @@ int launch_one(cudaStream_t st, int sm_count, int nbatch, const GView& v, const 
   return 0;
 }
 
+#if EVC_GCLASS_PART == 5
+// ---------------------------------------------------------------------------------------------------------
+// One-electron class kernels: one warp per ORDERED shell pair (A, B) of class (LA, LB) (the derivative acts on
+// the first function only, evcont/ab_initio_gradients_loewdin.py:25, 147: <nabla a|O|b>).  The lanes form
+// 32 / gs groups of gs = 2^k >= #primitive pairs lanes; a group takes one "slot" at a time -- nucleus C
+// (nuclear attraction and its derivative, needed per nucleus) or the extra slot natm (overlap and kinetic
+// energy) -- with its lanes over the primitive pairs; Boys values, R table and Hermite coefficients are
+// compile-time indexed registers as in the two-electron kernels.  Group results go through shared memory,
+// then the lanes assemble ovlp, hcore, int1e_ipovlp and the per-nucleus rows the caller symmetrises into
+// hcore_generator's arrays.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int k1eThreads = 128;
+
+// E^{ij}_0 for i <= 2, j <= 3 (1-D overlap factor without sqrt(pi / p))
+__device__ __forceinline__ double ovl1d(int i, int j, double xa, double xb, double h) {
+  double E[6];
+  E[0] = 1.0;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    if (s < i + j) {
+      const double x = s < i ? xa : xb;
+      double nw[6];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+        if (t <= s + 1) {
+          double v = (t <= s) ? x * E[t] : h * E[t - 1];
+          if (t >= 1 && t <= s) v = fma(h, E[t - 1], v);
+          if (t + 1 <= s) v = fma(static_cast<double>(t + 1), E[t + 1], v);
+          nw[t] = v;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 6; ++t)
+        if (t <= s + 1) E[t] = nw[t];
+    }
+  }
+  return E[0];
+}
+
+// per primitive pair: 1-D overlap factors O[d][i][j] = E^{ij}_0 (i <= LA + 1, j <= LB + 2) and 1-D Hermite
+// tables EH[d][i][j][t] (i <= LA + 1, j <= LB), built once and indexed at compile time by every component
+struct Prim1 {
+  double O[3][3][4];
+  double EH[3][3][2][4];
+  double ea2, eb;
+};
+
+__device__ __forceinline__ double ovl3c(int ax, int ay, int az, int bx, int by, int bz, const Prim1& q) {
+  return q.O[0][ax][bx] * q.O[1][ay][by] * q.O[2][az][bz];
+}
+
+// <a| -1/2 nabla^2 |b> / ((pi/p)^1.5 K) for b in {s, p}
+__device__ __forceinline__ double kin3c(int ax, int ay, int az, int bx, int by, int bz, const Prim1& q) {
+  double r = q.eb * static_cast<double>(2 * (bx + by + bz) + 3) * ovl3c(ax, ay, az, bx, by, bz, q);
+  const double m = -2.0 * q.eb * q.eb;
+  r = fma(m, ovl3c(ax, ay, az, bx + 2, by, bz, q), r);
+  r = fma(m, ovl3c(ax, ay, az, bx, by + 2, bz, q), r);
+  r = fma(m, ovl3c(ax, ay, az, bx, by, bz + 2, q), r);
+  return r;
+}
+
+template <int L>
+__device__ __forceinline__ double rinv3c(int ax, int ay, int az, int bx, int by, int bz, const Prim1& q,
+                                         const double (&R)[L + 1][L + 1][L + 1]) {
+  double s = 0.0;
+  bool first = true;
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (t > ax + bx || u > ay + by || v > az + bz) continue;
+        const double e = q.EH[0][ax][bx][t] * q.EH[1][ay][by][u] * q.EH[2][az][bz][v];
+        if (first) { s = e * R[t][u][v]; first = false; }
+        else s = fma(e, R[t][u][v], s);
+      }
+  return s;
+}
+
+// acc[0] value, acc[1..3] d/dA of it (both for operator O given by the functor f(ax..bz))
+template <int AX, int AY, int AZ, int BX, int BY, int BZ, typename F>
+__device__ __forceinline__ void with_grad(double wgt, double ea2, double* acc, F f) {
+  acc[0] = fma(wgt, f(AX, AY, AZ, BX, BY, BZ), acc[0]);
+  double gx = ea2 * f(AX + 1, AY, AZ, BX, BY, BZ), gy = ea2 * f(AX, AY + 1, AZ, BX, BY, BZ),
+         gz = ea2 * f(AX, AY, AZ + 1, BX, BY, BZ);
+  if (AX > 0) gx = fma(-static_cast<double>(AX), f(AX - 1, AY, AZ, BX, BY, BZ), gx);
+  if (AY > 0) gy = fma(-static_cast<double>(AY), f(AX, AY - 1, AZ, BX, BY, BZ), gy);
+  if (AZ > 0) gz = fma(-static_cast<double>(AZ), f(AX, AY, AZ - 1, BX, BY, BZ), gz);
+  acc[1] = fma(wgt, gx, acc[1]);
+  acc[2] = fma(wgt, gy, acc[2]);
+  acc[3] = fma(wgt, gz, acc[3]);
+}
+
+template <int LA, int LB, int IA, int IB, bool NUC, int L>
+__device__ __forceinline__ void block1e(const Prim1& q, double so, double vo, const double (&R)[L + 1][L + 1][L + 1],
+                                        double* acc) {
+  constexpr int AX = LA && IA == 0, AY = LA && IA == 1, AZ = LA && IA == 2;
+  constexpr int BX = LB && IB == 0, BY = LB && IB == 1, BZ = LB && IB == 2;
+  if constexpr (NUC) {
+    with_grad<AX, AY, AZ, BX, BY, BZ>(vo, q.ea2, acc, [&](int ax, int ay, int az, int bx, int by, int bz) {
+      return rinv3c<L>(ax, ay, az, bx, by, bz, q, R);
+    });
+  } else {
+    with_grad<AX, AY, AZ, BX, BY, BZ>(so, q.ea2, acc, [&](int ax, int ay, int az, int bx, int by, int bz) {
+      return ovl3c(ax, ay, az, bx, by, bz, q);
+    });
+    with_grad<AX, AY, AZ, BX, BY, BZ>(so, q.ea2, acc + 4, [&](int ax, int ay, int az, int bx, int by, int bz) {
+      return kin3c(ax, ay, az, bx, by, bz, q);
+    });
+  }
+}
+
+template <int LA, int LB, bool NUC>
+__device__ __forceinline__ void slot1e(const GView& bs, const double (&A)[3], const double (&B)[3], const double* Cc, int p0a,
+                                       int npa, int p0b, int npb, int lig, int gs,
+                                       double (&acc)[(LA ? 3 : 1) * (LB ? 3 : 1)][8]) {
+  constexpr int L = LA + LB + 1, NA = LA ? 3 : 1, NB = LB ? 3 : 1;
+  const double ab2 = (A[0] - B[0]) * (A[0] - B[0]) + (A[1] - B[1]) * (A[1] - B[1]) + (A[2] - B[2]) * (A[2] - B[2]);
+#pragma unroll 1
+  for (int t = lig; t < npa * npb; t += gs) {
+    const int i = t / npb, j = t - i * npb;
+    const double ea = __ldg(bs.prim_exp + p0a + i), eb = __ldg(bs.prim_exp + p0b + j);
+    const double p = ea + eb, ip = 1.0 / p, hp = 0.5 * ip;
+    const double w = __ldg(bs.prim_wt + p0a + i) * __ldg(bs.prim_wt + p0b + j) * exp(-(ea * eb * ip) * ab2);
+    Prim1 q;
+    double P[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      P[d] = (ea * A[d] + eb * B[d]) * ip;
+      const double xpa = P[d] - A[d], xpb = P[d] - B[d];
+#pragma unroll
+      for (int ii = 0; ii <= LA + 1; ++ii) {
+        if constexpr (NUC) {
+#pragma unroll
+          for (int jj = 0; jj <= LB; ++jj) herm_fixed(ii, jj, xpa, xpb, hp, q.EH[d][ii][jj]);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj <= LB + 2; ++jj) q.O[d][ii][jj] = ovl1d(ii, jj, xpa, xpb, hp);
+        }
+      }
+    }
+    q.ea2 = 2.0 * ea; q.eb = eb;
+    const double pip = 3.14159265358979323846 * ip;
+    const double so = w * pip * sqrt(pip), vo = w * 6.28318530717958647692 * ip;
+    double R[L + 1][L + 1][L + 1];
+    if constexpr (NUC) {
+      const double X = P[0] - Cc[0], Y = P[1] - Cc[1], Z = P[2] - Cc[2];
+      double F[L + 1];
+      boys_fixed<L>(p * (X * X + Y * Y + Z * Z), bs.boys, F);
+      build_R_fixed<L>(p, X, Y, Z, F, R);
+    }
+#define EVC_B1(IA, IB) block1e<LA, LB, IA, IB, NUC, L>(q, so, vo, R, acc[IA * NB + IB]);
+    EVC_B1(0, 0)
+    if constexpr (NB == 3) { EVC_B1(0, 1) EVC_B1(0, 2) }
+    if constexpr (NA == 3) {
+      EVC_B1(1, 0) EVC_B1(2, 0)
+      if constexpr (NB == 3) { EVC_B1(1, 1) EVC_B1(1, 2) EVC_B1(2, 1) EVC_B1(2, 2) }
+    }
+#undef EVC_B1
+  }
+}
+
+template <int LA, int LB>
+__global__ void __launch_bounds__(k1eThreads)
+gint1e_class_kernel(GView bs, const int32_t* __restrict__ plist, int npairs, const double* __restrict__ coords, GOut out) {
+  extern __shared__ double sm1e[];
+  constexpr int NA = LA ? 3 : 1, NB = LB ? 3 : 1, NC = NA * NB, NW = k1eThreads / 32;
+  const int n = bs.nao, natm = bs.natm, nslot = natm + 1;
+  const int g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* Rc = coords + static_cast<int64_t>(g) * natm * 3;
+  double* buf = sm1e + static_cast<size_t>(warp) * (kGMaxAtoms + 1) * NC * 8;   // [slot][comp][8]
+  const int64_t n2 = static_cast<int64_t>(n) * n;
+  for (int pi = blockIdx.x * NW + warp; pi < npairs; pi += gridDim.x * NW) {
+    const int code = plist[pi], shA = code & 0xff, shB = (code >> 8) & 0xff;
+    const int atA = bs.sh_atom[shA], atB = bs.sh_atom[shB];
+    const int p0a = bs.sh_p0[shA], npa = bs.sh_np[shA], p0b = bs.sh_p0[shB], npb = bs.sh_np[shB];
+    const int a0 = bs.sh_ao0[shA], b0 = bs.sh_ao0[shB];
+    double A[3], B[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { A[d] = Rc[3 * atA + d]; B[d] = Rc[3 * atB + d]; }
+    int gs = 1;
+    while (gs < 32 && gs < npa * npb) gs <<= 1;
+    const int ngrp = 32 / gs, grp = lane / gs, lig = lane - grp * gs;
+    for (int slot0 = 0; slot0 < nslot; slot0 += ngrp) {
+      const int slot = slot0 + grp;
+      double acc[NC][8];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[c][k] = 0.0;
+      if (slot < natm) {
+        const double Cc[3] = {Rc[3 * slot], Rc[3 * slot + 1], Rc[3 * slot + 2]};
+        slot1e<LA, LB, true>(bs, A, B, Cc, p0a, npa, p0b, npb, lig, gs, acc);
+      } else if (slot == natm) {
+        slot1e<LA, LB, false>(bs, A, B, nullptr, p0a, npa, p0b, npb, lig, gs, acc);
+      }
+      for (int o = gs >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[c][k] += __shfl_xor_sync(0xffffffffu, acc[c][k], o);
+      }
+      if (lig == 0 && slot < nslot) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) buf[(slot * NC + c) * 8 + k] = acc[c][k];
+      }
+    }
+    __syncwarp();
+    // assemble: buf[C][c][0] = rinv value, [1..3] = d/dA; buf[natm][c][0] = S, [1..3] = dS/dA, [4] = T, [5..7] = dT/dA
+    for (int c = lane; c < NC; c += 32) {
+      const int ia = c / NB, ib = c - ia * NB;
+      const int64_t ab = static_cast<int64_t>(a0 + ia) * n + (b0 + ib);
+      const double* st = buf + (natm * NC + c) * 8;
+      double vsum = 0.0;
+      for (int C = 0; C < natm; ++C) vsum += bs.charges[C] * buf[(C * NC + c) * 8];
+      out.ovlp[static_cast<int64_t>(g) * n2 + ab] = st[0];
+      out.hcore[static_cast<int64_t>(g) * n2 + ab] = st[4] - vsum;
+      for (int d = 0; d < 3; ++d) out.ipovlp[(static_cast<int64_t>(g) * 3 + d) * n2 + ab] = -st[1 + d];
+    }
+    // v[C][x][a][b] = -Z_C iprinv^C[x][a][b] - [atom(a) == C] (ipkin + ipnuc)[x][a][b],
+    //   iprinv^C = -d/dA rinv^C,  ipkin = -dT/dA,  ipnuc = +sum_C Z_C d/dA rinv^C
+    for (int it = lane; it < NC * natm * 3; it += 32) {
+      const int c = it / (natm * 3), r = it - c * natm * 3, C = r / 3, d = r - 3 * C;
+      const int ia = c / NB, ib = c - ia * NB;
+      const int64_t ab = static_cast<int64_t>(a0 + ia) * n + (b0 + ib);
+      double v = bs.charges[C] * buf[(C * NC + c) * 8 + 1 + d];
+      if (C == atA) {
+        double nsum = 0.0;
+        for (int C2 = 0; C2 < natm; ++C2) nsum += bs.charges[C2] * buf[(C2 * NC + c) * 8 + 1 + d];
+        v -= -buf[(natm * NC + c) * 8 + 5 + d] + nsum;
+      }
+      out.vtmp[((static_cast<int64_t>(g) * natm + C) * 3 + d) * n2 + ab] = v;
+    }
+    __syncwarp();
+  }
+}
+
+template <int LA, int LB>
+int launch_1e(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* plist, int npairs, const double* coords,
+              const GOut& o) {
+  if (npairs <= 0) return 0;
+  constexpr int nw = k1eThreads / 32, NC = (LA ? 3 : 1) * (LB ? 3 : 1);
+  const size_t smem = static_cast<size_t>(nw) * (kGMaxAtoms + 1) * NC * 8 * sizeof(double);
+  auto kern = gint1e_class_kernel<LA, LB>;
+  EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const long long want = (npairs + nw - 1) / nw, cap = std::max(1LL, 8LL * sm_count / nbatch);
+  const int split = static_cast<int>(std::max(1LL, std::min(want, cap)));
+  kern<<<dim3(split, nbatch), k1eThreads, smem, st>>>(v, plist, npairs, coords, o);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+#endif  // EVC_GCLASS_PART == 5
+
 }  // namespace
 
 #define EVC_ARGS st, sm_count, nbatch, v, cq
@@ -431,6 +688,7 @@ int launch_gclass_part0(cudaStream_t st, int sm_count, int nbatch, const GView& 
   if ((rc = launch_one<1, 1, 0, 0, 0, 0>(EVC_ARGS, EVC_UNITS(2)))) return rc;
   return launch_one<1, 0, 1, 0, 0, 0>(EVC_ARGS, EVC_UNITS(3));
 }
+
 #elif EVC_GCLASS_PART == 1
 int launch_gclass_part1(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o) {
@@ -438,6 +696,16 @@ int launch_gclass_part1(cudaStream_t st, int sm_count, int nbatch, const GView& 
   if ((rc = launch_one<1, 1, 1, 0, 0, 0>(EVC_ARGS, EVC_UNITS(4)))) return rc;
   if ((rc = launch_one<1, 1, 1, 0, 1, 0>(EVC_ARGS, EVC_UNITS(4)))) return rc;
   return launch_one<1, 1, 1, 0, 2, 0>(EVC_ARGS, EVC_UNITS(4));
+}
+#elif EVC_GCLASS_PART == 5
+// one-electron classes: plist holds the ordered shell pairs of (s|s), (p|s), (s|p), (p|p) back to back
+int launch_g1e(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* plist, const int* p_off,
+               const double* coords, const GOut& o) {
+  int rc;
+  if ((rc = launch_1e<0, 0>(st, sm_count, nbatch, v, plist + p_off[0], p_off[1] - p_off[0], coords, o))) return rc;
+  if ((rc = launch_1e<1, 0>(st, sm_count, nbatch, v, plist + p_off[1], p_off[2] - p_off[1], coords, o))) return rc;
+  if ((rc = launch_1e<0, 1>(st, sm_count, nbatch, v, plist + p_off[2], p_off[3] - p_off[2], coords, o))) return rc;
+  return launch_1e<1, 1>(st, sm_count, nbatch, v, plist + p_off[3], p_off[4] - p_off[3], coords, o);
 }
 #else
 #define EVC_PPPP(N, JBV)                                                                                                 \

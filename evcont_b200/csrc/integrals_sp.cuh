@@ -31,6 +31,8 @@ struct GOut {
 // 2..4: pppp with the component of the second function fixed) for the unit lists of the basis
 int launch_gclass_part0(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o);
+int launch_g1e(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* plist, const int* p_off,
+               const double* coords, const GOut& o);
 int launch_gclass_part1(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o);
 int launch_gclass_part2(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
@@ -47,6 +49,8 @@ struct evc_gbasis {
   int32_t *ao_atom, *ao_pow, *ao_poff, *aoslices;  // ao_pow: [nao][3]
   int32_t *sh_atom, *sh_ao0, *sh_p0, *sh_np;       // shells (s: one AO, p: three consecutive AOs)
   int32_t *cq, *cunits;                            // shell-quartet work lists of the class kernels
+  int32_t *plist;                                  // ordered shell pairs of the one-electron classes
+  int p_off[5];
   int cq_off[evc_gint::kGClasses + 1], cunit_off[evc_gint::kGClasses + 1];
   double *prim_exp, *prim_wt, *charges, *boys;
 };
