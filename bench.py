@@ -346,6 +346,63 @@ def run_coords_leg(args, eng, stack, timed, world, rank, torch):
                                    "peak_source": "64 DFMA lanes/clk/SM x SMs x 1.965 GHz (tools/fp64_latency.cu)"}}
 
 
+
+def run_sp_legs(args, eng, timed, world, rank, torch):
+    """The same from-coordinates MD step for the s+p configurations of BASELINE.json (configs[2] and
+    configs[4]): water / 6-31G (13 orbitals, 10 training states, full layout) and the Zundel cation
+    H5O2+ / 6-31G (28 orbitals, 20 training states, layout (N(N+1)/2, n^2(n^2+1)/2)), synthetic stacks,
+    geometries = reference geometry + N(0, 0.05 bohr).  Integrals by evc_ao_integrals_sp (K9g)."""
+    from evcont_b200.engine import DeviceAO, DeviceStack
+    ang = 1.0 / 0.52917721092
+    r, th = 0.9572 * ang, np.deg2rad(104.52)
+    water = (["O", "H", "H"], np.array([[0, 0, 0], [r * np.sin(th / 2), 0, r * np.cos(th / 2)],
+                                        [-r * np.sin(th / 2), 0, r * np.cos(th / 2)]]), 10, 6, 1024)
+    zundel = (["O", "O", "H", "H", "H", "H", "H"],
+              np.array([[-2.25, 0, 0], [2.25, 0, 0], [0, 0.1, 0], [-2.9, 1.45, 0.3], [-2.9, -1.45, -0.3],
+                        [2.9, 0.3, 1.45], [2.9, -0.3, -1.45]], dtype=float), 20, 2, 64)
+    out = {}
+    K = max(2, min(args.steps, 10))
+    for name, (sym, base, N, layout, G) in (("h2o_6-31g", water), ("zundel_6-31g", zundel)):
+        sb = eng.sbasis(sym, "6-31g")
+        natm, n = len(sym), sb.nao
+        g = torch.Generator(device=eng.device)
+        g.manual_seed(11)
+        n2 = n * n
+        L = n2 * n2 if layout == 6 else n2 * (n2 + 1) // 2
+        P = N * N if layout == 6 else N * (N + 1) // 2
+        two = torch.randn(P, L, generator=g, dtype=torch.float64, device=eng.device)
+        one = torch.randn(N, N, n, n, generator=g, dtype=torch.float64, device=eng.device)
+        b = torch.randn(N, N, generator=g, dtype=torch.float64, device=eng.device)
+        S = torch.eye(N, dtype=torch.float64, device=eng.device) + 0.01 * (b + b.T)
+        stack = DeviceStack(S, one, two.reshape((N, N, n, n, n, n) if layout == 6 else (P, L)), engine=eng, norb=n)
+        rng = np.random.default_rng(7000 + rank)
+        co_h = torch.from_numpy(base[None] + 0.05 * rng.standard_normal((G,) + base.shape)).pin_memory()
+        co_d = eng.empty(G, natm, 3)
+        ao = DeviceAO(eng, G, n, natm, sb.aoslices_host)
+        res = (eng.empty(G), eng.empty(G, natm, 3), eng.empty(G, N))
+        E_h = torch.empty(G, dtype=torch.float64).pin_memory()
+        g_h = torch.empty(G, natm, 3, dtype=torch.float64).pin_memory()
+
+        def step(_i):
+            co_d.copy_(co_h, non_blocking=True)
+            eng.energy_with_grad_coords(stack, sb, co_d, ao=ao, out=res)
+            E_h.copy_(res[0], non_blocking=True)
+            g_h.copy_(res[1], non_blocking=True)
+
+        for i in range(3):
+            step(i)
+        ms = timed(step, K)
+        ints_ms = timed(lambda i: eng.ao_integrals(sb, co_d, out=ao), K) / K
+        out[name] = {"value": world * G * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+                     "geometries_per_step_per_gpu": G, "norb": n, "natm": natm, "ntrain": N, "layout": layout,
+                     "integrals_ms_per_step": ints_ms, "integrals_geometries_per_s": G / (ints_ms * 1e-3),
+                     "h2d_bytes_per_step": int(co_h.numel() * 8),
+                     "d2h_bytes_per_step": int((E_h.numel() + g_h.numel()) * 8)}
+        del stack, two, one, ao
+        torch.cuda.empty_cache()
+    return out
+
+
 def measure_dgemm_peak(torch, dev):
     m = 6144
     a = torch.randn(m, m, dtype=torch.float64, device=dev)
@@ -494,9 +551,10 @@ def run_b200(args):
         step_e2e(i)
     e2e_ms = timed(step_e2e, K)
     # ---- the same step from nuclear coordinates only (K9: AO integrals on the device) ----
-    coords_leg = None
+    coords_leg, sp_legs = None, None
     if not args.no_coords:
         coords_leg = run_coords_leg(args, eng, stack, timed, world, rank, torch)
+        sp_legs = run_sp_legs(args, eng, timed, world, rank, torch)
     t1 = time.time()
     clocks = sampler.stop(window=(t0, t1)) if rank == 0 else None
     value = world * G * K / (total_ms * 1e-3)
@@ -560,6 +618,7 @@ def run_b200(args):
         "roofline": roofline, "trans_rdm12": trdm, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "fp64_dgemm_tflops": dgemm_tf,
         "from_coordinates": coords_leg,
+        "from_coordinates_sp": sp_legs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -307,14 +307,22 @@ __device__ __forceinline__ void class_prim_loop(const GView& bs, const ShellQ& s
   }
 }
 
+// 128-thread CTAs, EVC_GCLASS_MINB CTAs per SM.  At 2 the p classes take ~255 registers without spilling
+// (8 warps per SM; ncu: "wait" is the top stall, the FP64 pipe waits on its own dependent latency); at 3
+// (168 registers, 12 warps) they spill 200-900 bytes per thread and run at the same speed (measured).
+constexpr int kCThreads = 128;
+#ifndef EVC_GCLASS_MINB
+#define EVC_GCLASS_MINB 2
+#endif
+
 template <int LA, int LB, int LC, int LD, int JB, int JC>
-__global__ void __launch_bounds__(kGThreads)
+__global__ void __launch_bounds__(kCThreads, EVC_GCLASS_MINB)
 gint2e_class_kernel(GView bs, const int32_t* __restrict__ qlist, const int32_t* __restrict__ units, int nunits,
                     const double* __restrict__ coords, GOut out) {
   using CI = ClassInfo<LA, LB, LC, LD>;
   const int n = bs.nao, natm = bs.natm;
   const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NW = kGThreads / 32;
+  constexpr int NW = kCThreads / 32;
   const double* Rc = coords + static_cast<int64_t>(g) * natm * 3;
   const int64_t n2 = static_cast<int64_t>(n) * n, n3 = n2 * n, n4 = n2 * n2;
   double* eri = out.eri + static_cast<int64_t>(g) * n4;
@@ -410,11 +418,11 @@ template <int LA, int LB, int LC, int LD, int JB, int JC>
 int launch_one(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits, int nun,
                const double* coords, const GOut& o) {
   if (nun <= 0) return 0;
-  constexpr int nw = kGThreads / 32;
+  constexpr int nw = kCThreads / 32;
   // CTAs sized so that the grid covers the device a few times over
-  const long long want = (nun + nw - 1) / nw, cap = std::max(1LL, 8LL * sm_count / nbatch);
+  const long long want = (nun + nw - 1) / nw, cap = std::max(1LL, 16LL * sm_count / nbatch);
   const int split = static_cast<int>(std::max(1LL, std::min(want, cap)));
-  gint2e_class_kernel<LA, LB, LC, LD, JB, JC><<<dim3(split, nbatch), kGThreads, 0, st>>>(v, cq, cunits, nun, coords, o);
+  gint2e_class_kernel<LA, LB, LC, LD, JB, JC><<<dim3(split, nbatch), kCThreads, 0, st>>>(v, cq, cunits, nun, coords, o);
   EVC_CHECK_LAUNCH();
   return 0;
 }
