@@ -477,7 +477,7 @@ def run_b200(args):
 
     def build_once(_i=0):
         if world > 1:
-            return evd.build_stack_sharded(vecs, n, NELEC, group=None, device=dev)
+            return evd.build_stack_sharded(vecs_d, n, NELEC, group=None, device=dev)
         ov, d1, d2 = eng.trans_rdm12_batch(vecs_d, pairs, n, NELEC)
         return ov, d1, d2
 

@@ -24,8 +24,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // doubles of shared memory per warp
-__host__ __device__ inline size_t lowest_warp_doubles(int N) {
-  return 2 * static_cast<size_t>(N) * (N + 1) + 10 * static_cast<size_t>(N) + 2;
+// shared-memory doubles of one problem: the CTA team keeps two N x (N+1) matrices (A, M), the warp team only M
+// (its first triangular product reads H from global memory, the second runs in place), so that 4096 problems of
+// N = 20 are resident at once (28 warps per SM x 5 KB) instead of running as two waves
+__host__ __device__ inline size_t lowest_warp_doubles(int N, bool warp_team = false) {
+  return (warp_team ? 1 : 2) * static_cast<size_t>(N) * (N + 1) + 10 * static_cast<size_t>(N) + 2;
 }
 
 template <int TEAM>
@@ -56,8 +59,8 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     return t;
   };
   const int ld = N + 1;
-  double* A = sm + (TEAM == 32 ? static_cast<size_t>(warp) * lowest_warp_doubles(N) : 0);
-  double* M = A + N * ld;
+  double* A = sm + (TEAM == 32 ? static_cast<size_t>(warp) * lowest_warp_doubles(N, true) : 0);
+  double* M = TEAM == 32 ? A : A + N * ld;
   double* d = M + N * ld;
   double* e = d + N;        // e[i] couples i and i+1
   double* tau = e + N;
@@ -69,39 +72,52 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
   double* du2 = du + N;
   int* ipiv = reinterpret_cast<int*>(du2 + N);  // N ints fit in N doubles
 
-  // ---- M <- lower triangle of H, mirrored ----
-  if (packed_lower) {
-    const double* Hb = H + static_cast<int64_t>(b) * (N * (N + 1) / 2);
-    for (int k = lane; k < N * N; k += TEAM) {
-      const int i = k / N, j = k - i * N;
-      const int hi = i > j ? i : j, lo = i > j ? j : i;
-      M[i * ld + j] = Hb[hi * (hi + 1) / 2 + lo];
-    }
-  } else {
-    const double* Hb = H + static_cast<int64_t>(b) * N * N;
-    for (int k = lane; k < N * N; k += TEAM) {
-      const int i = k / N, j = k - i * N;
-      M[i * ld + j] = (i >= j) ? Hb[i * N + j] : Hb[j * N + i];
-    }
-  }
-  team_sync();
-  if (TEAM == 32) {
-    // ---- A <- Linv M   (Linv lower triangular) ----
-    for (int k = lane; k < N * N; k += TEAM) {
-      const int i = k / N, j = k - i * N;
-      double acc = 0.0;
-      for (int r = 0; r <= i; ++r) acc += __ldg(Linv + i * N + r) * M[r * ld + j];
-      A[i * ld + j] = acc;
+  if (TEAM != 32) {
+    // ---- M <- lower triangle of H, mirrored ----
+    if (packed_lower) {
+      const double* Hb = H + static_cast<int64_t>(b) * (N * (N + 1) / 2);
+      for (int k = lane; k < N * N; k += TEAM) {
+        const int i = k / N, j = k - i * N;
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        M[i * ld + j] = Hb[hi * (hi + 1) / 2 + lo];
+      }
+    } else {
+      const double* Hb = H + static_cast<int64_t>(b) * N * N;
+      for (int k = lane; k < N * N; k += TEAM) {
+        const int i = k / N, j = k - i * N;
+        M[i * ld + j] = (i >= j) ? Hb[i * N + j] : Hb[j * N + i];
+      }
     }
     team_sync();
-    // ---- M <- A Linv^T, lower triangle computed and mirrored ----
+  }
+  if (TEAM == 32) {
+    // ---- M <- Linv Hsym   (Linv lower triangular; H read through L1 from its lower triangle) ----
+    const double* Hb = H + static_cast<int64_t>(b) * (packed_lower ? N * (N + 1) / 2 : N * N);
+    auto hsym = [&](int r, int c) {
+      const int hi = r > c ? r : c, lo = r > c ? c : r;
+      return __ldg(Hb + (packed_lower ? hi * (hi + 1) / 2 + lo : hi * N + lo));
+    };
     for (int k = lane; k < N * N; k += TEAM) {
       const int i = k / N, j = k - i * N;
-      if (j > i) continue;
       double acc = 0.0;
-      for (int r = 0; r <= j; ++r) acc += A[i * ld + r] * __ldg(Linv + j * N + r);
+      for (int r = 0; r <= i; ++r) acc += __ldg(Linv + i * N + r) * hsym(r, j);
       M[i * ld + j] = acc;
-      M[j * ld + i] = acc;
+    }
+    team_sync();
+    // ---- M <- M Linv^T in place: lanes own rows, j descends (entry j needs the old entries r <= j of its
+    //      row), lower triangle computed and mirrored ----
+    for (int i = lane; i < N; i += TEAM) {
+      double* row = M + i * ld;
+      for (int j = i; j >= 0; --j) {
+        double acc = 0.0;
+        for (int r = 0; r <= j; ++r) acc += row[r] * __ldg(Linv + j * N + r);
+        row[j] = acc;
+      }
+    }
+    team_sync();
+    for (int k = lane; k < N * N; k += TEAM) {
+      const int i = k / N, j = k - i * N;
+      if (j > i) M[i * ld + j] = M[j * ld + i];
     }
     team_sync();
   } else {
@@ -397,6 +413,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
 int evc_launch_geneig_lowest(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H,
                              const double* Linv, double* E, double* C) {
   const size_t per_warp = lowest_warp_doubles(N) * sizeof(double);
+  const size_t per_warp32 = lowest_warp_doubles(N, true) * sizeof(double);
   EVC_REQUIRE(per_warp <= ctx->smem_optin, "geneig: N=%d needs %zu bytes of shared memory", N, per_warp);
   if (nbatch <= 2 * ctx->sm_count) {
     // few geometries: one 256-thread CTA each
@@ -407,8 +424,8 @@ int evc_launch_geneig_lowest(evc_ctx* ctx, int nbatch, int N, int packed_lower, 
     return 0;
   }
   int wpc = 4;
-  while (wpc > 1 && (wpc * per_warp > ctx->smem_optin || wpc * per_warp > 48 * 1024)) wpc >>= 1;
-  const size_t smem = wpc * per_warp;
+  while (wpc > 1 && (wpc * per_warp32 > ctx->smem_optin || wpc * per_warp32 > 48 * 1024)) wpc >>= 1;
+  const size_t smem = wpc * per_warp32;
   EVC_CHECK_CUDA(cudaFuncSetAttribute(geneig_lowest_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
   geneig_lowest_kernel<32><<<(nbatch + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(N, packed_lower, nbatch, H, Linv,

@@ -71,7 +71,8 @@ def build_stack_sharded(civecs, norb, nelec, pair_fn=None, group=None, device=No
     untransposed like the reference (evcont/FCI_EVCont.py:124-127).
     """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    civecs = np.asarray(civecs, dtype=np.float64)
+    if not isinstance(civecs, torch.Tensor):   # device tensors stay where they are (no re-upload per build)
+        civecs = np.asarray(civecs, dtype=np.float64)
     N, n = civecs.shape[0], int(norb)
     pairs = tril_pairs(N)
     lo, hi = shard_range(len(pairs), rank, world)
