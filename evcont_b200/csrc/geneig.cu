@@ -31,6 +31,13 @@ __host__ __device__ inline size_t lowest_warp_doubles(int N, bool warp_team = fa
   return (warp_team ? 1 : 2) * static_cast<size_t>(N) * (N + 1) + 10 * static_cast<size_t>(N) + 2;
 }
 
+#ifdef EVC_PHASE_TIMING
+__device__ long long g_geneig_phase[16];
+#define GEN_MARK(idx) do { if (TEAM == 32 && blockIdx.x == 0 && threadIdx.x == 0) g_geneig_phase[idx] = clock64(); } while (0)
+#else
+#define GEN_MARK(idx) do { } while (0)
+#endif
+
 template <int TEAM>
 __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM)
 geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restrict__ H,
@@ -72,6 +79,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
   double* du2 = du + N;
   int* ipiv = reinterpret_cast<int*>(du2 + N);  // N ints fit in N doubles
 
+  GEN_MARK(0);
   if (TEAM != 32) {
     // ---- M <- lower triangle of H, mirrored ----
     if (packed_lower) {
@@ -91,27 +99,58 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     team_sync();
   }
   if (TEAM == 32) {
-    // ---- M <- Linv Hsym   (Linv lower triangular; H read through L1 from its lower triangle) ----
-    const double* Hb = H + static_cast<int64_t>(b) * (packed_lower ? N * (N + 1) / 2 : N * N);
-    auto hsym = [&](int r, int c) {
-      const int hi = r > c ? r : c, lo = r > c ? c : r;
-      return __ldg(Hb + (packed_lower ? hi * (hi + 1) / 2 + lo : hi * N + lo));
-    };
-    for (int k = lane; k < N * N; k += TEAM) {
-      const int i = k / N, j = k - i * N;
-      double acc = 0.0;
-      for (int r = 0; r <= i; ++r) acc += __ldg(Linv + i * N + r) * hsym(r, j);
-      M[i * ld + j] = acc;
+    // ---- M <- lower triangle of H, mirrored ----
+    {
+      const double* Hb = H + static_cast<int64_t>(b) * (packed_lower ? N * (N + 1) / 2 : N * N);
+      for (int k = lane; k < N * N; k += TEAM) {
+        const int i = k / N, j = k - i * N;
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        M[i * ld + j] = __ldg(Hb + (packed_lower ? hi * (hi + 1) / 2 + lo : hi * N + lo));
+      }
     }
     team_sync();
-    // ---- M <- M Linv^T in place: lanes own rows, j descends (entry j needs the old entries r <= j of its
-    //      row), lower triangle computed and mirrored ----
-    for (int i = lane; i < N; i += TEAM) {
-      double* row = M + i * ld;
-      for (int j = i; j >= 0; --j) {
-        double acc = 0.0;
-        for (int r = 0; r <= j; ++r) acc += row[r] * __ldg(Linv + j * N + r);
-        row[j] = acc;
+    // Both triangular products run IN PLACE on the one matrix the warp keeps in shared memory, with the
+    // Linv element of every step uniform over the lanes (one broadcast load) and four independent partial
+    // sums per lane (the dependent FP64 latency, not the flop count, is what a lone warp waits for).
+    // ---- M <- Linv M: lanes own columns j, rows i descend (row i needs the old rows r <= i) ----
+    for (int j0 = 0; j0 < N; j0 += TEAM) {
+      const int j = j0 + lane;
+      for (int i = N - 1; i >= 0; --i) {
+        const double* li = Linv + i * N;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int r = 0;
+        if (j < N) {
+          for (; r + 3 <= i; r += 4) {
+            a0 = fma(__ldg(li + r), M[r * ld + j], a0);
+            a1 = fma(__ldg(li + r + 1), M[(r + 1) * ld + j], a1);
+            a2 = fma(__ldg(li + r + 2), M[(r + 2) * ld + j], a2);
+            a3 = fma(__ldg(li + r + 3), M[(r + 3) * ld + j], a3);
+          }
+          for (; r <= i; ++r) a0 = fma(__ldg(li + r), M[r * ld + j], a0);
+          M[i * ld + j] = (a0 + a1) + (a2 + a3);
+        }
+      }
+    }
+    team_sync();
+    // ---- M <- M Linv^T: lanes own rows i, columns j descend (entry j needs the old entries r <= j of the
+    //      row); only j <= i is kept, the upper triangle is mirrored so that M stays exactly symmetric ----
+    for (int i0 = 0; i0 < N; i0 += TEAM) {
+      const int i = i0 + lane;
+      double* row = M + (i < N ? i : 0) * ld;
+      for (int j = N - 1; j >= 0; --j) {
+        const double* lj = Linv + j * N;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int r = 0;
+        if (i < N && j <= i) {
+          for (; r + 3 <= j; r += 4) {
+            a0 = fma(row[r], __ldg(lj + r), a0);
+            a1 = fma(row[r + 1], __ldg(lj + r + 1), a1);
+            a2 = fma(row[r + 2], __ldg(lj + r + 2), a2);
+            a3 = fma(row[r + 3], __ldg(lj + r + 3), a3);
+          }
+          for (; r <= j; ++r) a0 = fma(row[r], __ldg(lj + r), a0);
+          row[j] = (a0 + a1) + (a2 + a3);
+        }
       }
     }
     team_sync();
@@ -150,6 +189,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     }
   }
 
+  GEN_MARK(1);
   // ---- Householder tridiagonalisation of M (both triangles kept up to date) ----
   for (int k = 0; k + 2 < N; ++k) {
     const int m = N - k - 1;
@@ -178,8 +218,16 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     if (TEAM == 32) {
       for (int i = lane; i < m; i += TEAM) {
         const double* row = M + (k + 1 + i) * ld + k + 1;
-        double acc = 0.0;
-        for (int j = 0; j < m; ++j) acc += row[j] * col[j * ld];
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        int j = 0;
+        for (; j + 3 < m; j += 4) {
+          c0 = fma(row[j], col[j * ld], c0);
+          c1 = fma(row[j + 1], col[(j + 1) * ld], c1);
+          c2 = fma(row[j + 2], col[(j + 2) * ld], c2);
+          c3 = fma(row[j + 3], col[(j + 3) * ld], c3);
+        }
+        for (; j < m; ++j) c0 = fma(row[j], col[j * ld], c0);
+        const double acc = (c0 + c1) + (c2 + c3);
         const double p = taup * acc;
         w1[i] = p;
         pu_part += p * col[i * ld];
@@ -215,6 +263,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
       for (int i = lane; i < m; i += TEAM) {
         double* row = M + (k + 1 + i) * ld + k + 1;
         const double ui = col[i * ld], qi = w1[i];
+#pragma unroll 4
         for (int j = 0; j < m; ++j) row[j] -= ui * w1[j] + qi * col[j * ld];
       }
     } else {
@@ -230,6 +279,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
   if (lane == 0 && N >= 2) e[N - 2] = M[(N - 1) * ld + N - 2];
   team_sync();
 
+  GEN_MARK(2);
   // ---- lowest eigenvalue of T = tridiag(e, d, e): multisection on Sturm counts (first warp) ----
   double lam = 0.0, tnorm = 0.0;
   if (TEAM == 32) {
@@ -256,14 +306,23 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     if (width <= 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) break;
     const double h = width / 33.0;
     const double xs = lo + (lane + 1) * h;
-    double q = d[0] - xs;
-    if (fabs(q) < pivmin) q = -pivmin;
-    int cnt = q < 0.0;
+    // Sturm count from the determinant recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (sign changes
+    // = eigenvalues below x): two dependent FMAs per row instead of the FP64 division of the quotient
+    // form, which is the longest dependent chain of this kernel; rescaled by 2^-+500 against over/underflow,
+    // an exact zero takes the sign opposite to its predecessor (as the -pivmin rule of the quotient form)
+    double pm = 1.0, pc = d[0] - xs;
+    if (pc == 0.0) pc = -1.0e-100;
+    int cnt = pc < 0.0;
     for (int i = 1; i < N; ++i) {
       const double ei = e[i - 1];
-      q = d[i] - xs - ei * ei / q;
-      if (fabs(q) < pivmin) q = -pivmin;
-      cnt += q < 0.0;
+      double pn = fma(d[i] - xs, pc, -(ei * ei) * pm);
+      if (pn == 0.0) pn = -pc * 1.0e-100;
+      cnt += (pn < 0.0) != (pc < 0.0);
+      pm = pc;
+      pc = pn;
+      const double mag = fabs(pc);
+      if (mag > 3.2733906078961419e150) { pc *= 3.0549363634996047e-151; pm *= 3.0549363634996047e-151; }        // 2^500, 2^-500
+      else if (mag < 3.0549363634996047e-151) { pc *= 3.2733906078961419e150; pm *= 3.2733906078961419e150; }
     }
     const unsigned ball = __ballot_sync(0xffffffffu, cnt >= 1);
     const int f = ball ? __ffs(ball) - 1 : 32;  // first sample point with an eigenvalue below it
@@ -322,6 +381,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     lam = 0.5 * (lo + hi);
   }
 
+  GEN_MARK(3);
   // ---- eigenvector of T by inverse iteration (lane 0; pivoted LU of T - lam I) ----
   if (lane == 0) {
     const double tiny = fmax(DBL_EPSILON * tnorm, DBL_MIN * 1e16);
@@ -387,6 +447,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
   }
   team_sync();
 
+  GEN_MARK(4);
   // ---- y = H_0 H_1 ... H_{N-3} z ----
   for (int k = N - 3; k >= 0; --k) {
     const double taup = tau[k];
@@ -399,6 +460,7 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     for (int i = lane; i < m; i += TEAM) z[k + 1 + i] -= s * col[i * ld];
     team_sync();
   }
+  GEN_MARK(5);
   // ---- c = Linv^T y ----
   double* Cb = C + static_cast<int64_t>(b) * N;
   for (int i = lane; i < N; i += TEAM) {
@@ -406,9 +468,17 @@ geneig_lowest_kernel(int N, int packed_lower, int nbatch, const double* __restri
     for (int r = i; r < N; ++r) acc += __ldg(Linv + r * N + i) * z[r];
     Cb[i] = acc;
   }
+  GEN_MARK(6);
 }
 
 }  // namespace
+
+#ifdef EVC_PHASE_TIMING
+extern "C" int evc_debug_geneig_clocks(long long* out_host) {   // development aid, not part of the ABI
+  EVC_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_geneig_phase, sizeof(long long) * 16));
+  return 0;
+}
+#endif
 
 int evc_launch_geneig_lowest(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H,
                              const double* Linv, double* E, double* C) {
