@@ -15,8 +15,9 @@ namespace {
 // =====================================================================================================
 // Class kernels: contracted SHELL quartets, everything in registers.
 //
-// The generic kernel above evaluates one contracted AO quartet at a time and keeps its Hermite tables in
-// per-thread local arrays (9 GB of local-memory DRAM traffic per Zundel launch, FP64 pipe 4 % active).
+// The first version of K9g evaluated one contracted AO quartet at a time and kept its Hermite tables in
+// per-thread local arrays (9 GB of local-memory DRAM traffic per Zundel launch, FP64 pipe 4 % active:
+// profiles/r01c_gint_sp_ncu_full.txt).
 // Here the work unit is a shell quartet in canonical class order (p shells first inside bra and ket, the
 // pair with more p shells as the bra): ssss, psss, ppss, psps, ppps, pppp.  Lanes of a group run over the
 // primitive quartets as before, but per primitive quartet the Boys values, the R table and all Hermite
@@ -269,13 +270,20 @@ __device__ __forceinline__ void class_prim_loop(const GView& bs, const ShellQ& s
                      (ctr[0][2] - ctr[1][2]) * (ctr[0][2] - ctr[1][2]);
   const double cd2 = (ctr[2][0] - ctr[3][0]) * (ctr[2][0] - ctr[3][0]) + (ctr[2][1] - ctr[3][1]) * (ctr[2][1] - ctr[3][1]) +
                      (ctr[2][2] - ctr[3][2]) * (ctr[2][2] - ctr[3][2]);
+  // mixed-radix decode of the primitive index without integer division: (r + 1/2) / np in single precision is
+  // exact for r < 2^16 (at most 16 primitives per shell)
+  const float inv3 = 1.0f / static_cast<float>(sq.np[3]), inv2 = 1.0f / static_cast<float>(sq.np[2]),
+              inv1 = 1.0f / static_cast<float>(sq.np[1]);
 #pragma unroll 1
   for (int t = lig; t < tot; t += gs) {
     int r = t;
-    const int il = r % sq.np[3]; r /= sq.np[3];
-    const int ik = r % sq.np[2]; r /= sq.np[2];
-    const int ij = r % sq.np[1]; r /= sq.np[1];
-    const int ii = r;
+    int qd = __float2int_rz((static_cast<float>(r) + 0.5f) * inv3);
+    const int il = r - qd * sq.np[3]; r = qd;
+    qd = __float2int_rz((static_cast<float>(r) + 0.5f) * inv2);
+    const int ik = r - qd * sq.np[2]; r = qd;
+    qd = __float2int_rz((static_cast<float>(r) + 0.5f) * inv1);
+    const int ij = r - qd * sq.np[1];
+    const int ii = qd;
     const double ea = __ldg(bs.prim_exp + sq.p0[0] + ii), eb = __ldg(bs.prim_exp + sq.p0[1] + ij),
                  ec = __ldg(bs.prim_exp + sq.p0[2] + ik), ed = __ldg(bs.prim_exp + sq.p0[3] + il);
     const double w4 = __ldg(bs.prim_wt + sq.p0[0] + ii) * __ldg(bs.prim_wt + sq.p0[1] + ij) *
