@@ -91,8 +91,8 @@ def predict_energies(init_mol, geometries, one_rdm, two_rdm, overlap):
     stack = as_device_stack(one_rdm, two_rdm, overlap)
     eng = stack.engine
     geometries = np.ascontiguousarray(geometries, dtype=np.float64).reshape(-1, init_mol.natm, 3)
-    out = eng.energy_with_grad_coords(stack, init_mol.sbasis(eng), geometries)
-    return out[0].cpu().numpy()
+    ao = eng.ao_integrals(init_mol.sbasis(eng), geometries)
+    return eng.energies(stack, ao)[0].cpu().numpy()   # energies only: no predicted RDMs, no gradient kernels
 
 
 def oao_hamiltonian_rows(init_mol, geometries):

@@ -1061,9 +1061,13 @@ int evc_energy_with_grad_packed_workspace_bytes(int N, int n, int natm, int nbat
 int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const double* RH, const double* RG,
                                 const double* Linv, int nbatch, const evc_ao_bundle* ao, double* E,
                                 double* grad, double* Cvec, void* workspace, size_t workspace_bytes) {
-  EVC_REQUIRE(ctx && RH && RG && Linv && ao && E && grad && workspace, "evc_energy_with_grad_packed: NULL argument");
-  EVC_REQUIRE(ao->ovlp && ao->hcore && ao->eri && ao->ipovlp && ao->hcore_deriv && ao->eri_ip1 && ao->aoslices,
-              "evc_energy_with_grad_packed: incomplete AO bundle");
+  EVC_REQUIRE(ctx && RH && RG && Linv && ao && E && workspace, "evc_energy_with_grad_packed: NULL argument");
+  // grad == NULL: energies (and Cvec) only -- the approximate_ground_state_OAO part of the step (K3, K4, K5, K6),
+  // evcont/ab_initio_eigenvector_continuation.py:178-211; the derivative arrays of the bundle are not read
+  const bool want_grad = grad != nullptr;
+  EVC_REQUIRE(ao->ovlp && ao->hcore && ao->eri, "evc_energy_with_grad_packed: incomplete AO bundle");
+  EVC_REQUIRE(!want_grad || (ao->ipovlp && ao->hcore_deriv && ao->eri_ip1 && ao->aoslices),
+              "evc_energy_with_grad_packed: incomplete AO bundle (derivative arrays)");
   EVC_REQUIRE(n >= 1 && n <= 32 && N >= 1 && N <= 112, "evc_energy_with_grad_packed: n=%d N=%d unsupported", n, N);
   if (nbatch <= 0) return 0;
   const size_t G = static_cast<size_t>(nbatch);
@@ -1124,21 +1128,23 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
   if ((rc = evc_rows_dot(ctx, RH, L8, P, hvec, nbatch, Hp, dot_ws, dot_b))) return rc;
   if ((rc = evc_stage_mark(ctx, EVC_STAGE_GENEIG))) return rc;
   if ((rc = evc_launch_geneig(ctx, nbatch, N, 1, Hp, Linv, 1, E0, C))) return rc;
-  if ((rc = evc_stage_mark(ctx, EVC_STAGE_PREDICT))) return rc;
-  if ((rc = evc_packed_pair_weights(ctx, nbatch, N, C, N, w))) return rc;
-  if ((rc = evc_rows_axpy(ctx, RG, L8, P, w, nbatch, out7, axpy_ws, axpy_b))) return rc;
-  if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD))) return rc;
-  if (small) {
-    if ((rc = evc_packed_grad(ctx, nbatch, n, natm, ao->aoslices, X, evals, evecs, ao->hcore, T, out7, ao->ipovlp,
-                              ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, Wg, OmS, Pao, grad)))
-      return rc;
-  } else {
-    if ((rc = evc_packed_unpack_rdms(ctx, nbatch, n, out7, gamma, Gamma8))) return rc;
-    if ((rc = evc_grad_elec_full(ctx, nbatch, n, natm, ao->aoslices, evals, evecs, X, ao->hcore, t3, gamma, Gamma8,
-                                 ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b, 1)))
-      return rc;
+  if (want_grad) {
+    if ((rc = evc_stage_mark(ctx, EVC_STAGE_PREDICT))) return rc;
+    if ((rc = evc_packed_pair_weights(ctx, nbatch, N, C, N, w))) return rc;
+    if ((rc = evc_rows_axpy(ctx, RG, L8, P, w, nbatch, out7, axpy_ws, axpy_b))) return rc;
+    if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD))) return rc;
+    if (small) {
+      if ((rc = evc_packed_grad(ctx, nbatch, n, natm, ao->aoslices, X, evals, evecs, ao->hcore, T, out7, ao->ipovlp,
+                                ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, Wg, OmS, Pao, grad)))
+        return rc;
+    } else {
+      if ((rc = evc_packed_unpack_rdms(ctx, nbatch, n, out7, gamma, Gamma8))) return rc;
+      if ((rc = evc_grad_elec_full(ctx, nbatch, n, natm, ao->aoslices, evals, evecs, X, ao->hcore, t3, gamma, Gamma8,
+                                   ao->ipovlp, ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, grad, grad_ws, grad_b, 1)))
+        return rc;
+    }
+    if (!small && (rc = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM))) return rc;
   }
-  if (!small && (rc = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM))) return rc;
   add_enuc_kernel_p<<<(nbatch + 127) / 128, 128, 0, ctx->stream>>>(nbatch, E0, ao->e_nuc, E);
   EVC_CHECK_LAUNCH();
   return evc_stage_mark(ctx, EVC_NSTAGE);

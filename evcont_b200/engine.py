@@ -314,6 +314,24 @@ class Engine:
         ao = self.ao_integrals(sbasis, coords, out=ao)
         return self.energy_with_grad(stack, ao, want_rdms=want_rdms, out=out)
 
+    def energies(self, stack, ao, out=None):
+        """Continuation energies only (K3, K4, K5, K6: ``approximate_ground_state_OAO`` for a batch): the packed
+        step with ``grad = NULL``.  Returns ``(E[G], cvec[G, N])``."""
+        G, n, natm, N = ao.nbatch, ao.nao, ao.natm, stack.ntrain
+        if n != stack.norb:
+            raise ValueError(f"mol.nao={n} does not match the stack's norb={stack.norb}")
+        E, cvec = (self.empty(G), self.empty(G, N)) if out is None else out
+        rh, rg = stack.packed()
+        nbytes = C.c_size_t()
+        check(self.lib.evc_energy_with_grad_packed_workspace_bytes(N, n, natm, G, C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        bundle = ao.bundle()
+        check(self.lib.evc_energy_with_grad_packed(
+            self._ctx, N, n, natm, _ptr(rh), _ptr(rg), _ptr(stack.linv), G, C.byref(bundle),
+            _ptr(E), None, _ptr(cvec), _ptr(ws), ws.numel()))
+        return E, cvec
+
     # -- device-resident velocity Verlet ------------------------------------------------------
     def md_positions(self, dt, x, v, a):
         G, natm = x.shape[0], x.shape[1]

@@ -239,7 +239,10 @@ int evc_energy_with_grad(evc_ctx *ctx, int layout, int ntrain, int n, int natm,
  *   -> Hp = hvec . RH -> eigensolve -> out7 = w . RG -> gradient (three DMMA GEMMs
  *   per geometry in shared memory, int2e_ip1 streamed once).  Same outputs as
  *   evc_energy_with_grad (E, grad, optional Cvec); the full predicted RDMs are not
- *   formed -- use evc_energy_with_grad when they are wanted. */
+ *   formed -- use evc_energy_with_grad when they are wanted.  grad == NULL: energies (and
+ *   Cvec) only, i.e. approximate_ground_state_OAO for a batch
+ *   (ab_initio_eigenvector_continuation.py:178-211); the derivative arrays of the bundle
+ *   are not read then. */
 int64_t evc_packed_row_len(int n);
 int evc_stack_pack8(evc_ctx *ctx, int layout, int ntrain, int n, const double *one_rdm,
                     const double *two_rdm, double *RH, double *RG);

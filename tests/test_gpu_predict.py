@@ -311,3 +311,22 @@ def test_host_buffer_pipeline(G, chunk):
         assert abs(E[k] - oe) < E_TOL and np.abs(grad[k] - ogr).max() < F_TOL
     E2, grad2 = eng.energy_with_grad_host(stack, host, chunk=chunk)
     assert np.array_equal(E, E2.numpy()) and np.array_equal(grad, grad2.numpy())
+
+
+def test_energy_only_mode_matches_the_full_step():
+    """``evc_energy_with_grad_packed`` with grad = NULL (approximate_ground_state_OAO for a batch)."""
+    from evcont_b200.engine import DeviceAO, DeviceStack, get_engine
+    from evcont_b200.mol import ao_bundle, synthetic_mol
+    eng = get_engine()
+    for norb, natm, ntrain in ((6, 6, 3), (10, 10, 7), (15, 4, 4)):
+        rng = np.random.default_rng(norb)
+        b = rng.standard_normal((ntrain, ntrain))
+        S = np.eye(ntrain) + 0.01 * (b + b.T)
+        one = rng.standard_normal((ntrain, ntrain, norb, norb))
+        two = rng.standard_normal((ntrain, ntrain) + (norb,) * 4)
+        stack = DeviceStack(S, one, two, engine=eng, norb=norb)
+        ao = DeviceAO.from_bundles(eng, [ao_bundle(synthetic_mol(norb, natm, seed=70 + k)) for k in range(5)])
+        E, _, _, _, cvec = eng.energy_with_grad(stack, ao)
+        E2, c2 = eng.energies(stack, ao)
+        assert np.array_equal(E.cpu().numpy(), E2.cpu().numpy())
+        assert np.array_equal(cvec.cpu().numpy(), c2.cpu().numpy())
