@@ -21,6 +21,9 @@ import torch
 import torch.distributed as dist
 
 
+_SCATTER_INDEX = {}   # (ntrain, world, device) -> (row, column) block indices of the gathered rows
+
+
 def tril_pairs(ntrain):
     """Pairs (a, b) with a >= b in ``np.tril_indices`` order."""
     return [(a, b) for a in range(ntrain) for b in range(a + 1)]
@@ -82,29 +85,40 @@ def build_stack_sharded(civecs, norb, nelec, pair_fn=None, group=None, device=No
 
         def pair_fn(vecs, plist):
             return eng.trans_rdm12_batch(vecs, plist, n, nelec)
-    mine = pairs[lo:hi]
-    n2 = n * n
-    width = 1 + n2 + n2 * n2
-    if mine:
-        ovlp, dm1, dm2 = pair_fn(civecs, mine)
-        local = torch.cat([ovlp.reshape(-1, 1), dm1.reshape(-1, n2), dm2.reshape(-1, n2 * n2)], dim=1)
-    else:
-        like = pair_fn(civecs, pairs[:1])[0]
-        local = like.new_empty((0, width))
-    rows = _all_gather_rows(local.contiguous(), len(pairs), group=group)
-    overlap = rows.new_empty((N, N))
-    one = rows.new_empty((N, N, n, n))
-    two = rows.new_empty((N, N, n, n, n, n))
-    ia = torch.tensor([p[0] for p in pairs], device=rows.device)
-    ib = torch.tensor([p[1] for p in pairs], device=rows.device)
-    overlap[ia, ib] = rows[:, 0]
-    overlap[ib, ia] = rows[:, 0]
-    d1 = rows[:, 1:1 + n2].reshape(-1, n, n)
-    d2 = rows[:, 1 + n2:].reshape(-1, n, n, n, n)
-    one[ia, ib] = d1
-    one[ib, ia] = d1
-    two[ia, ib] = d2
-    two[ib, ia] = d2
+    # Every rank computes exactly `slab` pairs -- its share, padded with repeats of pairs[0] -- so that the kernel
+    # outputs ARE the equally sized send buffers of the all_gather (no concatenation / zero-fill copies), and the
+    # gathered rows scatter straight into the (N, N, ...) layout: the padding rows rewrite block [0, 0] with the
+    # value it already has.
+    slab = slab_size(len(pairs), world)
+    padded = pairs[lo:hi] + [pairs[0]] * (slab - (hi - lo))
+    ovlp, dm1, dm2 = pair_fn(civecs, padded)
+    ovlp, dm1, dm2 = ovlp.reshape(slab).contiguous(), dm1.reshape(slab, n, n).contiguous(), \
+        dm2.reshape(slab, n, n, n, n).contiguous()
+    g_ov = ovlp.new_empty((world * slab,))
+    g_d1 = dm1.new_empty((world * slab, n, n))
+    g_d2 = dm2.new_empty((world * slab, n, n, n, n))
+    dist.all_gather_into_tensor(g_d2, dm2, group=group)
+    dist.all_gather_into_tensor(g_d1, dm1, group=group)
+    dist.all_gather_into_tensor(g_ov, ovlp, group=group)
+    key = (N, world, str(g_ov.device))
+    if key not in _SCATTER_INDEX:
+        ia, ib = [], []
+        for r in range(world):
+            rlo, rhi = shard_range(len(pairs), r, world)
+            rows = pairs[rlo:rhi] + [pairs[0]] * (slab - (rhi - rlo))
+            ia += [p[0] for p in rows]
+            ib += [p[1] for p in rows]
+        _SCATTER_INDEX[key] = (torch.tensor(ia, device=g_ov.device), torch.tensor(ib, device=g_ov.device))
+    ia, ib = _SCATTER_INDEX[key]
+    overlap = g_ov.new_empty((N, N))
+    one = g_ov.new_empty((N, N, n, n))
+    two = g_ov.new_empty((N, N, n, n, n, n))
+    overlap[ia, ib] = g_ov
+    overlap[ib, ia] = g_ov
+    one[ia, ib] = g_d1
+    one[ib, ia] = g_d1
+    two[ia, ib] = g_d2
+    two[ib, ia] = g_d2
     return overlap, one, two
 
 

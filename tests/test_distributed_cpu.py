@@ -41,8 +41,9 @@ def _worker(rank, world, port, ntrain, out_dir):
     S, one, two = evd.build_stack_sharded(vecs, norb, nelec, pair_fn=pair_fn)
     npairs = ntrain * (ntrain + 1) // 2
     lo, hi = evd.shard_range(npairs, rank, world)
-    if hi > lo:
-        assert calls[0] == evd.tril_pairs(ntrain)[lo:hi]
+    # the rank's share first, padded to the common slab size with repeats of the first pair
+    slab = evd.slab_size(npairs, world)
+    assert calls[0] == evd.tril_pairs(ntrain)[lo:hi] + [evd.tril_pairs(ntrain)[0]] * (slab - (hi - lo))
     idx = evd.shard_geometries(7, rank, world)
     E = torch.from_numpy(idx.astype(np.float64))
     G = E.reshape(-1, 1, 1).expand(-1, 3, 3).contiguous()
