@@ -557,7 +557,12 @@ def run_b200(args):
     coords_leg, sp_legs = None, None
     if not args.no_coords:
         coords_leg = run_coords_leg(args, eng, stack, timed, world, rank, torch)
-        sp_legs = run_sp_legs(args, eng, timed, world, rank, torch)
+        try:   # extra legs (other BASELINE configs): never let them take the headline line down
+            sp_legs = run_sp_legs(args, eng, timed, world, rank, torch)
+        except Exception as exc:  # noqa: BLE001 -- reported in the JSON line
+            if world > 1:
+                raise          # ranks must stay in step inside the collectives of timed()
+            sp_legs = {"error": f"{type(exc).__name__}: {exc}"}
     t1 = time.time()
     clocks = sampler.stop(window=(t0, t1)) if rank == 0 else None
     value = world * G * K / (total_ms * 1e-3)
