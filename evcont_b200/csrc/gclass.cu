@@ -693,10 +693,10 @@ int launch_1e(cudaStream_t st, int sm_count, int nbatch, const GView& v, const i
 
 }  // namespace
 
-#define EVC_ARGS st, sm_count, nbatch, v, cq
+#define EVC_ARGS sts[(k++) % nst], sm_count, nbatch, v, cq
 #define EVC_UNITS(C) cunits + 2 * cunit_off[C], cunit_off[C + 1] - cunit_off[C], coords, o
 #if EVC_GCLASS_PART == 0
-int launch_gclass_part0(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+int launch_gclass_part0(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o) {
   int rc;
   if ((rc = launch_one<0, 0, 0, 0, 0, 0>(EVC_ARGS, EVC_UNITS(0)))) return rc;
@@ -706,7 +706,7 @@ int launch_gclass_part0(cudaStream_t st, int sm_count, int nbatch, const GView& 
 }
 
 #elif EVC_GCLASS_PART == 1
-int launch_gclass_part1(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+int launch_gclass_part1(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o) {
   int rc;
   if ((rc = launch_one<1, 1, 1, 0, 0, 0>(EVC_ARGS, EVC_UNITS(4)))) return rc;
@@ -715,17 +715,18 @@ int launch_gclass_part1(cudaStream_t st, int sm_count, int nbatch, const GView& 
 }
 #elif EVC_GCLASS_PART == 5
 // one-electron classes: plist holds the ordered shell pairs of (s|s), (p|s), (s|p), (p|p) back to back
-int launch_g1e(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* plist, const int* p_off,
-               const double* coords, const GOut& o) {
+int launch_g1e(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* plist,
+               const int* p_off, const double* coords, const GOut& o) {
   int rc;
-  if ((rc = launch_1e<0, 0>(st, sm_count, nbatch, v, plist + p_off[0], p_off[1] - p_off[0], coords, o))) return rc;
-  if ((rc = launch_1e<1, 0>(st, sm_count, nbatch, v, plist + p_off[1], p_off[2] - p_off[1], coords, o))) return rc;
-  if ((rc = launch_1e<0, 1>(st, sm_count, nbatch, v, plist + p_off[2], p_off[3] - p_off[2], coords, o))) return rc;
-  return launch_1e<1, 1>(st, sm_count, nbatch, v, plist + p_off[3], p_off[4] - p_off[3], coords, o);
+  if ((rc = launch_1e<0, 0>(sts[(k++) % nst], sm_count, nbatch, v, plist + p_off[0], p_off[1] - p_off[0], coords, o))) return rc;
+  if ((rc = launch_1e<1, 0>(sts[(k++) % nst], sm_count, nbatch, v, plist + p_off[1], p_off[2] - p_off[1], coords, o))) return rc;
+  if ((rc = launch_1e<0, 1>(sts[(k++) % nst], sm_count, nbatch, v, plist + p_off[2], p_off[3] - p_off[2], coords, o))) return rc;
+  return launch_1e<1, 1>(sts[(k++) % nst], sm_count, nbatch, v, plist + p_off[3], p_off[4] - p_off[3], coords, o);
 }
 #else
 #define EVC_PPPP(N, JBV)                                                                                                 \
-  int launch_gclass_part##N(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq,                \
+  int launch_gclass_part##N(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v,          \
+                            const int32_t* cq,                                                                           \
                             const int32_t* cunits, const int* cunit_off, const double* coords, const GOut& o) {          \
     int rc;                                                                                                              \
     if ((rc = launch_one<1, 1, 1, 1, JBV, 0>(EVC_ARGS, EVC_UNITS(5)))) return rc;                                        \

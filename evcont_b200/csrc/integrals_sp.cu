@@ -213,12 +213,22 @@ int evc_gbasis_create(evc_ctx* ctx, int natm, const double* charges_host, int na
     delete b;
     return rc;
   }
+  for (int k = 0; k < kGAux; ++k) {
+    EVC_CHECK_CUDA(cudaStreamCreateWithFlags(&b->aux[k], cudaStreamNonBlocking));
+    EVC_CHECK_CUDA(cudaEventCreateWithFlags(&b->ev_join[k], cudaEventDisableTiming));
+  }
+  EVC_CHECK_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
   *out = b;
   return 0;
 }
 
 int evc_gbasis_destroy(evc_gbasis* b) {
   if (b) {
+    for (int k = 0; k < kGAux; ++k) {
+      if (b->aux[k]) cudaStreamDestroy(b->aux[k]);
+      if (b->ev_join[k]) cudaEventDestroy(b->ev_join[k]);
+    }
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     cudaFree(b->ao_atom); cudaFree(b->ao_pow); cudaFree(b->ao_poff); cudaFree(b->aoslices); cudaFree(b->prim_exp);
     cudaFree(b->prim_wt); cudaFree(b->charges); cudaFree(b->boys);
     cudaFree(b->sh_atom); cudaFree(b->sh_ao0); cudaFree(b->sh_p0); cudaFree(b->sh_np); cudaFree(b->cq); cudaFree(b->cunits); cudaFree(b->plist);
@@ -246,20 +256,37 @@ int evc_ao_integrals_sp(evc_ctx* ctx, const evc_gbasis* b, int nbatch, const dou
   GView v{b->natm, b->nao, b->ao_atom, b->ao_pow, b->ao_poff,
           b->sh_atom, b->sh_ao0, b->sh_p0, b->sh_np, b->prim_exp, b->prim_wt, b->charges, b->boys};
   GOut o{ovlp, hcore, eri, ipovlp, static_cast<double*>(workspace), eri_ip1, e_nuc, grad_nuc};
-  {
-    int rc;
-    if ((rc = launch_gclass_part0(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
-    if ((rc = launch_gclass_part1(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
-    if ((rc = launch_gclass_part2(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
-    if ((rc = launch_gclass_part3(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
-    if ((rc = launch_gclass_part4(ctx->stream, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+  // Few geometries: every class kernel is bounded by its longest unit, not by throughput, so the 21 launches run
+  // concurrently on side streams (fork / join through events: capturable in a CUDA graph); many geometries: one stream.
+  cudaStream_t ring[kGAux + 1];
+  ring[0] = ctx->stream;
+  int nst = 1;
+  if (nbatch <= 16) {
+    EVC_CHECK_CUDA(cudaEventRecord(b->ev_fork, ctx->stream));
+    for (int k = 0; k < kGAux; ++k) {
+      EVC_CHECK_CUDA(cudaStreamWaitEvent(b->aux[k], b->ev_fork, 0));
+      ring[1 + k] = b->aux[k];
+    }
+    nst = kGAux + 1;
   }
   {
     int rc;
-    if ((rc = launch_g1e(ctx->stream, ctx->sm_count, nbatch, v, b->plist, b->p_off, coords, o))) return rc;
+    // heaviest kernels first on distinct streams: part 0 = ssss, psss, ppss, psps
+    if ((rc = launch_gclass_part0(ring, nst, 0, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+    if ((rc = launch_gclass_part1(ring, nst, 4, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+    if ((rc = launch_g1e(ring, nst, 7, ctx->sm_count, nbatch, v, b->plist, b->p_off, coords, o))) return rc;
+    if ((rc = launch_gclass_part2(ring, nst, 3, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+    if ((rc = launch_gclass_part3(ring, nst, 6, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
+    if ((rc = launch_gclass_part4(ring, nst, 1, ctx->sm_count, nbatch, v, b->cq, b->cunits, b->cunit_off, coords, o))) return rc;
   }
-  gnuc_kernel<<<nbatch, 32, 0, ctx->stream>>>(b->natm, b->charges, coords, e_nuc, grad_nuc);
+  gnuc_kernel<<<nbatch, 32, 0, ring[nst - 1]>>>(b->natm, b->charges, coords, e_nuc, grad_nuc);
   EVC_CHECK_LAUNCH();
+  if (nst > 1) {
+    for (int k = 0; k < kGAux; ++k) {
+      EVC_CHECK_CUDA(cudaEventRecord(b->ev_join[k], b->aux[k]));
+      EVC_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, b->ev_join[k], 0));
+    }
+  }
   const int64_t total = static_cast<int64_t>(nbatch) * b->natm * 3 * b->nao * b->nao;
   ghd_sym_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->stream>>>(total, b->nao, o.vtmp, hcore_deriv);
   EVC_CHECK_LAUNCH();

@@ -13,6 +13,7 @@ constexpr int kGThreads = 256;
 constexpr int kGMaxAtoms = 16;
 constexpr int kGMaxL = 6;            // highest Boys order: (pp|pp) with one derivative = 5 (+1 spare)
 
+constexpr int kGAux = 7;       // side streams of a basis (small batches: concurrent class kernels)
 constexpr int kGClasses = 6;   // ssss, psss, ppss, psps, ppps, pppp (canonical shell-quartet classes)
 
 struct GView {
@@ -27,19 +28,20 @@ struct GOut {
   double *ovlp, *hcore, *eri, *ipovlp, *vtmp, *eri_ip1, *e_nuc, *grad_nuc;
 };
 
+// Every launcher takes a ring of `nst` streams and puts its i-th kernel on sts[(k + i) % nst] (nst = 1: one stream).
 // launches the two-electron class kernels of compilation part `part` (0: ssss, psss, ppss, psps; 1: ppps;
 // 2..4: pppp with the component of the second function fixed) for the unit lists of the basis
-int launch_gclass_part0(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+int launch_gclass_part0(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o);
-int launch_g1e(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* plist, const int* p_off,
+int launch_g1e(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* plist, const int* p_off,
                const double* coords, const GOut& o);
-int launch_gclass_part1(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+int launch_gclass_part1(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o);
-int launch_gclass_part2(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+int launch_gclass_part2(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o);
-int launch_gclass_part3(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+int launch_gclass_part3(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o);
-int launch_gclass_part4(cudaStream_t st, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
+int launch_gclass_part4(const cudaStream_t* sts, int nst, int k, int sm_count, int nbatch, const GView& v, const int32_t* cq, const int32_t* cunits,
                         const int* cunit_off, const double* coords, const GOut& o);
 
 }  // namespace evc_gint
@@ -51,6 +53,8 @@ struct evc_gbasis {
   int32_t *cq, *cunits;                            // shell-quartet work lists of the class kernels
   int32_t *plist;                                  // ordered shell pairs of the one-electron classes
   int p_off[5];
+  cudaStream_t aux[evc_gint::kGAux];               // side streams: the class kernels of a SMALL batch run concurrently
+  cudaEvent_t ev_fork, ev_join[evc_gint::kGAux];
   int cq_off[evc_gint::kGClasses + 1], cunit_off[evc_gint::kGClasses + 1];
   double *prim_exp, *prim_wt, *charges, *boys;
 };
