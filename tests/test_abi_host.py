@@ -76,6 +76,27 @@ def test_bad_arguments_are_errors():
         cistring.make_strings([0, 2, 3], 2)
 
 
+def test_argument_checks_of_the_training_side_entry_points():
+    """NULL handles / bad sizes are rejected before any device work, with a message in evc_last_error; the
+    workspace queries are pure host arithmetic."""
+    lib = _lib.lib()
+    nbytes = C.c_size_t()
+    assert lib.evc_transform_ci_workspace_bytes(10, 252, 252, C.byref(nbytes)) == 0
+    # Ta^T (252^2) + Tb + two (252 x 252) work matrices, plus GEMM scratch
+    assert nbytes.value >= 4 * 252 * 252 * 8
+    assert lib.evc_transform_ci_workspace_bytes(13, 1287, 1287, C.byref(nbytes)) == 0
+    assert nbytes.value >= (1287 * 1287 + 3 * 1287 * 1288) * 8      # odd row length padded to even
+    assert lib.evc_transform_ci_workspace_bytes(0, 1, 1, C.byref(nbytes)) != 0
+    assert lib.evc_transform_ci(None, 4, 2, 2, 6, 6, None, None, None, None, None, None, 0) != 0
+    assert b"evc_transform_ci" in lib.evc_last_error()
+    assert lib.evc_fock_rhf(None, 4, None, None, None, None) != 0
+    assert b"evc_fock_rhf" in lib.evc_last_error()
+    assert lib.evc_min_sqdist(None, 1, 1, 4, 20, None, None, None) != 0
+    assert b"evc_min_sqdist" in lib.evc_last_error()
+    assert lib.evc_fci_contract_workspace_bytes(10, 252, 252, C.byref(nbytes)) == 0
+    assert nbytes.value >= 2 * 63504 * 100 * 8
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device every compute entry point must fail loudly."""
     import torch
