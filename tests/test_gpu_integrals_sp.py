@@ -109,3 +109,31 @@ def test_water_step_from_coordinates():
     E, _ = get_energy_with_grad_coords(mol, np.stack(disp), one, two, ovlp)
     fd = (E[0::2] - E[1::2]) / (2 * h)
     assert np.abs(fd - np.array([g[0, 0], g[1, 2], g[2, 1]])).max() < 2e-6 * max(1.0, np.abs(g).max())
+
+
+def test_water_md_graph_replay_equals_eager_small_and_large_batches():
+    """The s+p integrals inside the device MD step: with few replicas the class kernels of one call run
+    concurrently on side streams (event fork / join), which must be capturable in the CUDA graph of the step and
+    give bit-identical trajectories; with many replicas the single-stream path."""
+    from evcont_b200.md import DeviceNVE
+    from evcont_b200.mol import MolLite
+    ang = 1.0 / 0.52917721092
+    r, th = 0.9572 * ang, np.deg2rad(104.52)
+    mol = MolLite([("O", (0, 0, 0)), ("H", (r * np.sin(th / 2), 0, r * np.cos(th / 2))),
+                   ("H", (-r * np.sin(th / 2), 0, r * np.cos(th / 2)))], basis="6-31g")
+    n, N = mol.nao, 3
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal((N, N))
+    ovlp = np.eye(N) + 0.01 * (b + b.T)
+    one = rng.standard_normal((N, N, n, n))
+    one = one + one.transpose(1, 0, 3, 2)
+    two = 0.1 * rng.standard_normal((N, N) + (n,) * 4)
+    two = two + two.transpose(1, 0, 3, 2, 5, 4)
+    for B in (2, 24):      # <= 16: concurrent class kernels; > 16: one stream
+        x0 = mol.atom_coords()[None] + 0.02 * rng.standard_normal((B, 3, 3))
+        runs = {}
+        for graph in (False, True):
+            runs[graph] = DeviceNVE(mol, one, two, ovlp, x0, None, dt=2.0, max_frames=6, use_graph=graph).run(5).frames()
+        for a, c in zip(runs[False], runs[True]):
+            assert a.shape[0] == 6 and np.array_equal(a, c)
+        assert np.isfinite(runs[True][1]).all()
