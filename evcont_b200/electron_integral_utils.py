@@ -74,7 +74,11 @@ def get_basis(mol, basis_type="OAO"):
         return get_loewdin_trafo(mol.intor("int1e_ovlp"))
     if basis_type == "canonical" and not type(mol).__module__.startswith("pyscf."):
         from .scf import rhf
-        return rhf(mol).mo_coeff
+        res = rhf(mol)
+        if not res.converged:  # PySCF only warns here; an unconverged basis silently changes the FCI solve basis
+            import warnings
+            warnings.warn(f"RHF for the canonical basis did not converge in {res.cycles} cycles", RuntimeWarning)
+        return res.mo_coeff
     try:
         from pyscf import lo, scf
     except ImportError as exc:

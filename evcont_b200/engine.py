@@ -5,6 +5,7 @@ PyTorch is used only for what the C ABI leaves to the caller: device buffers
 (in ``evcont_b200.distributed``) the NCCL process group.  All arithmetic runs in
 ``libevcont_b200.so``.
 """
+import contextlib
 import ctypes as C
 import threading
 
@@ -56,20 +57,39 @@ class Engine:
         self.sm_count = self.lib.evc_ctx_sm_count(handle)
         self._links = {}
         self._sbases = {}
-        self._ws = None
+        self._ws = {}            # shared scratch, one Workspace per CUDA stream
+        self._ws_private = None  # a caller-owned Workspace (using_workspace)
 
     # -- plumbing ------------------------------------------------------------
     def _bind_stream(self):
+        """Make this engine's device current (the ``device=`` arguments of the public API work
+        without a prior ``torch.cuda.set_device``) and launch on torch's current stream of it."""
+        if torch.cuda.current_device() != self.device.index:
+            torch.cuda.set_device(self.device)
         stream = torch.cuda.current_stream(self.device)
         check(self.lib.evc_ctx_set_stream(self._ctx, C.c_void_p(stream.cuda_stream)))
 
     def workspace(self, nbytes):
-        """A reusable scratch buffer of at least ``nbytes`` (grown geometrically)."""
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8,
-                                   device=self.device)
-        return self._ws
+        """Scratch buffer of at least ``nbytes``: the caller-owned :class:`Workspace` inside a
+        :meth:`using_workspace` block, else this engine's shared one for the current stream
+        (grown geometrically; work queued on one stream is ordered, so sharing per stream is safe)."""
+        if self._ws_private is not None:
+            return self._ws_private.get(nbytes)
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        if key not in self._ws:
+            self._ws[key] = Workspace(self.device)
+        return self._ws[key].get(nbytes)
+
+    @contextlib.contextmanager
+    def using_workspace(self, ws):
+        """Route every scratch request of the enclosed engine calls to ``ws`` (a :class:`Workspace`
+        the caller keeps alive -- e.g. the owner of a captured CUDA graph, whose replays use the
+        pointer that was current at capture time)."""
+        prev, self._ws_private = self._ws_private, ws
+        try:
+            yield ws
+        finally:
+            self._ws_private = prev
 
     STAGES = ("loewdin", "ao2oao", "subspace_H", "geneig", "predict_rdm", "grad", "grad_stream")
 
@@ -432,6 +452,26 @@ class Engine:
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
         return host_ao.E, host_ao.grad
+
+
+class Workspace:
+    """A scratch tensor owned by whoever holds this object.  ``freeze()`` pins the buffer: a later,
+    larger request raises instead of re-allocating (a captured CUDA graph keeps the raw pointer)."""
+
+    def __init__(self, device):
+        self.device, self.tensor, self.frozen = device, None, False
+
+    def get(self, nbytes):
+        if self.tensor is None or self.tensor.numel() < nbytes:
+            if self.frozen:
+                raise RuntimeError(f"workspace frozen at {self.tensor.numel()} bytes (a CUDA graph references "
+                                   f"it); {nbytes} bytes requested")
+            self.tensor = None
+            self.tensor = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=self.device)
+        return self.tensor
+
+    def freeze(self):
+        self.frozen = True
 
 
 class FCIHamiltonian:

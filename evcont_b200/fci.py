@@ -47,6 +47,8 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
             V.append(g / nrm)
         if len(V) == nroots:
             break
+    if len(V) < nroots:
+        raise RuntimeError(f"FCI Davidson: only {len(V)} independent initial guesses for nroots={nroots}")
     W = [ham.contract(v) for v in V]
     theta, X = None, None
     for _cycle in range(max_cycle):
@@ -82,7 +84,21 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
             W.append(ham.contract(V[-1]))
             added += 1
         if added == 0:
-            break
+            # every correction vector was linearly dependent on the space although a residual is still above
+            # tol: collapse onto the Ritz vectors plus the (unpreconditioned) residuals instead of giving up
+            V, W = [], []
+            for k in range(nroots):
+                v, nrm = orth(X[k].clone(), V)
+                V.append(v / nrm)
+            for k in range(nroots):
+                if rn[k] >= tol:
+                    t, nrm = orth(sym(R[k].clone()), V)
+                    if nrm > 1e-12:
+                        V.append(t / nrm)
+                        added += 1
+            if added == 0:
+                raise RuntimeError(f"FCI Davidson stalled with residuals {rn} (tol {tol})")
+            W = [ham.contract(v) for v in V]
     else:
         raise RuntimeError(f"FCI Davidson did not converge in {max_cycle} cycles (residuals {rn})")
     out = []

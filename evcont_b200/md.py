@@ -59,9 +59,18 @@ class DeviceNVE:
         self.ekin_log = eng.empty(mf, B) if self.max_frames else None
         self.use_graph, self._graph = bool(use_graph), None
         self.nsteps = 0
+        # scratch owned by this object: the captured graph replays with this buffer's address, so it must
+        # neither be freed nor shared with other engine calls issued between two run() calls
+        from .engine import Workspace
+        self._ws = Workspace(eng.device)
         self._force(first=True)
 
     def _force(self, first):
+        eng = self.engine
+        with eng.using_workspace(self._ws):
+            self._force_impl(first)
+
+    def _force_impl(self, first):
         eng = self.engine
         eng.energy_with_grad_coords(self.stack, self.sbasis, self.x, ao=self.ao,
                                     out=(self.epot, self.grad, self.cvec))
@@ -96,6 +105,7 @@ class DeviceNVE:
             torch.cuda.current_stream(self.engine.device).wait_stream(side)
             # capturing does not execute: the captured step has not been applied
             self._graph = g
+            self._ws.freeze()
         for _ in range(steps):
             if self._graph is not None:
                 self._graph.replay()

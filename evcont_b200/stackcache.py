@@ -3,9 +3,15 @@
 The reference passes ``one_RDM, two_RDM, S`` as numpy arrays on every call
 (evcont/MD_utils.py:40-55 calls get_energy_with_grad once per MD step with the
 same three arrays).  Uploading 32 MB - 12 GB per step would dominate, so the
-device copy is cached per ``two_RDM`` array object and revalidated with a cheap
-fingerprint (shapes + strided samples), which catches re-assignment and most
-in-place edits; call :func:`invalidate` after editing a stack in place.
+device copy is cached per ``two_RDM`` array object (identity, data pointer, shape,
+strides) and revalidated with a fingerprint: full sums of ``one_RDM`` and ``S`` (small)
+plus 64 Ki strided samples and the full sum of ``two_RDM`` when it is small (< 64 MB).
+
+**In-place edits of a multi-GB ``two_RDM`` that miss the samples are not detected: call
+:func:`invalidate` after editing a stack in place** (``FCI_EVCont_obj`` re-allocates its
+arrays on every append / prune, like the reference, so its stacks never alias).
+Entries whose array died are evicted on the next call, so dead device stacks do not
+pile up in HBM.
 """
 import weakref
 
@@ -18,12 +24,18 @@ _MAX_ENTRIES = 4
 
 
 def _fingerprint(one_rdm, two_rdm, S):
-    flat = two_rdm.reshape(-1)
-    step = max(1, flat.size // 4096)
-    f1 = one_rdm.reshape(-1)
-    s1 = max(1, f1.size // 1024)
-    return (two_rdm.shape, one_rdm.shape, float(flat[::step].sum()), float(f1[::s1].sum()),
-            float(np.asarray(S).sum()), float(flat[-1]))
+    flat = two_rdm.reshape(-1) if two_rdm.flags.c_contiguous else two_rdm.ravel()
+    step = max(1, flat.size // 65536)
+    full = float(flat.sum()) if flat.size <= (1 << 23) else 0.0
+    S = np.asarray(S)
+    return (two_rdm.shape, one_rdm.shape, two_rdm.strides, two_rdm.__array_interface__["data"][0],
+            float(flat[::step].sum()), full, float(one_rdm.sum()), float(np.abs(one_rdm).sum()),
+            float(S.sum()), float(np.abs(S).sum()), float(flat[-1]) if flat.size else 0.0)
+
+
+def _evict_dead():
+    for k in [k for k, (ref, _, _) in _cache.items() if ref() is None]:
+        del _cache[k]
 
 
 def invalidate():
@@ -39,6 +51,7 @@ def as_device_stack(one_RDM, two_RDM, S, device=None):
     if two_RDM.ndim not in (2, 3, 5, 6):
         raise AssertionError("two_RDM must have 2, 3, 5 or 6 dimensions")
     eng = get_engine(device)
+    _evict_dead()
     key = (id(two_RDM), eng.device.index)
     fp = _fingerprint(one_RDM, two_RDM, S)
     hit = _cache.get(key)
@@ -51,7 +64,7 @@ def as_device_stack(one_RDM, two_RDM, S, device=None):
         _cache.pop(next(iter(_cache)))
     try:
         ref = weakref.ref(two_RDM)
-    except TypeError:  # views of some buffers cannot be weakly referenced
-        ref = (lambda obj: (lambda: obj))(two_RDM)
+    except TypeError:  # not weakly referenceable: do not pin it, let the entry die with the next eviction
+        ref = (lambda: None)
     _cache[key] = (ref, fp, stack)
     return stack
