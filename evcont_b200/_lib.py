@@ -21,7 +21,10 @@ class AoBundle(C.Structure):
     """Mirror of ``evc_ao_bundle``."""
     _fields_ = [(name, C.c_void_p) for name in (
         "ovlp", "hcore", "eri", "ipovlp", "hcore_deriv", "eri_ip1", "e_nuc", "grad_nuc",
-        "aoslices")]
+        "aoslices", "erip", "eri_ip1p")]
+
+
+ABI_VERSION = 2  # EVC_ABI_VERSION of include/evcont_b200.h
 
 
 class EvcError(RuntimeError):
@@ -85,6 +88,10 @@ SIGNATURES = {
                                             C.POINTER(AoBundle), C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_void_p, C.c_size_t]),
     "evc_packed_row_len": (c_i64, [C.c_int]),
+    "evc_erip_pitch": (C.c_int, [C.c_int]),
+    "evc_erip_len": (c_i64, [C.c_int]),
+    "evc_eri_ip1p_len": (c_i64, [C.c_int]),
+    "evc_ao_pack8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "evc_stack_pack8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
                                   c_double_p, c_double_p]),
     "evc_energy_with_grad_packed_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int,
@@ -108,6 +115,8 @@ SIGNATURES = {
     "evc_ao_integrals_s_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, c_sz_p]),
     "evc_ao_integrals_s": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9 +
                            [C.c_void_p, C.c_size_t]),
+    "evc_ao_integrals_s_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9 +
+                                  [C.c_void_p, C.c_size_t]),
     "evc_gbasis_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "evc_gbasis_destroy": (C.c_int, [C.c_void_p]),
@@ -149,7 +158,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the ABI drifted
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.evc_abi_version() != 1:
+        if handle.evc_abi_version() != ABI_VERSION:
             raise ImportError("libevcont_b200.so ABI version mismatch; rebuild it")
         _lib = handle
     return _lib

@@ -56,14 +56,23 @@ size_t evc_rows_axpy_ws_bytes(int64_t L, int P, int G);
 int evc_rows_axpy(evc_ctx* ctx, const double* rows, int64_t L, int P, const double* w, int G, double* out,
                   void* workspace, size_t workspace_bytes);
 // packed (8-fold symmetric) prediction step pieces, packed.cu
-constexpr int kPackedMaxNorb = 13;  // per-geometry shared-memory kernels up to this many orbitals
+constexpr int kPackedMaxNorb = 13;      // per-geometry shared-memory kernels up to this many orbitals
+constexpr int kPackedPipeMaxNorb = 10;  // persistent warp-specialised kernels (packed_pipe.cu) up to this many
+// erip: [nbatch][np][pA] packed (ab|cd); Tout: same layout; eri_ip1p: [nbatch][3][n][n][np]
 int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
-                      const double* eri, double* hvec, double* Tout);
+                      const double* erip, double* hvec, double* Tout);
 int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices, const double* x,
                     const double* evals, const double* evecs, const double* hcore, const double* Tin,
                     const double* out7, const double* ipovlp, const double* hcore_deriv,
-                    const double* eri_ip1, const double* grad_nuc, double* Wg, double* OmS, double* Pao,
+                    const double* eri_ip1p, const double* grad_nuc, double* Wg, double* OmS, double* Pao,
                     double* grad);
+// packed_pipe.cu
+bool evc_packed_pipe_supported(int n);
+int evc_packed_ao2oao_pipe(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
+                           const double* erip, double* hvec, double* Tout);
+int evc_packed_grad_pipe(evc_ctx* ctx, int nbatch, int n, const double* x, const double* evals,
+                         const double* evecs, const double* hcore, const double* Timg, const double* out7,
+                         double* Wg, double* OmS, double* Pao);
 // K8 on full (n^4) arrays with the nuclear gradient added (grad.cu); sym8 != 0: Gamma carries the 8-fold
 // permutational symmetry of the integrals (packed step), which turns the symmetrising gathers into streams
 int evc_grad_elec_full(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices,

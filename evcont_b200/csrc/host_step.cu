@@ -7,7 +7,7 @@
 // return on a third stream (double-buffered staging slots, CUDA events only -- no
 // host synchronisation inside).  With pinned host memory the whole call is
 // asynchronous with respect to the host; pageable memory works but serialises.
-#include "common.cuh"
+#include "packed.cuh"
 
 namespace {
 
@@ -117,10 +117,18 @@ int host_pipeline(evc_ctx* ctx, int n, int natm, int nbatch, const evc_ao_bundle
                                  cudaMemcpyHostToDevice, hs))
     EVC_H2D(ovlp, sz.ovlp);
     EVC_H2D(hcore, sz.hcore);
-    EVC_H2D(eri, sz.eri);
+    // two-electron arrays: packed (erip / eri_ip1p, into the same slot buffers) or full tensors
+    const size_t ne = static_cast<size_t>(evcp::erip_len(n)), ni = static_cast<size_t>(evcp::ip1p_len(n));
+    if (ao_host->erip)
+      EVC_CHECK_CUDA(cudaMemcpyAsync(s.eri, ao_host->erip + g0 * ne, cnt * ne * sizeof(double), cudaMemcpyHostToDevice, hs));
+    else
+      EVC_H2D(eri, sz.eri);
     EVC_H2D(ipovlp, sz.ipovlp);
     EVC_H2D(hcore_deriv, sz.hcore_deriv);
-    EVC_H2D(eri_ip1, sz.eri_ip1);
+    if (ao_host->eri_ip1p)
+      EVC_CHECK_CUDA(cudaMemcpyAsync(s.eri_ip1, ao_host->eri_ip1p + g0 * ni, cnt * ni * sizeof(double), cudaMemcpyHostToDevice, hs));
+    else
+      EVC_H2D(eri_ip1, sz.eri_ip1);
     if (ao_host->e_nuc) EVC_H2D(e_nuc, sz.e_nuc);
     if (ao_host->grad_nuc) EVC_H2D(grad_nuc, sz.grad_nuc);
 #undef EVC_H2D
@@ -129,8 +137,11 @@ int host_pipeline(evc_ctx* ctx, int n, int natm, int nbatch, const evc_ao_bundle
     // outputs of this slot are free once the read-back of chunk c-2 is done
     if (c >= 2) EVC_CHECK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_d2h[k], 0));
     evc_ao_bundle dev;
-    dev.ovlp = s.ovlp; dev.hcore = s.hcore; dev.eri = s.eri; dev.ipovlp = s.ipovlp;
-    dev.hcore_deriv = s.hcore_deriv; dev.eri_ip1 = s.eri_ip1;
+    dev.ovlp = s.ovlp; dev.hcore = s.hcore; dev.ipovlp = s.ipovlp; dev.hcore_deriv = s.hcore_deriv;
+    dev.eri = ao_host->erip ? nullptr : s.eri;
+    dev.erip = ao_host->erip ? s.eri : nullptr;
+    dev.eri_ip1 = ao_host->eri_ip1p ? nullptr : s.eri_ip1;
+    dev.eri_ip1p = ao_host->eri_ip1p ? s.eri_ip1 : nullptr;
     dev.e_nuc = ao_host->e_nuc ? s.e_nuc : nullptr;
     dev.grad_nuc = ao_host->grad_nuc ? s.grad_nuc : nullptr;
     dev.aoslices = aosl;
@@ -148,8 +159,9 @@ int host_pipeline(evc_ctx* ctx, int n, int natm, int nbatch, const evc_ao_bundle
   return 0;
 }
 
-bool host_bundle_ok(const evc_ao_bundle* a) {
-  return a->ovlp && a->hcore && a->eri && a->ipovlp && a->hcore_deriv && a->eri_ip1 && a->aoslices;
+bool host_bundle_ok(const evc_ao_bundle* a, bool packed_ok) {
+  return a->ovlp && a->hcore && (a->eri || (packed_ok && a->erip)) && a->ipovlp && a->hcore_deriv &&
+         (a->eri_ip1 || (packed_ok && a->eri_ip1p)) && a->aoslices;
 }
 
 }  // namespace
@@ -162,7 +174,7 @@ int evc_energy_with_grad_host(evc_ctx* ctx, int layout, int N, int n, int natm, 
                               void* workspace, size_t workspace_bytes) {
   EVC_REQUIRE(ctx && one_rdm && two_rdm && Linv && ao_host && E_host && grad_host && workspace,
               "evc_energy_with_grad_host: NULL argument");
-  EVC_REQUIRE(host_bundle_ok(ao_host), "evc_energy_with_grad_host: incomplete AO bundle");
+  EVC_REQUIRE(host_bundle_ok(ao_host, false), "evc_energy_with_grad_host: incomplete AO bundle (full tensors needed)");
   EVC_REQUIRE(chunk >= 1, "evc_energy_with_grad_host: chunk must be >= 1");
   if (nbatch <= 0) return 0;
   if (chunk > nbatch) chunk = nbatch;
@@ -192,7 +204,7 @@ int evc_energy_with_grad_packed_host(evc_ctx* ctx, int N, int n, int natm, const
                                      size_t workspace_bytes) {
   EVC_REQUIRE(ctx && RH && RG && Linv && ao_host && E_host && grad_host && workspace,
               "evc_energy_with_grad_packed_host: NULL argument");
-  EVC_REQUIRE(host_bundle_ok(ao_host), "evc_energy_with_grad_packed_host: incomplete AO bundle");
+  EVC_REQUIRE(host_bundle_ok(ao_host, n <= kPackedMaxNorb), "evc_energy_with_grad_packed_host: incomplete AO bundle");
   EVC_REQUIRE(chunk >= 1, "evc_energy_with_grad_packed_host: chunk must be >= 1");
   if (nbatch <= 0) return 0;
   if (chunk > nbatch) chunk = nbatch;

@@ -122,6 +122,10 @@ __device__ __forceinline__ void boys01(double T, const double* __restrict__ tab,
 
 struct IntOut {
   double *ovlp, *hcore, *eri, *ipovlp, *hcore_deriv, *eri_ip1, *e_nuc, *grad_nuc;
+  // packed two-electron output (evc_ao_integrals_s_packed): erip [np][pitch], eri_ip1p [3][n][n][np];
+  // eri / eri_ip1 are NULL then
+  double *erip, *ip1p;
+  int pitch;
 };
 
 struct BasisView {
@@ -251,8 +255,10 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out, const c
   __syncthreads();
 
   const int64_t n2 = static_cast<int64_t>(n) * n, n3 = n2 * n, n4 = n2 * n2;
-  double* eri = out.eri + static_cast<int64_t>(g) * n4;
-  double* ip1 = out.eri_ip1 + static_cast<int64_t>(g) * 3 * n4;
+  const bool packed = out.erip != nullptr;
+  const int64_t npk = bs.npc;  // contracted pairs = n (n + 1) / 2
+  double* eri = packed ? out.erip + static_cast<int64_t>(g) * npk * out.pitch : out.eri + static_cast<int64_t>(g) * n4;
+  double* ip1 = packed ? out.ip1p + static_cast<int64_t>(g) * 3 * n2 * npk : out.eri_ip1 + static_cast<int64_t>(g) * 3 * n4;
   const double* ppg = PP_IN_SMEM ? ppt : bs.pp;
 
   // ---- two-electron part: contracted quartets (I >= K) dealt to warps -----------------
@@ -354,11 +360,22 @@ sint_kernel(BasisView bs, const double* __restrict__ coords, IntOut out, const c
           gx = 2.0 * cdx * Mcd + 2.0 * vdx; gy = 2.0 * cdy * Mcd + 2.0 * vdy; gz = 2.0 * cdz * Mcd + 2.0 * vdz;
         }
       }
-      const int64_t idx = i0 * n3 + i1 * n2 + i2 * n + i3;
-      eri[idx] = E;
-      ip1[idx] = -gx;
-      ip1[n4 + idx] = -gy;
-      ip1[2 * n4 + idx] = -gz;
+      if (!packed) {
+        const int64_t idx = i0 * n3 + i1 * n2 + i2 * n + i3;
+        eri[idx] = E;
+        ip1[idx] = -gx;
+        ip1[n4 + idx] = -gy;
+        ip1[2 * n4 + idx] = -gz;
+      } else if ((lane & 1) == 0) {
+        // one representative per differentiated function: (d i0 i1 | pair of the other side)
+        const int64_t idx = (static_cast<int64_t>(i0) * n + i1) * npk + (who < 2 ? K : I);
+        const int64_t xs = n2 * npk;
+        ip1[idx] = -gx;
+        ip1[xs + idx] = -gy;
+        ip1[2 * xs + idx] = -gz;
+        if (who == 0) eri[static_cast<int64_t>(I) * out.pitch + K] = E;
+        if (who == 2) eri[static_cast<int64_t>(K) * out.pitch + I] = E;
+      }
     }
   }
 
@@ -628,9 +645,12 @@ int evc_ao_integrals_s_workspace_bytes(const evc_sbasis* b, int nbatch, size_t* 
   return 0;
 }
 
-int evc_ao_integrals_s(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const double* coords, double* ovlp,
-                       double* hcore, double* eri, double* ipovlp, double* hcore_deriv, double* eri_ip1,
-                       double* e_nuc, double* grad_nuc, void* workspace, size_t workspace_bytes) {
+}  // extern "C"
+
+namespace {
+int ao_integrals_s_impl(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const double* coords, double* ovlp,
+                        double* hcore, double* eri, double* ipovlp, double* hcore_deriv, double* eri_ip1,
+                        double* e_nuc, double* grad_nuc, void* workspace, size_t workspace_bytes, bool packed) {
   EVC_REQUIRE(ctx && b && coords && ovlp && hcore && eri && ipovlp && hcore_deriv && eri_ip1 && e_nuc && grad_nuc,
               "evc_ao_integrals_s: NULL argument");
   if (nbatch <= 0) return 0;
@@ -643,7 +663,11 @@ int evc_ao_integrals_s(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const doub
   v.ao_atom = b->ao_atom; v.ao_poff = b->ao_poff; v.prim_de = b->prim_de; v.pc_off = b->pc_off;
   v.prim_exp = b->prim_exp; v.prim_wt = b->prim_wt; v.charges = b->charges; v.pe1 = b->pe1; v.pp = b->pp;
   v.boys = b->boys;
-  IntOut o{ovlp, hcore, eri, ipovlp, hcore_deriv, eri_ip1, e_nuc, grad_nuc};
+  IntOut o{ovlp, hcore, eri, ipovlp, hcore_deriv, eri_ip1, e_nuc, grad_nuc, nullptr, nullptr, 0};
+  if (packed) {
+    o.erip = eri; o.ip1p = eri_ip1; o.eri = nullptr; o.eri_ip1 = nullptr;
+    o.pitch = evc_erip_pitch(b->nao);
+  }
   // few geometries: several CTAs per geometry so that the whole GPU works on them
   int split = 1;
   const long long nq = static_cast<long long>(b->npc) * (b->npc + 1) / 2;
@@ -671,6 +695,23 @@ int evc_ao_integrals_s(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const doub
 #undef EVC_SINT
   EVC_CHECK_LAUNCH();
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int evc_ao_integrals_s(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const double* coords, double* ovlp,
+                       double* hcore, double* eri, double* ipovlp, double* hcore_deriv, double* eri_ip1,
+                       double* e_nuc, double* grad_nuc, void* workspace, size_t workspace_bytes) {
+  return ao_integrals_s_impl(ctx, b, nbatch, coords, ovlp, hcore, eri, ipovlp, hcore_deriv, eri_ip1, e_nuc, grad_nuc,
+                             workspace, workspace_bytes, false);
+}
+
+int evc_ao_integrals_s_packed(evc_ctx* ctx, const evc_sbasis* b, int nbatch, const double* coords, double* ovlp,
+                              double* hcore, double* erip, double* ipovlp, double* hcore_deriv, double* eri_ip1p,
+                              double* e_nuc, double* grad_nuc, void* workspace, size_t workspace_bytes) {
+  return ao_integrals_s_impl(ctx, b, nbatch, coords, ovlp, hcore, erip, ipovlp, hcore_deriv, eri_ip1p, e_nuc,
+                             grad_nuc, workspace, workspace_bytes, true);
 }
 
 }  // extern "C"

@@ -28,7 +28,9 @@
 //   Gm[I, K]  = out7[tri(I,K)]   (symmetric np x np; RG rows carry the diagonal pairs doubled)
 //   Y[a, i]   = 2 sum_{b j} X_bj s_(ij) U0[(ab), (ij)]
 //   -1/2 sum_{m in A} sum_{bcd} (d_x m b|c d) W[(mb), (cd)]   is the ERI-derivative term.
-#include "common.cuh"
+#include <algorithm>
+
+#include "packed.cuh"
 
 // Optional phase timing of the per-geometry kernels (development aid): build with
 // -DEVC_PHASE_TIMING, read with evc_debug_phase_clocks().
@@ -50,34 +52,13 @@ __device__ long long g_evc_phase[4][24];
 #define EVC_MARK(slot, idx, cond) do { } while (0)
 #endif
 
-namespace {
+using namespace evcp;
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
-  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit_all() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+namespace {
 
 constexpr int kThreads = 256;      // K4p CTA
 constexpr int kGradThreads = 512;  // K8a CTA
 constexpr int kNJ = 4;  // 8x8 output tiles per warp work item (A fragment re-used kNJ times)
-
-__host__ __device__ inline int tri_idx(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
-__host__ __device__ inline int npair_of(int n) { return n * (n + 1) / 2; }
-__host__ __device__ inline int64_t packed_len(int n) {
-  const int64_t np = npair_of(n);
-  const int64_t l = static_cast<int64_t>(n) * n + np * (np + 1) / 2;
-  return (l + 1) & ~static_cast<int64_t>(1);
-}
-
-__device__ __forceinline__ void tril_unrank_i(int t, int& a, int& b) {
-  int x = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
-  while (x * (x + 1) / 2 > t) --x;
-  while ((x + 1) * (x + 2) / 2 <= t) ++x;
-  a = x;
-  b = t - x * (x + 1) / 2;
-}
 
 // ---------------------------------------------------------------------------
 // stack packing (once per stack)
@@ -199,34 +180,6 @@ __global__ void tril_weights_kernel(int N, int P, const double* __restrict__ C, 
 // ---------------------------------------------------------------------------
 // shared-memory geometry of the per-geometry kernels
 // ---------------------------------------------------------------------------
-struct PGeom {
-  int n, np, M8, rows8, K4, pA, pB;
-  size_t szA;  // doubles of an A-type image  [rows8][pA]
-  size_t szB;  // doubles of a B-type image   [K4][pB]
-};
-
-__host__ __device__ inline PGeom pgeom(int n) {
-  PGeom g;
-  g.n = n;
-  g.np = npair_of(n);
-  g.M8 = (g.np + 7) / 8;
-  g.rows8 = g.M8 * 8;
-  g.K4 = (g.np + 3) & ~3;
-  // 8-byte shared-memory loads are served one half-warp (lanes 0-15: g = 0..3, tg = 0..3) at a
-  // time over 16 double-wide banks.  A-type access (lane (g,tg) reads [row g][col tg], word
-  // g*pitch + tg) and B-type access ([row tg][col g], word tg*pitch + g) are both conflict-free
-  // when pitch == 4 (mod 8): the four row offsets land on banks {0,4,8,12}.
-  int pa = g.K4;
-  while ((pa & 7) != 4) ++pa;
-  int pb = g.rows8;
-  while ((pb & 7) != 4) ++pb;
-  g.pA = pa;
-  g.pB = pb;
-  g.szA = static_cast<size_t>(g.rows8) * pa;
-  g.szB = static_cast<size_t>(g.K4) * pb;
-  return g;
-}
-
 // Work items of a CTA-level GEMM, C(M8*8 x N8*8) = A * B on the FP64 tensor cores:
 // item = (row tile, group of kNJ column tiles).  DMMA issue is per SM sub-partition
 // (warp % 4), so the host deals the items to warps such that the four sub-partitions
@@ -313,7 +266,7 @@ __host__ __device__ inline size_t table_bytes(int n) {
 template <int MAXI, int NC>
 __global__ void __launch_bounds__(kThreads)
 packed_ao2oao_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8, const double* __restrict__ x, const double* __restrict__ hcore,
-                     const double* __restrict__ eri, double* __restrict__ hvec, double* __restrict__ Tout) {
+                     const double* __restrict__ erip, double* __restrict__ hvec, double* __restrict__ Tout) {
   extern __shared__ __align__(16) double sm[];
   const int n = NC > 0 ? NC : n_rt;  // compile-time orbital count for the common sizes
   const PGeom pg = pgeom(n);
@@ -328,24 +281,15 @@ packed_ao2oao_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t 
   unsigned short* pidx = pij + np;
   const int g = blockIdx.x, tid = threadIdx.x;
   const int64_t o2 = static_cast<int64_t>(g) * n2;
-  const double* eg = eri + static_cast<int64_t>(g) * n2 * n2;
+  const double* eg = erip + static_cast<int64_t>(g) * np * pA;
 
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int NW = kThreads / 32;
   EVC_PHASE(0, 0);
   // ---- asynchronous copies of this geometry's inputs first ----
-  // ERIp[AB][CD] = (ab|cd), a >= b, c >= d: rows of the full tensor, wanted elements only
+  // ERIp[AB][CD] = (ab|cd), a >= b, c >= d, arrives with the shared-memory row pitch: one contiguous block
+  for (int k = 2 * tid; k < np * pA; k += 2 * kThreads) cp_async16(Eb + k, eg + k);
   build_pair_tables<kThreads>(n, pij, pidx);  // integer only (no FP64 sqrt: that pipe is the DMMA pipe)
-  __syncthreads();
-  for (int AB = warp; AB < np; AB += NW) {
-    const int a = pij[AB] & 0xff, b = pij[AB] >> 8;
-    const double* row = eg + static_cast<int64_t>(a * n + b) * n2;
-    double* dst = Eb + AB * pA;
-    for (int y = lane; y < n2; y += 32) {
-      const int c = y / n, d = y - c * n;
-      if (c >= d) cp_async8(dst + tri_idx(c, d), row + y);
-    }
-  }
   for (int k = tid; k < n2; k += kThreads) {
     const int i = k / n, j = k - i * n;
     cp_async8(Xs + i * ld + j, x + o2 + k);
@@ -353,13 +297,7 @@ packed_ao2oao_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t 
   }
   cp_async_commit_all();
   {
-    // zero padding of ERIp (A-type) and of Q (B-type); the data regions are filled below
-    const int padc = pA - np;
-    for (int k = tid; k < np * padc; k += kThreads) {
-      const int r = k / padc, c = np + (k - r * padc);
-      Eb[r * pA + c] = 0.0;
-    }
-    for (int k = np * pA + tid; k < static_cast<int>(szE); k += kThreads) Eb[k] = 0.0;
+    // zero padding of Q (B-type); its data region is filled below
     const int padq = pB - np;
     for (int k = tid; k < np * padq; k += kThreads) {
       const int r = k / padq, c = np + (k - r * padq);
@@ -368,6 +306,16 @@ packed_ao2oao_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t 
     for (int k = np * pB + tid; k < static_cast<int>(pg.szB); k += kThreads) Qb[k] = 0.0;
   }
   cp_async_wait_all();
+  __syncthreads();
+  {
+    // zero padding of the ERIp image (the array in HBM carries none)
+    const int padc = pA - np;
+    for (int k = tid; k < np * padc; k += kThreads) {
+      const int r = k / padc, c = np + (k - r * padc);
+      Eb[r * pA + c] = 0.0;
+    }
+    for (int k = np * pA + tid; k < static_cast<int>(szE); k += kThreads) Eb[k] = 0.0;
+  }
   __syncthreads();
   EVC_PHASE(0, 1);
   // Q[CD][K] = (X_ck X_dl + X_dk X_cl) / s_CD
@@ -406,15 +354,15 @@ packed_ao2oao_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t 
                  [&](int k, int c) { return Qb[k * pB + c]; });
   __syncthreads();  // every warp is done reading ERIp: T may overwrite it
   EVC_PHASE(0, 3);
-  double* Tg = Tout + static_cast<int64_t>(g) * np * np;
+  double* Tg = Tout + static_cast<int64_t>(g) * np * pA;  // [np][pA], like the ERIp arrays
   gemm_store<MAXI>(acc, mfull, pg.M8, pg.M8, false, [&](int m, int c, double v0, double v1) {
     if (m < pg.K4) {
       Eb[m * pB + c] = v0;
       Eb[m * pB + c + 1] = v1;
     }
     if (m < np) {
-      if (c < np) Tg[m * np + c] = v0;
-      if (c + 1 < np) Tg[m * np + c + 1] = v1;
+      if (c < np) Tg[m * pA + c] = v0;
+      if (c + 1 < np) Tg[m * pA + c + 1] = v1;
     }
   });
   __syncthreads();
@@ -478,13 +426,12 @@ packed_grad_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8
   EVC_PHASE(1, 0);
   // ---- all global inputs of this geometry as asynchronous copies, issued first ----
   {
-    const double* Tg = Tin + static_cast<int64_t>(g) * np * np;
+    const double* Tg = Tin + static_cast<int64_t>(g) * np * pA;
+    for (int k = 2 * tid; k < np * pA; k += 2 * NT) cp_async16(B1 + k, Tg + k);                    // T ([np][pA])
     for (int r = warp; r < np; r += NT / 32) {
       const int rr = r * (r + 1) / 2;
-      for (int c = lane; c < np; c += 32) {
-        cp_async8(B1 + r * pA + c, Tg + r * np + c);                                               // T
+      for (int c = lane; c < np; c += 32)
         cp_async8(B2 + r * pA + c, o7 + n2 + (r >= c ? rr + c : c * (c + 1) / 2 + r));             // Gm = sym(out7)
-      }
     }
     for (int k = tid; k < n2; k += NT) {
       const int i = k / n, j = k - i * n;
@@ -501,8 +448,10 @@ packed_grad_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8
     sv[k] = s;
     rs[k] = s > 1.0e-15 ? sqrt(s) : 0.0;
   }
+  cp_async_wait_all();
+  __syncthreads();
   {
-    // zero padding: columns [np, pA) of the data rows, and the rows [np, rows8)
+    // zero padding: columns [np, pA) of the data rows, and the rows [np, rows8) (the T array in HBM has none)
     const int padc = pA - np;
     for (int k = tid; k < np * padc; k += NT) {
       const int r = k / padc, c = np + (k - r * padc);
@@ -511,7 +460,6 @@ packed_grad_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8
     }
     for (int k = np * pA + tid; k < pg.rows8 * pA; k += NT) { B1[k] = 0.0; B2[k] = 0.0; }
   }
-  cp_async_wait_all();
   __syncthreads();
   EVC_PHASE(1, 2);
 
@@ -680,70 +628,58 @@ packed_grad_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8
 // ---------------------------------------------------------------------------
 // K8b: streaming contraction of the derivative integrals, one CTA per (atom, geometry)
 //   grad[g][A][x] = - sum_{mu in A, nu} <d_x mu|nu> OmS[mu,nu] + sum_{mu nu} dh[A,x][mu,nu] Pao[mu,nu]
-//                   - 1/2 sum_{m in A} sum_{bcd} (d_x m b|c d) W[(mb),(cd)] + grad_nuc[g][A][x]
-// int2e_ip1, the core-Hamiltonian derivative and int1e_ipovlp are read exactly once,
-// with >= 12 independent 8-byte loads in flight per thread.
+//                   - 1/2 sum_{m in A} sum_{b, c >= d} (2 - d_cd) (d_x m b|c d) W[(mb),(cd)] + grad_nuc[g][A][x]
+// on the PACKED derivative integrals eri_ip1p[x][m][b][CD] (int2e_ip1 is symmetric in its last two
+// indices, evcont/ab_initio_gradients_loewdin.py:284): for a fixed (x, m) the n * np integrals are one
+// contiguous run that is dotted with the n rows (m, b) of W -- no index arithmetic in the loop.
+// Everything is read exactly once; the rows are staged with asynchronous 16-byte copies.
 // ---------------------------------------------------------------------------
 constexpr int kStreamThreads = 256;
 
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
-  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
-}
-
-// The three x/y/z rows (d_x m b|c d), m fixed, are contiguous runs of n^3 doubles: they are
-// staged in shared memory with asynchronous 16-byte copies (no register staging, so 7-8 CTAs
-// of ~27 KB in flight per SM), issued before anything that has to wait.
 __global__ void __launch_bounds__(kStreamThreads, 6)
 grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const double* __restrict__ Wg,
                    const double* __restrict__ OmS, const double* __restrict__ Pao,
                    const double* __restrict__ ipovlp, const double* __restrict__ hcore_deriv,
-                   const double* __restrict__ eri_ip1, const double* __restrict__ grad_nuc,
+                   const double* __restrict__ ip1p, const double* __restrict__ grad_nuc,
                    double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
-  const int np = npair_of(n), n2 = n * n, n3 = n2 * n;
-  const int n3p = (n3 + 1) & ~1, n2p = (n2 + 1) & ~1;
-  const int64_t n4 = static_cast<int64_t>(n3) * n;
-  double* stage = sm;                    // [3][n3p]  int2e_ip1 rows of the current m
-  double* hds = stage + 3 * n3p;         // [3][n2p]  d hcore / d(A, x)
-  double* Ws = hds + 3 * n2p;            // [n][np]   rows (m, b) of W
-  double* red = Ws + n * np;             // [3][8]
-  unsigned short* pidx = reinterpret_cast<unsigned short*>(red + 24);
+  const int np = npair_of(n), n2 = n * n, rl = n * np;  // rl: doubles of one (x, m) run
+  const int rlp = (rl + 1) & ~1, n2p = (n2 + 1) & ~1;
+  double* stage = sm;                    // [3][rlp]  runs (x, m, :, :) of the current m
+  double* hds = stage + 3 * rlp;         // [3][n2p]  d hcore / d(A, x)
+  double* Ws = hds + 3 * n2p;            // [n][np]   W[(m, b), (cd)]
+  double* red = Ws + rlp;                // [3][8]
   const int At = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
   const int p0 = aoslices[2 * At], p1 = aoslices[2 * At + 1];
   const double* W = Wg + static_cast<int64_t>(g) * np * np;
-  const double* ipg = eri_ip1 + static_cast<int64_t>(g) * 3 * n4;
+  const double* ipg = ip1p + static_cast<int64_t>(g) * 3 * n * rl;
   const double* hd = hcore_deriv + (static_cast<int64_t>(g) * natm + At) * 3 * n2;
-  const bool vec = ((n3 & 1) == 0);      // rows start 16-byte aligned iff n^3 is even
+  const bool vec = ((rl & 1) == 0);      // runs start 16-byte aligned iff n * np is even
 
+  // every global input of a row set as asynchronous copies: the three integral runs and the n rows
+  // (m, b) of W (stored as its lower triangle: an 8-byte gather)
   auto issue_rows = [&](int m) {
-    const double* r0 = ipg + static_cast<int64_t>(m) * n3;
+    const double* r0 = ipg + static_cast<int64_t>(m) * rl;
+    const int64_t xs = static_cast<int64_t>(n) * rl;  // stride between the x, y, z components
     if (vec) {
-      for (int e = 2 * tid; e < n3; e += 2 * kStreamThreads) {
+      for (int e = 2 * tid; e < rl; e += 2 * kStreamThreads) {
         cp_async16(stage + e, r0 + e);
-        cp_async16(stage + n3p + e, r0 + n4 + e);
-        cp_async16(stage + 2 * n3p + e, r0 + 2 * n4 + e);
+        cp_async16(stage + rlp + e, r0 + xs + e);
+        cp_async16(stage + 2 * rlp + e, r0 + 2 * xs + e);
       }
     } else {
-      for (int e = tid; e < n3; e += kStreamThreads) {
+      for (int e = tid; e < rl; e += kStreamThreads) {
         cp_async8(stage + e, r0 + e);
-        cp_async8(stage + n3p + e, r0 + n4 + e);
-        cp_async8(stage + 2 * n3p + e, r0 + 2 * n4 + e);
+        cp_async8(stage + rlp + e, r0 + xs + e);
+        cp_async8(stage + 2 * rlp + e, r0 + 2 * xs + e);
       }
     }
-  };
-  // rows (m, b), b < n, of W (stored as its lower triangle); pair index computed, not looked up,
-  // so the copies can be issued before any table exists
-  auto issue_w = [&](int m) {
     for (int b = tid >> 5; b < n; b += kStreamThreads / 32) {
       const int r = m >= b ? tri_idx(m, b) : tri_idx(b, m);
-      for (int c = tid & 31; c < np; c += 32) cp_async8(Ws + b * np + c, W + (r > c ? r * np + c : c * np + r));
+      for (int C = tid & 31; C < np; C += 32) cp_async8(Ws + b * np + C, W + (r > C ? r * np + C : C * np + r));
     }
   };
-  if (p0 < p1) {
-    issue_rows(p0);
-    issue_w(p0);
-  }
+  if (p0 < p1) issue_rows(p0);
   for (int k = tid; k < n2; k += kStreamThreads) {
     cp_async8(hds + k, hd + k);
     cp_async8(hds + n2p + k, hd + n2 + k);
@@ -751,9 +687,15 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
   }
   cp_async_commit_all();
 
-  for (int k = tid; k < n2; k += kStreamThreads) {
-    const int i = k / n, j = k - i * n;
-    pidx[k] = static_cast<unsigned short>(i >= j ? tri_idx(i, j) : tri_idx(j, i));
+  // weight of the packed pair (c >= d) of this thread's elements e = tid + k * kStreamThreads: 2 - delta_cd
+  constexpr int kMaxPer = 6;  // n * np <= 13 * 91 = 1183 < 6 * 256
+  double fac[kMaxPer];
+#pragma unroll
+  for (int k = 0; k < kMaxPer; ++k) {
+    const int e = tid + k * kStreamThreads;
+    int C = e % np, c = 0;
+    while (C > c) { C -= c + 1; ++c; }   // pair index -> (c, d = C)
+    fac[k] = (C == c) ? 1.0 : 2.0;
   }
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   {  // overlap term: - sum_{mu in A, nu} <d_x mu|nu> OmS[mu,nu]
@@ -766,12 +708,10 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
       a2 = fma(-i2, o, a2);
     }
   }
-  const float inv_n2 = 1.0f / static_cast<float>(n2);
   for (int m = p0; m < p1; ++m) {
     if (m > p0) {
       __syncthreads();  // Ws and stage of the previous m consumed
       issue_rows(m);
-      issue_w(m);
       cp_async_commit_all();
     }
     cp_async_wait_all();
@@ -786,15 +726,15 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
       }
     }
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll 2
-    for (int e = tid; e < n3; e += kStreamThreads) {
-      int b = static_cast<int>((static_cast<float>(e) + 0.5f) * inv_n2);
-      int cd = e - b * n2;
-      if (cd < 0) { --b; cd += n2; } else if (cd >= n2) { ++b; cd -= n2; }
-      const double w = Ws[b * np + pidx[cd]];
-      s0 = fma(stage[e], w, s0);
-      s1 = fma(stage[n3p + e], w, s1);
-      s2 = fma(stage[2 * n3p + e], w, s2);
+#pragma unroll
+    for (int k = 0; k < kMaxPer; ++k) {
+      const int e = tid + k * kStreamThreads;
+      if (e < rl) {
+        const double w = Ws[e] * fac[k];
+        s0 = fma(stage[e], w, s0);
+        s1 = fma(stage[rlp + e], w, s1);
+        s2 = fma(stage[2 * rlp + e], w, s2);
+      }
     }
     a0 -= 0.5 * s0;
     a1 -= 0.5 * s1;
@@ -830,10 +770,41 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
 }
 
 size_t grad_stream_smem_bytes(int n) {
-  const size_t n2 = static_cast<size_t>(n) * n, n3 = n2 * n;
-  return (3 * ((n3 + 1) & ~static_cast<size_t>(1)) + 3 * ((n2 + 1) & ~static_cast<size_t>(1)) +
-          static_cast<size_t>(n) * npair_of(n) + 24) * sizeof(double) +
-         (n2 * sizeof(unsigned short) + 15) / 16 * 16;
+  const size_t n2 = static_cast<size_t>(n) * n, rl = static_cast<size_t>(n) * npair_of(n);
+  const size_t rlp = (rl + 1) & ~static_cast<size_t>(1);
+  return (3 * rlp + 3 * ((n2 + 1) & ~static_cast<size_t>(1)) + rlp + 24) * sizeof(double);
+}
+
+// ---------------------------------------------------------------------------
+// int2e / int2e_ip1 as full tensors -> the packed arrays (callers that hold libcint-style tensors)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ao_pack8_kernel(int n, const double* __restrict__ eri, const double* __restrict__ eri_ip1,
+                double* __restrict__ erip, double* __restrict__ ip1p) {
+  const int g = blockIdx.y, np = npair_of(n), n2 = n * n;
+  const PGeom pg = pgeom(n);
+  const int64_t n4 = static_cast<int64_t>(n2) * n2;
+  const int64_t ne = static_cast<int64_t>(np) * np, ni = static_cast<int64_t>(3) * n2 * np;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < ne + ni;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (t < ne) {
+      if (erip == nullptr) continue;
+      const int AB = static_cast<int>(t / np), CD = static_cast<int>(t - static_cast<int64_t>(AB) * np);
+      int a, b, c, d;
+      tril_unrank_i(AB, a, b);
+      tril_unrank_i(CD, c, d);
+      erip[static_cast<int64_t>(g) * np * pg.pA + static_cast<int64_t>(AB) * pg.pA + CD] =
+          eri[static_cast<int64_t>(g) * n4 + (static_cast<int64_t>(a) * n + b) * n2 + c * n + d];
+    } else {
+      if (ip1p == nullptr) continue;
+      const int64_t u = t - ne;
+      const int64_t xmb = u / np;
+      const int CD = static_cast<int>(u - xmb * np);
+      int c, d;
+      tril_unrank_i(CD, c, d);
+      ip1p[static_cast<int64_t>(g) * ni + u] = eri_ip1[static_cast<int64_t>(g) * 3 * n4 + xmb * n2 + c * n + d];
+    }
+  }
 }
 
 size_t grad_smem_bytes(int n) {
@@ -903,8 +874,9 @@ __global__ void add_enuc_kernel_p(int G, const double* __restrict__ e0, const do
 
 // ---- internal entry points (common.cuh) -------------------------------------
 int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
-                      const double* eri, double* hvec, double* Tout) {
+                      const double* erip, double* hvec, double* Tout) {
   EVC_REQUIRE(n >= 1 && n <= kPackedMaxNorb, "packed_ao2oao: n=%d unsupported", n);
+  if (evc_packed_pipe_supported(n)) return evc_packed_ao2oao_pipe(ctx, nbatch, n, x, hcore, erip, hvec, Tout);
   const size_t smem = ao2oao_smem_bytes(n);
   EVC_REQUIRE(smem <= ctx->smem_optin, "packed_ao2oao: needs %zu bytes of shared memory", smem);
   const int64_t L8 = packed_len(n);
@@ -915,7 +887,7 @@ int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const do
     auto kern = packed_ao2oao_kernel<MI, NCV>;                                                       \
     EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                         static_cast<int>(smem)));                                    \
-    kern<<<nbatch, kThreads, smem, ctx->stream>>>(mf, ml, n, L8, x, hcore, eri, hvec, Tout);                 \
+    kern<<<nbatch, kThreads, smem, ctx->stream>>>(mf, ml, n, L8, x, hcore, erip, hvec, Tout);                 \
   }
   // compile-time orbital counts for the benchmark systems (H6, H10, H2O/6-31G), generic otherwise
   if (n == 6) EVC_CASE(1, 6) else if (n == 10) EVC_CASE(2, 10) else if (n == 13) EVC_CASE(5, 13)
@@ -929,9 +901,13 @@ int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const do
 int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* aoslices, const double* x,
                     const double* evals, const double* evecs, const double* hcore, const double* Tin,
                     const double* out7, const double* ipovlp, const double* hcore_deriv,
-                    const double* eri_ip1, const double* grad_nuc, double* Wg, double* OmS, double* Pao,
+                    const double* eri_ip1p, const double* grad_nuc, double* Wg, double* OmS, double* Pao,
                     double* grad) {
   EVC_REQUIRE(n >= 1 && n <= kPackedMaxNorb, "packed_grad: n=%d unsupported", n);
+  if (evc_packed_pipe_supported(n)) {
+    int rcp = evc_packed_grad_pipe(ctx, nbatch, n, x, evals, evecs, hcore, Tin, out7, Wg, OmS, Pao);
+    if (rcp) return rcp;
+  } else {
   const size_t smem = grad_smem_bytes(n);
   EVC_REQUIRE(smem <= ctx->smem_optin, "packed_grad: needs %zu bytes of shared memory", smem);
   const int64_t L8 = packed_len(n);
@@ -948,6 +924,7 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
   else if (mi <= 1) EVC_CASE(1, 0) else if (mi <= 2) EVC_CASE(2, 0) else EVC_CASE(3, 0)
 #undef EVC_CASE
   EVC_CHECK_LAUNCH();
+  }
   {
     int rcm = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM);
     if (rcm) return rcm;
@@ -958,7 +935,7 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
                                         cudaSharedmemCarveoutMaxShared));
     dim3 grid(natm, nbatch);
     grad_stream_kernel<<<grid, kStreamThreads, sm2, ctx->stream>>>(n, natm, aoslices, Wg, OmS, Pao, ipovlp,
-                                                                    hcore_deriv, eri_ip1, grad_nuc, grad);
+                                                                    hcore_deriv, eri_ip1p, grad_nuc, grad);
     EVC_CHECK_LAUNCH();
   }
   return 0;
@@ -1004,6 +981,23 @@ int evc_debug_phase_clocks(long long* out_host) {
 
 int64_t evc_packed_row_len(int n) { return n >= 1 ? packed_len(n) : -1; }
 
+int evc_erip_pitch(int n) { return n >= 1 ? pgeom(n).pA : -1; }
+int64_t evc_erip_len(int n) { return n >= 1 ? erip_len(n) : -1; }
+int64_t evc_eri_ip1p_len(int n) { return n >= 1 ? ip1p_len(n) : -1; }
+
+int evc_ao_pack8(evc_ctx* ctx, int nbatch, int n, const double* eri, const double* eri_ip1, double* erip,
+                 double* eri_ip1p) {
+  EVC_REQUIRE(ctx != nullptr && n >= 1 && n <= 64, "evc_ao_pack8: bad arguments (n=%d)", n);
+  EVC_REQUIRE((erip == nullptr) == (eri == nullptr) && (eri_ip1p == nullptr) == (eri_ip1 == nullptr),
+              "evc_ao_pack8: each output needs its input tensor");
+  if (nbatch <= 0 || (erip == nullptr && eri_ip1p == nullptr)) return 0;
+  const int64_t work = static_cast<int64_t>(npair_of(n)) * npair_of(n) + static_cast<int64_t>(3) * n * n * npair_of(n);
+  dim3 grid(static_cast<unsigned>(std::min<int64_t>((work + 255) / 256, 64)), nbatch);
+  ao_pack8_kernel<<<grid, 256, 0, ctx->stream>>>(n, eri, eri_ip1, erip, eri_ip1p);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
 int evc_stack_pack8(evc_ctx* ctx, int layout, int N, int n, const double* one_rdm, const double* two_rdm,
                     double* RH, double* RG) {
   EVC_REQUIRE(ctx && one_rdm && two_rdm && RH && RG, "evc_stack_pack8: NULL argument");
@@ -1044,8 +1038,11 @@ int evc_energy_with_grad_packed_workspace_bytes(int N, int n, int natm, int nbat
   tot += evc_align_up(evc_rows_dot_ws_bytes(L8, P, nbatch), 256);
   tot += evc_align_up(evc_rows_axpy_ws_bytes(L8, P, nbatch), 256);
   if (n <= kPackedMaxNorb) {
-    tot += 2 * evc_align_up(G * np * np * 8, 256); // T, W
-    tot += 2 * evc_align_up(G * n2 * 8, 256);      // OmS, Pao
+    tot += evc_align_up(G * erip_len(n) * 8, 256);  // T ([np][pA], like erip)
+    tot += evc_align_up(G * np * np * 8, 256);      // W
+    tot += 2 * evc_align_up(G * n2 * 8, 256);       // OmS, Pao
+    // room for the packed copies of int2e / int2e_ip1 when the caller passes the full tensors
+    tot += evc_align_up(G * erip_len(n) * 8, 256) + evc_align_up(G * ip1p_len(n) * 8, 256);
   } else {
     size_t gb = 0;
     int rc = evc_grad_workspace_bytes(n, natm, nbatch, &gb);
@@ -1065,17 +1062,19 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
   // grad == NULL: energies (and Cvec) only -- the approximate_ground_state_OAO part of the step (K3, K4, K5, K6),
   // evcont/ab_initio_eigenvector_continuation.py:178-211; the derivative arrays of the bundle are not read
   const bool want_grad = grad != nullptr;
-  EVC_REQUIRE(ao->ovlp && ao->hcore && ao->eri, "evc_energy_with_grad_packed: incomplete AO bundle");
-  EVC_REQUIRE(!want_grad || (ao->ipovlp && ao->hcore_deriv && ao->eri_ip1 && ao->aoslices),
-              "evc_energy_with_grad_packed: incomplete AO bundle (derivative arrays)");
   EVC_REQUIRE(n >= 1 && n <= 32 && N >= 1 && N <= 112, "evc_energy_with_grad_packed: n=%d N=%d unsupported", n, N);
+  const bool small = n <= kPackedMaxNorb;
+  // two-electron arrays: packed (erip / eri_ip1p) or full tensors (eri / eri_ip1); n > 13 needs the tensors
+  EVC_REQUIRE(ao->ovlp && ao->hcore && (ao->eri || (small && ao->erip)),
+              "evc_energy_with_grad_packed: incomplete AO bundle");
+  EVC_REQUIRE(!want_grad || (ao->ipovlp && ao->hcore_deriv && ao->aoslices && (ao->eri_ip1 || (small && ao->eri_ip1p))),
+              "evc_energy_with_grad_packed: incomplete AO bundle (derivative arrays)");
   if (nbatch <= 0) return 0;
   const size_t G = static_cast<size_t>(nbatch);
   const size_t n2 = static_cast<size_t>(n) * n, n4 = n2 * n2;
   const int64_t L8 = packed_len(n);
   const int P = N * (N + 1) / 2;
   const size_t np = npair_of(n);
-  const bool small = n <= kPackedMaxNorb;
   const size_t dot_b = evc_rows_dot_ws_bytes(L8, P, nbatch), axpy_b = evc_rows_axpy_ws_bytes(L8, P, nbatch);
   evc_arena ar(workspace, workspace_bytes);
   double* X = ar.take<double>(G * n2);
@@ -1096,12 +1095,26 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
   char* grad_ws = nullptr;
   size_t grad_b = 0;
   int rc;
+  const double* erip = ao->erip;
+  const double* ip1p = ao->eri_ip1p;
   if (small) {
-    T = ar.take<double>(G * np * np);
+    T = ar.take<double>(G * erip_len(n));
     Wg = ar.take<double>(G * np * np);
     OmS = ar.take<double>(G * n2);
     Pao = ar.take<double>(G * n2);
     EVC_REQUIRE(T && Wg && OmS && Pao, "evc_energy_with_grad_packed: workspace too small (%zu bytes)", workspace_bytes);
+    // callers holding the full libcint-style tensors: pack them first (one extra streaming pass)
+    const bool need_e = erip == nullptr, need_i = want_grad && ip1p == nullptr;
+    if (need_e || need_i) {
+      double* ep = need_e ? ar.take<double>(G * erip_len(n)) : nullptr;
+      double* ipp = need_i ? ar.take<double>(G * ip1p_len(n)) : nullptr;
+      EVC_REQUIRE((!need_e || ep) && (!need_i || ipp), "evc_energy_with_grad_packed: workspace too small (%zu bytes)",
+                  workspace_bytes);
+      if ((rc = evc_ao_pack8(ctx, nbatch, n, need_e ? ao->eri : nullptr, need_i ? ao->eri_ip1 : nullptr, ep, ipp)))
+        return rc;
+      if (need_e) erip = ep;
+      if (need_i) ip1p = ipp;
+    }
   } else {
     if ((rc = evc_grad_workspace_bytes(n, natm, nbatch, &grad_b))) return rc;
     h1 = ar.take<double>(G * n2);
@@ -1119,7 +1132,7 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
   if ((rc = evc_loewdin(ctx, nbatch, n, ao->ovlp, X, evals, evecs))) return rc;
   if ((rc = evc_stage_mark(ctx, EVC_STAGE_AO2OAO))) return rc;
   if (small) {
-    if ((rc = evc_packed_ao2oao(ctx, nbatch, n, X, ao->hcore, ao->eri, hvec, T))) return rc;
+    if ((rc = evc_packed_ao2oao(ctx, nbatch, n, X, ao->hcore, erip, hvec, T))) return rc;
   } else {
     if ((rc = evc_ao2oao(ctx, nbatch, n, ao->hcore, ao->eri, X, 0, h1, h2, t3, scratch, evc_align_up(G * n4 * 8, 256)))) return rc;
     if ((rc = evc_packed_hvec_from_full(ctx, nbatch, n, h1, h2, hvec))) return rc;
@@ -1135,7 +1148,7 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
     if ((rc = evc_stage_mark(ctx, EVC_STAGE_GRAD))) return rc;
     if (small) {
       if ((rc = evc_packed_grad(ctx, nbatch, n, natm, ao->aoslices, X, evals, evecs, ao->hcore, T, out7, ao->ipovlp,
-                                ao->hcore_deriv, ao->eri_ip1, ao->grad_nuc, Wg, OmS, Pao, grad)))
+                                ao->hcore_deriv, ip1p, ao->grad_nuc, Wg, OmS, Pao, grad)))
         return rc;
     } else {
       if ((rc = evc_packed_unpack_rdms(ctx, nbatch, n, out7, gamma, Gamma8))) return rc;

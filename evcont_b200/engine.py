@@ -309,29 +309,53 @@ class Engine:
             self._sbases[key] = SBasis(self, symbols, basis)
         return self._sbases[key]
 
-    def ao_integrals(self, sbasis, coords, out=None):
+    def ao_integrals(self, sbasis, coords, out=None, packed=False):
         """AO integrals of a batch of geometries on the device: ``coords`` (G, natm, 3) in
-        bohr (device tensor or numpy) -> :class:`DeviceAO` (filled in place if given)."""
+        bohr (device tensor or numpy) -> :class:`DeviceAO` (filled in place if given).
+        ``packed`` (s-shell bases): emit the two-electron arrays in the packed layouts
+        (``evc_ao_integrals_s_packed``); with ``out`` given, its own ``packed`` flag decides."""
         coords = self.to_device(coords).reshape(-1, sbasis.natm, 3)
         G = coords.shape[0]
-        ao = out if out is not None else DeviceAO(self, G, sbasis.nao, sbasis.natm, sbasis.aoslices_host)
+        if out is None:
+            packed = bool(packed) and not sbasis.general
+            ao = DeviceAO(self, G, sbasis.nao, sbasis.natm, sbasis.aoslices_host, packed=packed)
+        else:
+            ao = out
         if ao.nbatch != G or ao.nao != sbasis.nao or ao.natm != sbasis.natm:
             raise ValueError("DeviceAO does not match the basis / batch size")
+        if ao.packed and sbasis.general:
+            raise ValueError("packed integral output exists for s-shell bases only (use DeviceAO.to_packed())")
         nbytes = C.c_size_t()
-        ws_fn, fn = ((self.lib.evc_ao_integrals_sp_workspace_bytes, self.lib.evc_ao_integrals_sp) if sbasis.general
-                     else (self.lib.evc_ao_integrals_s_workspace_bytes, self.lib.evc_ao_integrals_s))
+        if sbasis.general:
+            ws_fn, fn = self.lib.evc_ao_integrals_sp_workspace_bytes, self.lib.evc_ao_integrals_sp
+        else:
+            ws_fn = self.lib.evc_ao_integrals_s_workspace_bytes
+            fn = self.lib.evc_ao_integrals_s_packed if ao.packed else self.lib.evc_ao_integrals_s
         check(ws_fn(sbasis.handle, G, C.byref(nbytes)))
         ws = self.workspace(nbytes.value)
         self._bind_stream()
-        check(fn(self._ctx, sbasis.handle, G, _ptr(coords), _ptr(ao.ovlp), _ptr(ao.hcore), _ptr(ao.eri),
-                 _ptr(ao.ipovlp), _ptr(ao.hcore_deriv), _ptr(ao.eri_ip1), _ptr(ao.e_nuc), _ptr(ao.grad_nuc),
+        e2, d2 = (ao.erip, ao.eri_ip1p) if ao.packed else (ao.eri, ao.eri_ip1)
+        check(fn(self._ctx, sbasis.handle, G, _ptr(coords), _ptr(ao.ovlp), _ptr(ao.hcore), _ptr(e2),
+                 _ptr(ao.ipovlp), _ptr(ao.hcore_deriv), _ptr(d2), _ptr(ao.e_nuc), _ptr(ao.grad_nuc),
                  _ptr(ws), ws.numel()))
         return ao
+
+    def ao_pack8(self, eri=None, eri_ip1=None):
+        """Device: full ``int2e (G, n, n, n, n)`` / ``int2e_ip1 (G, 3, n, n, n, n)`` -> packed
+        ``(erip, eri_ip1p)`` (``evc_ao_pack8``); either may be ``None``."""
+        src = eri if eri is not None else eri_ip1
+        G, n = src.shape[0], src.shape[-1]
+        shp = ao_shapes(G, n, 1, True)
+        erip = self.empty(*shp["erip"]) if eri is not None else None
+        ip1p = self.empty(*shp["eri_ip1p"]) if eri_ip1 is not None else None
+        self._bind_stream()
+        check(self.lib.evc_ao_pack8(self._ctx, G, n, _ptr(eri), _ptr(eri_ip1), _ptr(erip), _ptr(ip1p)))
+        return erip, ip1p
 
     def energy_with_grad_coords(self, stack, sbasis, coords, ao=None, out=None, want_rdms=False):
         """The whole MD step from nuclear coordinates: K9 (integrals) then K3..K8.
         ``coords`` (G, natm, 3) bohr.  Same return value as :meth:`energy_with_grad`."""
-        ao = self.ao_integrals(sbasis, coords, out=ao)
+        ao = self.ao_integrals(sbasis, coords, out=ao, packed=(sbasis.nao <= 13 and not want_rdms))
         return self.energy_with_grad(stack, ao, want_rdms=want_rdms, out=out)
 
     def energies(self, stack, ao, out=None):
@@ -391,6 +415,9 @@ class Engine:
         else:
             E, grad, cvec = out
         packed = (USE_PACKED if packed is None else packed) and not want_rdms
+        if getattr(ao, "packed", False) and not (packed and n <= 13):
+            raise ValueError("packed AO arrays (erip / eri_ip1p) feed the packed step for n <= 13 only; "
+                             "compute the full tensors for want_rdms / packed=False / larger n")
         if packed:
             rh, rg = stack.packed()
             nbytes = C.c_size_t()
@@ -576,38 +603,43 @@ class HostAO:
     :meth:`Engine.energy_with_grad_host`.  Fields as in :class:`DeviceAO`."""
 
     FIELDS = ("ovlp", "hcore", "eri", "ipovlp", "hcore_deriv", "eri_ip1", "e_nuc", "grad_nuc")
+    PACKED_FIELDS = ("ovlp", "hcore", "erip", "ipovlp", "hcore_deriv", "eri_ip1p", "e_nuc", "grad_nuc")
 
-    def __init__(self, nbatch, nao, natm, aoslices, pin=True):
-        n = nao
+    def __init__(self, nbatch, nao, natm, aoslices, pin=True, packed=False):
         self.nbatch, self.nao, self.natm = nbatch, nao, natm
-        self.shapes = dict(ovlp=(nbatch, n, n), hcore=(nbatch, n, n), eri=(nbatch, n, n, n, n),
-                           ipovlp=(nbatch, 3, n, n), hcore_deriv=(nbatch, natm, 3, n, n),
-                           eri_ip1=(nbatch, 3, n, n, n, n), e_nuc=(nbatch,),
-                           grad_nuc=(nbatch, natm, 3))
+        self.packed = bool(packed)
+        self.fields = self.PACKED_FIELDS if self.packed else self.FIELDS
+        self.shapes = ao_shapes(nbatch, nao, natm, self.packed)
         pin = bool(pin and torch.cuda.is_available())
-        for k, shp in self.shapes.items():
-            setattr(self, k, torch.empty(shp, dtype=torch.float64, pin_memory=pin))
+        self.eri = self.eri_ip1 = self.erip = self.eri_ip1p = None
+        for k in self.fields:
+            t = torch.empty(self.shapes[k], dtype=torch.float64, pin_memory=pin)
+            if k == "erip":
+                t.zero_()
+            setattr(self, k, t)
         self.aoslices = torch.from_numpy(
             np.ascontiguousarray(aoslices, dtype=np.int32).reshape(natm, 2).copy())
         self.E = torch.empty(nbatch, dtype=torch.float64, pin_memory=pin)
         self.grad = torch.empty(nbatch, natm, 3, dtype=torch.float64, pin_memory=pin)
 
     @classmethod
-    def from_bundles(cls, bundles, pin=True):
+    def from_bundles(cls, bundles, pin=True, packed=False):
         b0 = bundles[0]
-        self = cls(len(bundles), b0["nao"], b0["natm"], b0["aoslices"], pin=pin)
-        for k in cls.FIELDS:
-            dst = getattr(self, k).numpy()
-            for g, b in enumerate(bundles):
-                dst[g] = np.asarray(b[k], dtype=np.float64).reshape(self.shapes[k][1:])
+        self = cls(len(bundles), b0["nao"], b0["natm"], b0["aoslices"], pin=pin, packed=packed)
+        for g, b in enumerate(bundles):
+            src = dict(b)
+            if packed:
+                src["erip"], src["eri_ip1p"] = pack_ao_host(np.asarray(b["eri"]), np.asarray(b["eri_ip1"]))
+            for k in self.fields:
+                getattr(self, k).numpy()[g] = np.asarray(src[k], dtype=np.float64).reshape(self.shapes[k][1:])
         return self
 
     def nbytes(self):
-        return sum(getattr(self, k).numel() * 8 for k in self.FIELDS)
+        return sum(getattr(self, k).numel() * 8 for k in self.fields)
 
     def bundle(self):
         b = AoBundle()
-        for k in self.FIELDS:
+        for k in self.fields:
             setattr(b, k, getattr(self, k).data_ptr())
         b.aoslices = self.aoslices.data_ptr()
         return b
@@ -667,19 +699,24 @@ class DeviceStack:
 
 
 class DeviceAO:
-    """AO arrays of a batch of geometries on the device (the ``evc_ao_bundle``)."""
+    """AO arrays of a batch of geometries on the device (the ``evc_ao_bundle``).
+
+    ``packed=True`` holds the two-electron arrays in the packed layouts of the bundle
+    (``erip (G, np, pitch)``, ``eri_ip1p (G, 3, n, n, np)``, np = n(n+1)/2) instead of the full
+    tensors ``eri`` / ``eri_ip1`` -- what ``evc_ao_integrals_s_packed`` emits and the packed
+    prediction step reads directly (n <= 13)."""
 
     FIELDS = ("ovlp", "hcore", "eri", "ipovlp", "hcore_deriv", "eri_ip1", "e_nuc", "grad_nuc")
+    PACKED_FIELDS = ("ovlp", "hcore", "erip", "ipovlp", "hcore_deriv", "eri_ip1p", "e_nuc", "grad_nuc")
 
-    def __init__(self, engine, nbatch, nao, natm, aoslices):
+    def __init__(self, engine, nbatch, nao, natm, aoslices, packed=False):
         self.engine, self.nbatch, self.nao, self.natm = engine, nbatch, nao, natm
-        n = nao
-        shapes = dict(ovlp=(nbatch, n, n), hcore=(nbatch, n, n), eri=(nbatch, n, n, n, n),
-                      ipovlp=(nbatch, 3, n, n), hcore_deriv=(nbatch, natm, 3, n, n),
-                      eri_ip1=(nbatch, 3, n, n, n, n), e_nuc=(nbatch,), grad_nuc=(nbatch, natm, 3))
-        self.shapes = shapes
-        for k, shp in shapes.items():
-            setattr(self, k, engine.empty(*shp))
+        self.packed = bool(packed)
+        self.shapes = ao_shapes(nbatch, nao, natm, self.packed)
+        self.fields = self.PACKED_FIELDS if self.packed else self.FIELDS
+        self.eri = self.eri_ip1 = self.erip = self.eri_ip1p = None
+        for k in self.fields:
+            setattr(self, k, engine.empty(*self.shapes[k]))
         self.aoslices = torch.from_numpy(
             np.ascontiguousarray(aoslices, dtype=np.int32).reshape(natm, 2)).to(engine.device)
 
@@ -693,12 +730,56 @@ class DeviceAO:
             getattr(self, k).copy_(torch.from_numpy(host.reshape(self.shapes[k])))
         return self
 
+    def to_packed(self):
+        """A packed copy (``evc_ao_pack8`` for the two-electron arrays; the small arrays are shared)."""
+        if self.packed:
+            return self
+        out = DeviceAO.__new__(DeviceAO)
+        out.engine, out.nbatch, out.nao, out.natm = self.engine, self.nbatch, self.nao, self.natm
+        out.packed, out.fields = True, self.PACKED_FIELDS
+        out.shapes = ao_shapes(self.nbatch, self.nao, self.natm, True)
+        out.eri = out.eri_ip1 = None
+        for k in ("ovlp", "hcore", "ipovlp", "hcore_deriv", "e_nuc", "grad_nuc"):
+            setattr(out, k, getattr(self, k))
+        out.aoslices = self.aoslices
+        out.erip, out.eri_ip1p = self.engine.ao_pack8(self.eri, self.eri_ip1)
+        return out
+
     def nbytes(self):
-        return sum(getattr(self, k).numel() * 8 for k in self.FIELDS)
+        return sum(getattr(self, k).numel() * 8 for k in self.fields)
 
     def bundle(self):
         b = AoBundle()
-        for k in self.FIELDS:
+        for k in self.fields:
             setattr(b, k, getattr(self, k).data_ptr())
         b.aoslices = self.aoslices.data_ptr()
         return b
+
+
+def ao_shapes(nbatch, n, natm, packed=False):
+    """Shapes of the ``evc_ao_bundle`` arrays of ``nbatch`` geometries."""
+    shp = dict(ovlp=(nbatch, n, n), hcore=(nbatch, n, n), ipovlp=(nbatch, 3, n, n),
+               hcore_deriv=(nbatch, natm, 3, n, n), e_nuc=(nbatch,), grad_nuc=(nbatch, natm, 3))
+    if packed:
+        npair = n * (n + 1) // 2
+        shp.update(erip=(nbatch, npair, int(_lib.lib().evc_erip_pitch(n))), eri_ip1p=(nbatch, 3, n, n, npair))
+    else:
+        shp.update(eri=(nbatch, n, n, n, n), eri_ip1=(nbatch, 3, n, n, n, n))
+    return shp
+
+
+def pack_ao_host(eri, eri_ip1):
+    """numpy: full ``int2e (..., n, n, n, n)`` / ``int2e_ip1 (..., 3, n, n, n, n)`` -> the packed host arrays
+    ``erip (..., np, pitch)`` (padding columns zero), ``eri_ip1p (..., 3, n, n, np)``.  Either may be ``None``."""
+    erip = ip1p = None
+    src = eri if eri is not None else eri_ip1
+    n = src.shape[-1]
+    ii, jj = np.tril_indices(n)
+    if eri is not None:
+        pitch = int(_lib.lib().evc_erip_pitch(n))
+        pk = np.asarray(eri)[..., ii, jj, :, :][..., ii, jj]
+        erip = np.zeros(pk.shape[:-1] + (pitch,))
+        erip[..., : pk.shape[-1]] = pk
+    if eri_ip1 is not None:
+        ip1p = np.ascontiguousarray(np.asarray(eri_ip1)[..., ii, jj])
+    return erip, ip1p

@@ -50,7 +50,8 @@ class DeviceNVE:
         self.epot, self.ekin = eng.empty(B), eng.empty(B)
         self.grad, self.cvec = eng.empty(B, natm, 3), eng.empty(B, N)
         from .engine import DeviceAO
-        self.ao = DeviceAO(eng, B, self.sbasis.nao, natm, self.sbasis.aoslices_host)
+        self.ao = DeviceAO(eng, B, self.sbasis.nao, natm, self.sbasis.aoslices_host,
+                           packed=(self.sbasis.nao <= 13 and not self.sbasis.general))
         self.max_frames = int(max_frames)
         self.frame_idx = torch.zeros(1, dtype=torch.int32, device=eng.device)
         mf = max(1, self.max_frames)

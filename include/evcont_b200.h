@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EVC_ABI_VERSION 1
+#define EVC_ABI_VERSION 2
 
 typedef struct evc_ctx evc_ctx;
 
@@ -210,6 +210,16 @@ typedef struct {
   const double *e_nuc;       /* [nbatch]                                    */
   const double *grad_nuc;    /* [nbatch][natm][3]                           */
   const int32_t *aoslices;   /* [natm][2] (ao start, ao stop), shared       */
+  /* Packed two-electron arrays (ABI 2) -- the fast inputs of the packed step (n <= 13); when
+   * set, `eri` / `eri_ip1` may be NULL.  What the device integral kernels emit directly
+   * (evc_ao_integrals_s_packed) and what evc_ao_pack8 makes from the full tensors:
+   *   erip     [nbatch][np][evc_erip_pitch(n)]  erip[AB][CD] = (ab|cd), a >= b, c >= d,
+   *            AB = a(a+1)/2 + b, np = n(n+1)/2; the columns [np, pitch) are padding (ignored)
+   *   eri_ip1p [nbatch][3][n][n][np]            (d_x m b|c d), CD = c(c+1)/2 + d, c >= d
+   * (int2e has the 8-fold symmetry, int2e_ip1 is symmetric in its last two indices:
+   * evcont/ab_initio_gradients_loewdin.py:283-284.) */
+  const double *erip;
+  const double *eri_ip1p;
 } evc_ao_bundle;
 
 int evc_energy_with_grad_workspace_bytes(int layout, int ntrain, int n, int natm,
@@ -244,6 +254,13 @@ int evc_energy_with_grad(evc_ctx *ctx, int layout, int ntrain, int n, int natm,
  *   (ab_initio_eigenvector_continuation.py:178-211); the derivative arrays of the bundle
  *   are not read then. */
 int64_t evc_packed_row_len(int n);
+/* layout of the packed AO two-electron arrays of evc_ao_bundle: row pitch / doubles per geometry */
+int evc_erip_pitch(int n);
+int64_t evc_erip_len(int n);     /* np * pitch       */
+int64_t evc_eri_ip1p_len(int n); /* 3 * n * n * np   */
+/* int2e [nbatch][n^4] -> erip, int2e_ip1 [nbatch][3][n^4] -> eri_ip1p (either pair may be NULL) */
+int evc_ao_pack8(evc_ctx *ctx, int nbatch, int n, const double *eri, const double *eri_ip1,
+                 double *erip, double *eri_ip1p);
 int evc_stack_pack8(evc_ctx *ctx, int layout, int ntrain, int n, const double *one_rdm,
                     const double *two_rdm, double *RH, double *RG);
 int evc_energy_with_grad_packed_workspace_bytes(int ntrain, int n, int natm, int nbatch,
@@ -312,6 +329,14 @@ int evc_ao_integrals_s(evc_ctx *ctx, const evc_sbasis *basis, int nbatch, const 
                        double *ovlp, double *hcore, double *eri, double *ipovlp,
                        double *hcore_deriv, double *eri_ip1, double *e_nuc, double *grad_nuc,
                        void *workspace, size_t workspace_bytes);
+/* The same with the two-electron arrays emitted directly in the packed layouts of evc_ao_bundle
+ * (erip [nbatch][np][evc_erip_pitch(n)], eri_ip1p [nbatch][3][n][n][np]): every contracted quartet
+ * is stored once per symmetry-distinct position instead of eight times, and the prediction step
+ * reads 2.2x fewer bytes. */
+int evc_ao_integrals_s_packed(evc_ctx *ctx, const evc_sbasis *basis, int nbatch,
+                              const double *coords, double *ovlp, double *hcore, double *erip,
+                              double *ipovlp, double *hcore_deriv, double *eri_ip1p, double *e_nuc,
+                              double *grad_nuc, void *workspace, size_t workspace_bytes);
 
 /* ---- device-resident velocity Verlet (batched over trajectories) ------------------
  * Replaces the host loop of pyscf.md.NVE that get_trajectory drives

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(handle, name), f"{name} declared in the header but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert _lib.lib().evc_abi_version() == 1
+    assert _lib.lib().evc_abi_version() == 2
 
 
 @pytest.mark.parametrize("norb,nocc", [(1, 0), (1, 1), (2, 1), (4, 2), (5, 3), (6, 3), (8, 4),

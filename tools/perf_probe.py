@@ -113,6 +113,8 @@ def probe_step(args):
     stack = DeviceStack(S, one, two, engine=eng, norb=n)
     base = [ao_bundle(synthetic_mol(n, natm, seed=50 + k)) for k in range(min(G, 8))]
     ao = DeviceAO.from_bundles(eng, [base[g % len(base)] for g in range(G)])
+    if args.packed:
+        ao = ao.to_packed()
     out = (eng.empty(G), eng.empty(G, natm, 3), eng.empty(G, N))
     for _ in range(3):
         eng.energy_with_grad(stack, ao, out=out)
@@ -121,7 +123,7 @@ def probe_step(args):
     ms = timed(torch, lambda: eng.energy_with_grad(stack, ao, out=out), args.reps, warm=0)
     stage, calls = eng.stage_times()
     eng.stage_timing(False)
-    print(json.dumps({"probe": "step", "norb": n, "natm": natm, "ntrain": N, "layout": args.layout, "batch": G,
+    print(json.dumps({"probe": "step", "packed_ao": bool(args.packed), "pipe": os.environ.get("EVC_PACKED_PIPE", "1"), "norb": n, "natm": natm, "ntrain": N, "layout": args.layout, "batch": G,
                       "ms": ms, "steps_per_s": G / ms * 1e3,
                       "stage_ms": {k: v / max(1, calls) for k, v in stage.items()}}), flush=True)
 
@@ -193,6 +195,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--basis", default="sto-6g")
+    ap.add_argument("--packed", action="store_true", help="step: hand the packed AO arrays (erip / eri_ip1p) in")
     args = ap.parse_args()
     {"trdm": probe_trdm, "stack": probe_stack, "step": probe_step, "ints": probe_ints, "ints_sp": probe_ints_sp}[args.probe](args)
 
