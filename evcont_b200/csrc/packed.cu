@@ -649,6 +649,7 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
   double* hds = stage + 3 * rlp;         // [3][n2p]  d hcore / d(A, x)
   double* Ws = hds + 3 * n2p;            // [n][np]   W[(m, b), (cd)]
   double* red = Ws + rlp;                // [3][8]
+  double* facs = red + 24;               // [np]
   const int At = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
   const int p0 = aoslices[2 * At], p1 = aoslices[2 * At + 1];
   const double* W = Wg + static_cast<int64_t>(g) * np * np;
@@ -687,16 +688,11 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
   }
   cp_async_commit_all();
 
-  // weight of the packed pair (c >= d) of this thread's elements e = tid + k * kStreamThreads: 2 - delta_cd
-  constexpr int kMaxPer = 6;  // n * np <= 13 * 91 = 1183 < 6 * 256
-  double fac[kMaxPer];
-#pragma unroll
-  for (int k = 0; k < kMaxPer; ++k) {
-    const int e = tid + k * kStreamThreads;
-    int C = e % np, c = 0;
-    while (C > c) { C -= c + 1; ++c; }   // pair index -> (c, d = C)
-    fac[k] = (C == c) ? 1.0 : 2.0;
-  }
+  // weight of the packed pair (c >= d): 2 - delta_cd, as a table over the pair index
+  for (int C = tid; C < np; C += kStreamThreads) facs[C] = 2.0;
+  __syncthreads();
+  if (tid < n) facs[tid * (tid + 3) / 2] = 1.0;   // diagonal pairs (c, c)
+  const int c_first = tid % np, c_step = kStreamThreads % np;  // pair index of element tid + k * kStreamThreads
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   {  // overlap term: - sum_{mu in A, nu} <d_x mu|nu> OmS[mu,nu]
     const double* ipo = ipovlp + static_cast<int64_t>(g) * 3 * n2;
@@ -726,15 +722,14 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
       }
     }
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-    for (int k = 0; k < kMaxPer; ++k) {
-      const int e = tid + k * kStreamThreads;
-      if (e < rl) {
-        const double w = Ws[e] * fac[k];
-        s0 = fma(stage[e], w, s0);
-        s1 = fma(stage[rlp + e], w, s1);
-        s2 = fma(stage[2 * rlp + e], w, s2);
-      }
+    int C = c_first;
+    for (int e = tid; e < rl; e += kStreamThreads) {
+      const double w = Ws[e] * facs[C];
+      s0 = fma(stage[e], w, s0);
+      s1 = fma(stage[rlp + e], w, s1);
+      s2 = fma(stage[2 * rlp + e], w, s2);
+      C += c_step;
+      if (C >= np) C -= np;
     }
     a0 -= 0.5 * s0;
     a1 -= 0.5 * s1;
@@ -772,7 +767,7 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
 size_t grad_stream_smem_bytes(int n) {
   const size_t n2 = static_cast<size_t>(n) * n, rl = static_cast<size_t>(n) * npair_of(n);
   const size_t rlp = (rl + 1) & ~static_cast<size_t>(1);
-  return (3 * rlp + 3 * ((n2 + 1) & ~static_cast<size_t>(1)) + rlp + 24) * sizeof(double);
+  return (3 * rlp + 3 * ((n2 + 1) & ~static_cast<size_t>(1)) + rlp + 24 + npair_of(n) + 1) * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------
