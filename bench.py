@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dgemm-peak", action="store_true")
     ap.add_argument("--no-coords", action="store_true", help="skip the from-coordinates leg (K9)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the single-GPU diagnostics (latency, stack streaming, other trans-RDM sizes)")
     ap.add_argument("--no-settle", action="store_true",
                     help="skip the 0.4 s clock-settling loop (for runs under ncu)")
     return ap.parse_args()
@@ -73,22 +75,27 @@ def civecs(ntrain):
 
 
 def host_ao_batch(G, seed0, pin):
-    """G seeded synthetic geometries as one pinned-host HostAO batch."""
+    """G seeded synthetic geometries as one pinned-host HostAO batch in the packed two-electron layouts
+    (erip / eri_ip1p: what the device integral kernel emits; built here with pack_ao_host)."""
     import torch
-    from evcont_b200.engine import HostAO
+    from evcont_b200.engine import HostAO, pack_ao_host
     from evcont_b200.mol import ao_bundle, synthetic_mol
     n, natm = NORB, NATM
     b0 = ao_bundle(synthetic_mol(n, natm, seed=seed0))
-    hao = HostAO(G, n, natm, b0["aoslices"], pin=pin)
+    hao = HostAO(G, n, natm, b0["aoslices"], pin=pin, packed=True)
     shapes = hao.shapes
-    host = {k: getattr(hao, k) for k in shapes}
+    host = {k: getattr(hao, k) for k in hao.fields}
     # distinct geometries are cheap to draw but slow to draw by the thousand in
     # Python: draw up to 64 and tile them with a per-geometry scale so no two are equal
-    base = [ao_bundle(synthetic_mol(n, natm, seed=seed0 + k)) for k in range(min(G, 64))]
+    base = []
+    for k in range(min(G, 64)):
+        b = dict(ao_bundle(synthetic_mol(n, natm, seed=seed0 + k)))
+        b["erip"], b["eri_ip1p"] = pack_ao_host(np.asarray(b["eri"]), np.asarray(b["eri_ip1"]))
+        base.append(b)
     for g in range(G):
         b = base[g % len(base)]
         f = 1.0 + 1.0e-3 * (g // len(base))
-        for k in shapes:
+        for k in hao.fields:
             src = np.asarray(b[k], dtype=np.float64)
             if k in ("hcore", "hcore_deriv", "e_nuc", "grad_nuc"):
                 src = src * f
@@ -260,35 +267,41 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------
-STAGE_WORK = {
-    # stage: (bound, flop per geometry, algorithmic HBM bytes per geometry, per-launch bytes)
-}
+STAGE_KERNEL = {"loewdin": "loewdin_kernel", "ao2oao": "ao2oao_pipe_kernel", "subspace_H": "dgemm_kernel (NT)",
+                "geneig": "geneig_lowest_kernel", "predict_rdm": "dgemm_kernel (NN)", "grad": "grad_pipe_kernel",
+                "grad_stream": "grad_stream_kernel"}
 
 
-def stage_work(n, natm, ntrain, G):
+def stage_work(n, natm, ntrain, G, pitch):
     """Algorithmic work of each stage of the packed prediction step for a batch of G
     geometries: flops on the FP64 tensor cores for the GEMM-shaped
-    stages, bytes that have to cross HBM for the streaming ones."""
-    n2, n4 = n * n, n ** 4
+    stages, bytes that have to cross HBM for the streaming ones.  The two-electron inputs
+    are the packed arrays erip [np][pitch] and eri_ip1p [3][n][n][np]."""
+    n2 = n * n
     npair = n * (n + 1) // 2
     L8 = n2 + npair * (npair + 1) // 2
     P = ntrain * (ntrain + 1) // 2
     stack_bytes = 8 * P * L8
     return {
-        "loewdin": dict(bound="hbm", flops=G * 30 * n ** 3, bytes=G * 8 * (4 * n2 + n)),
-        # T = ERIp Q (np^3 MACs) + lower triangle of Q^T T; reads the i>=j rows of the AO ERIs
+        "loewdin": dict(bound="latency", flops=G * 30 * n ** 3, bytes=G * 8 * (4 * n2 + n)),
+        # T = ERIp Q (np^3 MACs) + lower triangle of Q^T T; reads erip, writes T and hvec
         "ao2oao": dict(bound="tensor", flops=G * (2 * npair ** 3 + npair * npair * (npair + 1)),
-                       bytes=G * 8 * (npair * n2 + npair * npair + L8)),
+                       bytes=G * 8 * (2 * npair * pitch + L8 + 2 * n2)),
         "subspace_H": dict(bound="tensor", flops=G * 2 * P * L8, bytes=stack_bytes + G * 8 * (L8 + P)),
-        "geneig": dict(bound="hbm", flops=G * 4 * ntrain ** 3, bytes=G * 8 * (P + ntrain)),
+        "geneig": dict(bound="latency", flops=G * 4 * ntrain ** 3, bytes=G * 8 * (P + ntrain)),
         "predict_rdm": dict(bound="tensor", flops=G * 2 * P * L8, bytes=stack_bytes + G * 8 * (L8 + P)),
-        # U0 = T Gm, R = Gm P0^T, lower triangle of W = P0 R
+        # U0 = T Gm, R = Gm P0^T, lower triangle of W = P0 R; reads T and out7, writes W
         "grad": dict(bound="tensor", flops=G * (4 * npair ** 3 + npair * npair * (npair + 1)),
-                     bytes=G * 8 * (2 * npair * npair + L8 + 6 * n2)),
-        # int2e_ip1 + core-Hamiltonian derivative + int1e_ipovlp read once, W rows once
-        "grad_stream": dict(bound="hbm", flops=G * 2 * 3 * n4,
-                            bytes=G * 8 * (3 * n4 + natm * 3 * n2 + 3 * n2 + n * npair + 2 * n2)),
+                     bytes=G * 8 * (npair * pitch + L8 + npair * npair + 6 * n2)),
+        # eri_ip1p + core-Hamiltonian derivative + int1e_ipovlp read once; the n rows (m, b) of W per AO m
+        "grad_stream": dict(bound="hbm", flops=G * 2 * 3 * n2 * npair,
+                            bytes=G * 8 * (3 * n2 * npair + natm * 3 * n2 + 3 * n2 + n * n * npair + 2 * n2)),
     }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of 4096 geometries (H10 sizes, N = 20) from the
+# `ncu --set full` capture of the kernels of THIS commit: profiles/r02_packed_step_ncu_full.txt
+NCU_TRAFFIC_4096 = {}
 
 
 def h10_geometries(G, seed):
@@ -302,16 +315,45 @@ def h10_geometries(G, seed):
     return co + 0.3 * v / np.linalg.norm(v, axis=2)[..., None]
 
 
+def screened_quartet_fraction(coords, basis="sto-6g", thr=1.0e-17):
+    """Fraction of the primitive quartets of the contracted quartets (ab|cd), (ab) >= (cd), that pass the
+    Schwarz screen of K9 (csrc/integrals.cu: the leading rectangle of primitive pairs whose bound times the
+    partner's largest bound reaches kScreen = 1e-17), evaluated on the host for a few sample geometries."""
+    from evcont_b200.basis import s_basis_tables
+    fr = []
+    for co in coords:
+        natm = co.shape[0]
+        t = s_basis_tables(["H"] * natm, basis)
+        off = np.concatenate([[0], np.cumsum(t["ao_nprim"])])
+        bounds = []
+        for a in range(natm):
+            for b in range(a + 1):
+                ea, wa = t["prim_exp"][off[a]:off[a + 1]], t["prim_wt"][off[a]:off[a + 1]]
+                eb, wb = t["prim_exp"][off[b]:off[b + 1]], t["prim_wt"][off[b]:off[b + 1]]
+                r2 = float(((co[t["ao_atom"][a]] - co[t["ao_atom"][b]]) ** 2).sum())
+                p = ea[:, None] + eb[None, :]
+                kc = wa[:, None] * wb[None, :] * np.exp(-ea[:, None] * eb[None, :] / p * r2)
+                bounds.append(np.sort((np.abs(kc) * np.sqrt(2.0 * np.pi ** 2.5 / (p * p * np.sqrt(2.0 * p)))).ravel())[::-1])
+        kept = tot = 0
+        for i, bi in enumerate(bounds):
+            for bk in bounds[:i + 1]:
+                kept += int((bi * bk[0] >= thr).sum()) * int((bk * bi[0] >= thr).sum())
+                tot += bi.size * bk.size
+        fr.append(kept / tot)
+    return float(np.mean(fr))
+
+
 def run_coords_leg(args, eng, stack, timed, world, rank, torch):
     """MD steps/s when only the nuclear coordinates come from the host: pinned coordinates in,
-    AO integrals on the device (K9, s shells, STO-6G), prediction step, (E, grad) back in pinned
-    host memory.  Also times the integral kernel alone for its FP64 roofline."""
+    AO integrals on the device (K9, s shells, STO-6G, packed two-electron output), prediction step,
+    (E, grad) back in pinned host memory.  Also times the integral kernel alone for its FP64 roofline."""
     from evcont_b200.engine import DeviceAO
     G, K, W, N = args.batch, args.steps, args.warmup, args.ntrain
     sb = eng.sbasis(["H"] * NATM, "sto-6g")
-    co_h = torch.from_numpy(h10_geometries(G, 4000 + rank)).pin_memory()
+    geoms = h10_geometries(G, 4000 + rank)
+    co_h = torch.from_numpy(geoms).pin_memory()
     co_d = eng.empty(G, NATM, 3)
-    ao = DeviceAO(eng, G, sb.nao, NATM, sb.aoslices_host)
+    ao = DeviceAO(eng, G, sb.nao, NATM, sb.aoslices_host, packed=True)
     out = (eng.empty(G), eng.empty(G, NATM, 3), eng.empty(G, N))
     E_h = torch.empty(G, dtype=torch.float64).pin_memory()
     g_h = torch.empty(G, NATM, 3, dtype=torch.float64).pin_memory()
@@ -328,23 +370,149 @@ def run_coords_leg(args, eng, stack, timed, world, rank, torch):
     ms = timed(step, K)
     launches = eng.launch_count() - launches0
     ints_ms = timed(lambda i: eng.ao_integrals(sb, co_d, out=ao), K) / K
-    # algorithmic work of K9: contracted quartets (ab|cd), (ab) >= (cd), times the primitive quartets
-    # of each, ~45 FMA per primitive quartet (PQ, T, Boys F0/F1, 9 accumulators); DESIGN.md section 4
+    # algorithmic work of K9: contracted quartets (ab|cd), (ab) >= (cd), times the primitive quartets of each
+    # that pass the Schwarz screen, ~45 FMA per primitive quartet (PQ, T, Boys F0/F1, 9 accumulators)
     npc = NORB * (NORB + 1) // 2
     prim_quartets = npc * (npc + 1) // 2 * 6 ** 4
-    flops = G * prim_quartets * 90.0
+    kept = screened_quartet_fraction(geoms[:4])
+    flops = G * prim_quartets * kept * 90.0
     peak_tf = 64 * 2 * eng.sm_count * 1.965e9 / 1e12  # 64 DFMA lanes/clk/SM (tools/fp64_latency.cu)
     ach = flops / (ints_ms * 1e-3) / 1e12
     return {"value": world * G * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
             "h2d_bytes_per_step": int(co_h.numel() * 8), "d2h_bytes_per_step": int((E_h.numel() + g_h.numel()) * 8),
-            "basis": "STO-6G (s shells), integrals by evc_ao_integrals_s", "gpu_launches": int(launches),
+            "basis": "STO-6G (s shells), integrals by evc_ao_integrals_s_packed", "gpu_launches": int(launches),
             "integrals_ms_per_step": ints_ms,
             "integrals_roofline": {"kernel": "sint_kernel", "bound": "fp64 fma pipe", "achieved": ach, "peak": peak_tf,
                                    "unit": "TFLOP/s", "frac": ach / peak_tf,
-                                   "work": f"{prim_quartets} primitive quartets per geometry x 90 flop, before "
-                                           "Schwarz screening",
+                                   "work": f"{prim_quartets} primitive quartets per geometry x {kept:.3f} that pass the "
+                                           "Schwarz screen (host count on 4 sample geometries) x 90 flop",
+                                   "screened_fraction": kept,
                                    "peak_source": "64 DFMA lanes/clk/SM x SMs x 1.965 GHz (tools/fp64_latency.cu)"}}
 
+
+def run_latency_leg(args, eng, stack, torch):
+    """Single-trajectory latency (one geometry per step): ms per predicted MD step for the
+    H10 stack with the AO arrays resident and from nuclear coordinates."""
+    from evcont_b200.engine import DeviceAO
+    sb = eng.sbasis(["H"] * NATM, "sto-6g")
+    co = eng.to_device(h10_geometries(1, 77))
+    ao = DeviceAO(eng, 1, sb.nao, NATM, sb.aoslices_host, packed=True)
+    out = (eng.empty(1), eng.empty(1, NATM, 3), eng.empty(1, args.ntrain))
+    eng.ao_integrals(sb, co, out=ao)
+
+    def t(fn, reps=50):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    res = t(lambda: eng.energy_with_grad(stack, ao, out=out))
+    crd = t(lambda: eng.energy_with_grad_coords(stack, sb, co, ao=ao, out=out))
+    # the same step replayed as a CUDA graph (what the device MD integrator does)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(eng.device)
+    side.wait_stream(torch.cuda.current_stream(eng.device))
+    from evcont_b200.engine import Workspace
+    ws = Workspace(eng.device)
+    with eng.using_workspace(ws):
+        eng.energy_with_grad_coords(stack, sb, co, ao=ao, out=out)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                eng.energy_with_grad_coords(stack, sb, co, ao=ao, out=out)
+    ws.freeze()
+    torch.cuda.current_stream(eng.device).wait_stream(side)
+    grf = t(g.replay)
+    return {"workload": WORKLOAD, "geometries_per_step": 1, "resident_ms_per_step": res,
+            "from_coordinates_ms_per_step": crd, "from_coordinates_cuda_graph_ms_per_step": grf,
+            "from_coordinates_steps_per_s": 1000.0 / grf}
+
+
+def run_stream_legs(args, eng, torch, hbm_peak):
+    """The HBM-streaming regime of the stack contractions (north star subsystem 3): one geometry against
+    a stack far larger than L2.  H30 / STO-6G sizes (configs[3]: n = 30, N = 20, layout (N,N,n,n,n,n),
+    2.6 GB) and Zundel / 6-31G sizes (configs[4]: n = 28, N = 100, layout (N(N+1)/2, n^2(n^2+1)/2), 12.4 GB),
+    synthetic stacks.  K5 = evc_subspace_H, K7 = evc_predict_rdm on the reference's own layouts; achieved
+    GB/s = stack bytes / time, against the measured HBM copy bandwidth."""
+    from evcont_b200.engine import DeviceStack
+    out = {}
+    for name, n, N, layout in (("h30_sto6g_N20_layout6", 30, 20, 6), ("zundel_631g_N100_layout2", 28, 100, 2)):
+        gen = torch.Generator(device=eng.device)
+        gen.manual_seed(3)
+        n2 = n * n
+        L = n2 * n2 if layout == 6 else n2 * (n2 + 1) // 2
+        P = N * N if layout == 6 else N * (N + 1) // 2
+        two = torch.randn(P, L, generator=gen, dtype=torch.float64, device=eng.device)
+        one = torch.randn(N, N, n, n, generator=gen, dtype=torch.float64, device=eng.device)
+        b = torch.randn(N, N, generator=gen, dtype=torch.float64, device=eng.device)
+        S = torch.eye(N, dtype=torch.float64, device=eng.device) + 0.01 * (b + b.T)
+        stack = DeviceStack(S, one, two.reshape((N, N, n, n, n, n) if layout == 6 else (P, L)), engine=eng, norb=n)
+        h1 = torch.randn(1, n, n, generator=gen, dtype=torch.float64, device=eng.device)
+        h2 = torch.randn(1, n, n, n, n, generator=gen, dtype=torch.float64, device=eng.device)
+        cv = torch.randn(1, N, generator=gen, dtype=torch.float64, device=eng.device)
+        nbytes = two.numel() * 8 + one.numel() * 8
+        leg = {"norb": n, "ntrain": N, "layout": layout, "stack_GB": nbytes / 1e9, "geometries_per_step": 1}
+        for key, fn in (("subspace_H", lambda: eng.subspace_H(stack, h1, h2)),
+                        ("predict_rdm", lambda: eng.predict_rdm(stack, cv))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            leg[key] = {"ms": ms, "bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": nbytes / ms / 1e6 / hbm_peak}
+        out[name] = leg
+        del stack, two, one, h2
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_trdm_sizes(args, eng, torch, dgemm_tf):
+    """trans_rdm12 pairs/s at the other BASELINE sizes: H6 / STO-6G (configs[0]: 6 orbitals, 400 determinants,
+    3 states -> 6 pairs) and H2O / 6-31G (configs[2]: 13 orbitals, 1 656 369 determinants, 4 states -> 10 pairs)."""
+    import math
+    out = {}
+    for name, n, k, nvec, reps in (("h6_sto6g", 6, 3, 3, 20), ("h2o_631g", 13, 5, 4, 3)):
+        na = math.comb(n, k)
+        vecs = []
+        for v in range(nvec):
+            c = np.random.default_rng(1000 + v).standard_normal((na, na))
+            c = c + c.T
+            vecs.append(c / np.linalg.norm(c))
+        vd = eng.to_device(np.stack(vecs))
+        pairs = [(a, b) for a in range(nvec) for b in range(a + 1)]
+        for _ in range(2):
+            eng.trans_rdm12_batch(vd, pairs, n, (k, k))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            eng.trans_rdm12_batch(vd, pairs, n, (k, k))
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        ndet = na * na
+        alg = len(pairs) * (2.0 * n ** 4 * ndet + 2.0 * n * n * ndet)
+        issued = eng.trans_rdm12_issued_flops()
+        out[name] = {"norb": n, "ndet": ndet, "pairs": len(pairs), "ms": ms, "pairs_per_s": len(pairs) / ms * 1e3,
+                     "roofline": {"bound": "tensor", "achieved": alg / ms / 1e9, "issued_tflops": issued / ms / 1e9,
+                                  "peak": dgemm_tf, "unit": "TFLOP/s",
+                                  "frac": (alg / ms / 1e9 / dgemm_tf) if dgemm_tf else None,
+                                  "issued_frac": (issued / ms / 1e9 / dgemm_tf) if dgemm_tf else None}}
+        del vd
+    return out
 
 
 def run_sp_legs(args, eng, timed, world, rank, torch):
@@ -514,13 +682,13 @@ def run_b200(args):
 
     # ---- phase 2: prediction steps ------------------------------------------------------
     hao, host, aoslices = host_ao_batch(G, seed0=100 + 1000 * rank, pin=True)
-    ao = DeviceAO(eng, G, n, NATM, aoslices)
-    for k in DeviceAO.FIELDS:
+    ao = DeviceAO(eng, G, n, NATM, aoslices, packed=True)
+    for k in ao.fields:
         getattr(ao, k).copy_(host[k], non_blocking=True)
     torch.cuda.synchronize()
     E, grad, cvec = eng.empty(G), eng.empty(G, NATM, 3), eng.empty(G, N)
     out = (E, grad, cvec)
-    h2d_bytes = sum(host[k].numel() * 8 for k in DeviceAO.FIELDS)
+    h2d_bytes = sum(host[k].numel() * 8 for k in hao.fields)
     d2h_bytes = (hao.E.numel() + hao.grad.numel()) * 8
 
     def step_resident(_i):
@@ -554,7 +722,7 @@ def run_b200(args):
         step_e2e(i)
     e2e_ms = timed(step_e2e, K)
     # ---- the same step from nuclear coordinates only (K9: AO integrals on the device) ----
-    coords_leg, sp_legs = None, None
+    coords_leg, sp_legs, latency, stream_legs, trdm_sizes = None, None, None, None, None
     if not args.no_coords:
         coords_leg = run_coords_leg(args, eng, stack, timed, world, rank, torch)
         try:   # extra legs (other BASELINE configs): never let them take the headline line down
@@ -564,30 +732,56 @@ def run_b200(args):
                 raise          # ranks must stay in step inside the collectives of timed()
             sp_legs = {"error": f"{type(exc).__name__}: {exc}"}
     t1 = time.time()
+    if world == 1 and not args.no_extra:   # single-GPU diagnostics (no collectives inside)
+        for name, fn in (("latency", lambda: run_latency_leg(args, eng, stack, torch)),
+                         ("stream", lambda: run_stream_legs(args, eng, torch, hbm_peak)),
+                         ("trdm", lambda: run_trdm_sizes(args, eng, torch, dgemm_tf))):
+            try:
+                r = fn()
+            except Exception as exc:  # noqa: BLE001 -- reported in the JSON line
+                r = {"error": f"{type(exc).__name__}: {exc}"}
+            if name == "latency":
+                latency = r
+            elif name == "stream":
+                stream_legs = r
+            else:
+                trdm_sizes = r
     clocks = sampler.stop(window=(t0, t1)) if rank == 0 else None
     value = world * G * K / (total_ms * 1e-3)
     e2e_value = world * G * K / (e2e_ms * 1e-3)
 
-    # ---- roofline of the dominant prediction kernel + the trans-RDM kernel ----------------
-    work = stage_work(n, NATM, N, G)
+    # ---- roofline of every stage, the dominant one as `roofline`; the trans-RDM kernel ----------------
+    pitch = int(eng.lib.evc_erip_pitch(n))
+    work = stage_work(n, NATM, N, G, pitch)
     per_call = {k: v / max(1, calls) for k, v in stage_ms.items()}
-    top = max(per_call, key=per_call.get)
-    wk = work[top]
-    if wk["bound"] == "tensor" and dgemm_tf:
-        ach, peak, unit = wk["flops"] / (per_call[top] * 1e-3) / 1e12, dgemm_tf, "TFLOP/s"
-        peak_src = "cuBLAS DGEMM 6144^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"
-    else:
-        ach, peak, unit, peak_src = wk["bytes"] / (per_call[top] * 1e-3) / 1e9, hbm_peak, "GB/s", hbm_src
-    # dram__bytes_read.sum + dram__bytes_write.sum per geometry from the ncu --set full capture of the
-    # same kernels at G = 4096 (profiles/r01b_packed_step_ncu_full.txt), scaled to this launch
-    ncu_bytes_per_geom = {"loewdin": 3.323e6 / 4096, "ao2oao": (191.717e6 + 162.234e6) / 4096,
-                          "grad": (172.879e6 + 68.772e6) / 4096, "grad_stream": (1172.312e6 + 5.484e6) / 4096}
-    traffic = ncu_bytes_per_geom[top] * G if (top in ncu_bytes_per_geom and n == 10 and N == 20) else None
-    roofline = {"kernel": top, "bound": "tensor" if unit == "TFLOP/s" else "hbm", "achieved": ach,
-                "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
-                "traffic_source": "profiles/r01b_packed_step_ncu_full.txt (bytes per launch)" if traffic else None,
-                "algorithmic_bytes": wk["bytes"], "peak_source": peak_src,
-                "share_of_step": per_call[top] / max(1e-12, sum(per_call.values())),
+    fp64_src = "cuBLAS DGEMM 6144^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"
+    stages = []
+    for name in eng.STAGES:
+        wk, ms_k = work[name], per_call[name]
+        entry = {"stage": name, "kernel": STAGE_KERNEL[name], "ms_per_step": ms_k, "bound": wk["bound"],
+                 "share_of_step": ms_k / max(1e-12, sum(per_call.values()))}
+        if wk["bound"] == "tensor" and dgemm_tf:
+            ach = wk["flops"] / (ms_k * 1e-3) / 1e12
+            entry.update(achieved=ach, peak=dgemm_tf, unit="TFLOP/s", frac=ach / dgemm_tf, peak_source=fp64_src)
+        elif wk["bound"] == "hbm":
+            ach = wk["bytes"] / (ms_k * 1e-3) / 1e9
+            entry.update(achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=hbm_src)
+        else:  # latency-bound stages (small dense eigenproblems): no roofline, the time is the figure of merit
+            entry.update(achieved=None, peak=None, unit=None, frac=None,
+                         note="latency / instruction bound: one small dense eigenproblem per geometry")
+        entry["algorithmic_bytes"] = wk["bytes"]
+        entry["algorithmic_flops"] = wk["flops"]
+        tr = NCU_TRAFFIC_4096.get(name) if (n == 10 and N == 20) else None
+        entry["traffic"] = tr * G / 4096.0 if tr else None
+        stages.append(entry)
+    rated = [e for e in stages if e["frac"] is not None]
+    top = max(rated, key=lambda e: e["ms_per_step"])
+    roofline = {"kernel": top["kernel"], "stage": top["stage"], "bound": top["bound"], "achieved": top["achieved"],
+                "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": top["traffic"],
+                "traffic_source": ("profiles/r02_packed_step_ncu_full.txt (dram bytes per launch of 4096 geometries, "
+                                   "kernels of this commit)") if top["traffic"] else None,
+                "algorithmic_bytes": top["algorithmic_bytes"], "peak_source": top["peak_source"],
+                "share_of_step": top["share_of_step"],
                 "stage_ms_per_step": per_call,
                 "stage_pass": {"ms_per_step": staged_ms / K,
                                "note": "stage events recorded in a second pass of the same K steps on the same "
@@ -620,16 +814,21 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "ntrain": N, "layout": "full (N,N,n,n,n,n), packed once on the 8-fold "
                    "integral symmetry (evc_stack_pack8)",
+                   "ao_arrays": "two-electron arrays in the packed layouts erip / eri_ip1p (what the device integral "
+                                "kernel emits; evc_ao_pack8 / pack_ao_host make them from full tensors)",
                    "geometries_per_step_per_gpu": G,
                    "l2_policy": f"inputs larger than L2: {h2d_bytes / 1e6:.0f} MB of AO arrays per step "
                                 "(stack stays L2-resident as in production)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms / K},
         "gpu_launches": int(step_launches),
-        "roofline": roofline, "trans_rdm12": trdm, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "stages": stages, "trans_rdm12": trdm, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "fp64_dgemm_tflops": dgemm_tf,
         "from_coordinates": coords_leg,
         "from_coordinates_sp": sp_legs,
+        "latency": latency,
+        "stack_streaming": stream_legs,
+        "trans_rdm12_sizes": trdm_sizes,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

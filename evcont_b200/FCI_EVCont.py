@@ -38,6 +38,7 @@ class FCI_EVCont_obj:
         self.overlap = None
         self.one_rdm = None
         self.two_rdm = None
+        self._dev_civecs = None  # the training vectors resident in HBM (only the newest one is uploaded per append)
 
     # -- reference API -----------------------------------------------------------
     def append_to_rdms(self, mol):
@@ -69,6 +70,7 @@ class FCI_EVCont_obj:
             self.two_rdm = self.two_rdm[np.ix_(keep_ids, keep_ids)]
         self.fcivecs = [self.fcivecs[i] for i in keep_ids]
         self.ens = [self.ens[i] for i in keep_ids]
+        self._dev_civecs = None
 
     # -- extension ---------------------------------------------------------------
     def append_civec(self, fcivec, energy=None, norb=None, nelec=None, mol_index=None):
@@ -93,7 +95,10 @@ class FCI_EVCont_obj:
         n = int(norb)
         pairs = [(N - 1, i) for i in range(N)]
         solver = self.cisolver
-        if hasattr(solver, "trans_rdm12_batch"):
+        if hasattr(solver, "device_civecs"):
+            self._dev_civecs = solver.device_civecs(self._dev_civecs, self.fcivecs)
+            ovlp, dm1, dm2 = solver.trans_rdm12_batch(self._dev_civecs[:N], pairs, n, nelec)
+        elif hasattr(solver, "trans_rdm12_batch"):
             ovlp, dm1, dm2 = solver.trans_rdm12_batch(np.stack(self.fcivecs), pairs, n, nelec)
         else:  # a foreign cisolver: the reference's pair-by-pair loop
             ovlp = np.array([fcivec.ravel().dot(self.fcivecs[i].ravel()) for i in range(N)])

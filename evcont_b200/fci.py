@@ -175,9 +175,33 @@ class B200FCISolver:
         """All ``pairs`` [(bra, ket)] among ``civecs`` in one launch; numpy results
         ``(ovlp[np], dm1[np,n,n], dm2[np,n,n,n,n])``."""
         eng = get_engine(self._device)
-        ovlp, dm1, dm2 = eng.trans_rdm12_batch(np.asarray(civecs, dtype=np.float64), pairs, norb,
-                                               _unpack_nelec(nelec))
+        if not hasattr(civecs, "data_ptr"):  # numpy in; a device tensor (FCI_EVCont_obj's resident copy) passes through
+            civecs = np.asarray(civecs, dtype=np.float64)
+        ovlp, dm1, dm2 = eng.trans_rdm12_batch(civecs, pairs, norb, _unpack_nelec(nelec))
         return ovlp.cpu().numpy(), dm1.cpu().numpy(), dm2.cpu().numpy()
+
+    def device_civecs(self, cache, fcivecs):
+        """Keep the training vectors resident in HBM across appends: ``cache`` is the (capacity, ndet) device
+        tensor holding ``fcivecs[:-1]`` (or ``None``); only the newest vector is uploaded.  Returns the new cache."""
+        import torch
+        eng = get_engine(self._device)
+        N, ndet = len(fcivecs), fcivecs[-1].size
+        ids = [id(v) for v in fcivecs]
+        valid = cache is not None and cache.shape[1] == ndet and getattr(cache, "_evc_ids", None) == ids[:-1]
+        if not valid or cache.shape[0] < N:
+            new = torch.empty(max(8, 2 * N), ndet, dtype=torch.float64, device=eng.device)
+            if valid:
+                new[:N - 1] = cache[:N - 1]
+                first = N - 1
+            else:
+                first = 0
+            for k in range(first, N):
+                new[k] = torch.from_numpy(np.ascontiguousarray(fcivecs[k], dtype=np.float64).reshape(-1))
+            cache = new
+        else:
+            cache[N - 1] = torch.from_numpy(np.ascontiguousarray(fcivecs[-1], dtype=np.float64).reshape(-1))
+        cache._evc_ids = ids  # the host arrays this copy mirrors (a re-assigned fcivecs list invalidates it)
+        return cache
 
     def make_rdm12(self, fcivec, norb, nelec, link_index=None, reorder=True):
         return self.trans_rdm12(fcivec, fcivec, norb, nelec, link_index, reorder)
