@@ -643,12 +643,6 @@ def run_b200(args):
     lo, hi = evd.shard_range(len(pairs), rank, world)
     my_pairs = pairs[lo:hi]
 
-    def build_once(_i=0):
-        if world > 1:
-            return evd.build_stack_sharded(vecs_d, n, NELEC, group=None, device=dev)
-        ov, d1, d2 = eng.trans_rdm12_batch(vecs_d, pairs, n, NELEC)
-        return ov, d1, d2
-
     # kernel-only timing of this rank's share of the pair list
     for _ in range(max(1, W)):
         eng.trans_rdm12_batch(vecs_d, my_pairs, n, NELEC)
@@ -659,24 +653,19 @@ def run_b200(args):
     issued = eng.trans_rdm12_issued_flops()
     ndet = NA * NB
     trdm_alg_flops = len(my_pairs) * (2.0 * n ** 4 * ndet + 2.0 * n * n * ndet)
-    # full build (incl. all_gather for N>1) -> the stack used below
-    if world > 1:
-        S_d, one_d, two_d = build_once()
-        build_ms = timed(lambda i: build_once(), 2) / 2
-    else:
-        ov, d1, d2 = build_once()
-        ia = torch.tensor([p[0] for p in pairs], device=dev)
-        ib = torch.tensor([p[1] for p in pairs], device=dev)
-        S_d = eng.empty(N, N)
-        one_d = eng.empty(N, N, n, n)
-        two_d = eng.empty(N, N, n, n, n, n)
-        S_d[ia, ib] = ov
-        S_d[ib, ia] = ov
-        one_d[ia, ib] = d1
-        one_d[ib, ia] = d1
-        two_d[ia, ib] = d2
-        two_d[ib, ia] = d2
-        build_ms = trdm_ms
+    # full build -> the stack used below: the same row kernel + placement kernel at every N, plus ONE all_gather
+    # of the slabs for N > 1; timed identically
+    def full_build(_i=0):
+        if world > 1:
+            return evd.build_stack_sharded(vecs_d, n, NELEC, group=None, device=dev)
+        return evd.build_stack_single(vecs_d, n, NELEC, device=dev)
+
+    S_d, one_d, two_d = full_build()
+    build_ms = timed(full_build, 3) / 3
+    # checksum of the assembled stack: must be identical at every N (bit-reproducible across GPU counts)
+    import hashlib
+    stack_sha = hashlib.sha256(two_d.cpu().numpy().tobytes() + one_d.cpu().numpy().tobytes()
+                               + S_d.cpu().numpy().tobytes()).hexdigest()[:16]
     stack = DeviceStack(S_d, one_d, two_d, engine=eng, norb=n)
     pairs_per_s = len(pairs) / (build_ms * 1e-3)
 
@@ -786,7 +775,9 @@ def run_b200(args):
                 "stage_pass": {"ms_per_step": staged_ms / K,
                                "note": "stage events recorded in a second pass of the same K steps on the same "
                                        "stream; the headline pass (value) runs without them"}}
-    trdm = {"pairs_per_s": pairs_per_s, "pairs": len(pairs), "build_ms": build_ms,
+    trdm = {"pairs_per_s": pairs_per_s, "pairs": len(pairs), "build_ms": build_ms, "stack_sha256_16": stack_sha,
+            "build": "row kernel (evc_trans_rdm12_batch_strided) + one all_gather of the slabs (N > 1) + placement "
+                     "kernel (evc_stack_scatter_rows)",
             "kernel_ms_this_rank": trdm_ms, "launches": int(trdm_launches),
             "roofline": {"bound": "tensor", "achieved": trdm_alg_flops / (trdm_ms * 1e-3) / 1e12,
                          "issued_tflops": issued / (trdm_ms * 1e-3) / 1e12,

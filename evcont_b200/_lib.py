@@ -54,6 +54,13 @@ SIGNATURES = {
         C.c_void_p, C.c_int, c_i64, c_i64, c_double_p, c_i64, C.c_int, C.c_void_p, C.c_int,
         C.c_void_p, C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p,
         C.c_void_p, C.c_size_t]),
+    "evc_trans_rdm12_batch_strided": (C.c_int, [
+        C.c_void_p, C.c_int, c_i64, c_i64, c_double_p, c_i64, C.c_int, C.c_void_p, C.c_int,
+        C.c_void_p, C.c_int, C.c_void_p, C.c_int, c_double_p, c_i64, c_double_p, c_i64, c_double_p, c_i64,
+        C.c_void_p, C.c_size_t]),
+    "evc_stack_row_len": (c_i64, [C.c_int]),
+    "evc_stack_scatter_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_i64, C.c_int, C.c_void_p,
+                                         c_double_p, c_double_p, c_double_p]),
     "evc_trans_rdm12_last_issued_flops": (C.c_double, [C.c_void_p]),
     "evc_loewdin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                               c_double_p]),

@@ -21,6 +21,8 @@
 // conflict-free), then every warp multiplies its macro-blocks (16x16 outputs
 // = 2x2 DMMA tiles) with accumulators in registers.  Partial sums per CTA go to
 // the workspace and are reduced in slice order => deterministic.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -218,8 +220,8 @@ trdm_fused_kernel(const __grid_constant__ TrdmParams P) {
 // One CTA per pair: ordered reduction over the alpha slices, triangular fill,
 // PySCF reorder, dm1 transpose.
 __global__ void trdm_finalize_kernel(int norb, int T, int nsplit, const double* __restrict__ partial,
-                                     double* __restrict__ ovlp, double* __restrict__ dm1,
-                                     double* __restrict__ dm2) {
+                                     double* __restrict__ ovlp, int64_t ovlp_stride, double* __restrict__ dm1,
+                                     int64_t dm1_stride, double* __restrict__ dm2, int64_t dm2_stride) {
   extern __shared__ double r1[];  // rdm1_C[(p,q)] = <bra|p^+ q|ket>
   const int pair = blockIdx.x;
   const int n = norb, n2 = n * n;
@@ -235,15 +237,15 @@ __global__ void trdm_finalize_kernel(int norb, int T, int nsplit, const double* 
   };
   for (int y = threadIdx.x; y <= n2; y += blockDim.x) {
     const double v = fetch(n2, y);
-    if (y < n2) r1[y] = v; else ovlp[pair] = v;
+    if (y < n2) r1[y] = v; else ovlp[pair * ovlp_stride] = v;
   }
   __syncthreads();
-  double* d1 = dm1 + static_cast<int64_t>(pair) * n2;
+  double* d1 = dm1 + static_cast<int64_t>(pair) * dm1_stride;
   for (int k = threadIdx.x; k < n2; k += blockDim.x) {
     const int p = k / n, q = k - p * n;
     d1[k] = r1[q * n + p];  // dm1[p,q] = <bra|q^+ p|ket>
   }
-  double* d2 = dm2 + static_cast<int64_t>(pair) * n2 * n2;
+  double* d2 = dm2 + static_cast<int64_t>(pair) * dm2_stride;
   const int64_t tot = static_cast<int64_t>(n2) * n2;
   for (int64_t k = threadIdx.x; k < tot; k += blockDim.x) {
     const int x = static_cast<int>(k / n2), y = static_cast<int>(k - static_cast<int64_t>(x) * n2);
@@ -259,6 +261,32 @@ __global__ void trdm_finalize_kernel(int norb, int T, int nsplit, const double* 
     }
     if (q == r) v -= r1[p * n + s];  // reorder: p^+ q r^+ s = d_qr p^+ s + p^+ r^+ s q
     d2[k] = v;
+  }
+}
+
+// Rows [dm2 (n^4) | dm1 (n^2) | ovlp] of the pairs (a, b), a >= b, as the stack build gathers them from the
+// ranks -> the reference's (N, N, ...) arrays: block [a, b] and the same, untransposed, block at [b, a]
+// (evcont/FCI_EVCont.py:124-127).  Rows that repeat a pair (slab padding) rewrite the same values.
+__global__ void stack_scatter_rows_kernel(int N, int norb, const double* __restrict__ rows, int64_t row_stride,
+                                          const int32_t* __restrict__ row_pairs, double* __restrict__ overlap,
+                                          double* __restrict__ one_rdm, double* __restrict__ two_rdm) {
+  const int r = blockIdx.y, a = row_pairs[2 * r], b = row_pairs[2 * r + 1];
+  const int64_t n2 = static_cast<int64_t>(norb) * norb, n4 = n2 * n2, len = n4 + n2 + 1;
+  const double* src = rows + static_cast<int64_t>(r) * row_stride;
+  const int64_t ab = static_cast<int64_t>(a) * N + b, ba = static_cast<int64_t>(b) * N + a;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < len;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double v = src[k];
+    if (k < n4) {
+      two_rdm[ab * n4 + k] = v;
+      two_rdm[ba * n4 + k] = v;
+    } else if (k < n4 + n2) {
+      one_rdm[ab * n2 + (k - n4)] = v;
+      one_rdm[ba * n2 + (k - n4)] = v;
+    } else {
+      overlap[ab] = v;
+      overlap[ba] = v;
+    }
   }
 }
 
@@ -363,11 +391,11 @@ int evc_trans_rdm12_workspace_bytes(int norb, int64_t na, int64_t nb, int npairs
   return 0;
 }
 
-int evc_trans_rdm12_batch(evc_ctx* ctx, int norb, int64_t na, int64_t nb, const double* civecs,
-                          int64_t vec_stride, int nvec, const int32_t* pairs, int npairs,
-                          const uint64_t* link_a, int nlink_a, const uint64_t* link_b, int nlink_b,
-                          double* ovlp, double* dm1, double* dm2, void* workspace,
-                          size_t workspace_bytes) {
+int evc_trans_rdm12_batch_strided(evc_ctx* ctx, int norb, int64_t na, int64_t nb, const double* civecs,
+                                  int64_t vec_stride, int nvec, const int32_t* pairs, int npairs,
+                                  const uint64_t* link_a, int nlink_a, const uint64_t* link_b, int nlink_b,
+                                  double* ovlp, int64_t ovlp_stride, double* dm1, int64_t dm1_stride, double* dm2,
+                                  int64_t dm2_stride, void* workspace, size_t workspace_bytes) {
   EVC_REQUIRE(ctx != nullptr, "evc_trans_rdm12_batch: ctx is NULL");
   EVC_REQUIRE(norb >= 1 && norb <= 13, "evc_trans_rdm12_batch: norb=%d unsupported (1..13)", norb);
   EVC_REQUIRE(civecs && pairs && link_a && link_b && ovlp && dm1 && dm2 && workspace,
@@ -411,14 +439,44 @@ int evc_trans_rdm12_batch(evc_ctx* ctx, int norb, int64_t na, int64_t nb, const 
   }
   EVC_REQUIRE(rc != -1, "evc_trans_rdm12_batch: no kernel instance for nwarps=%d maxblk=%d", pl.nwarps, pl.maxblk);
   if (rc != 0) return rc;
+  EVC_REQUIRE(ovlp_stride >= 1 && dm1_stride >= P.n2 && dm2_stride >= static_cast<int64_t>(P.n2) * P.n2,
+              "evc_trans_rdm12_batch: output strides too small");
   trdm_finalize_kernel<<<npairs, 256, P.n2 * sizeof(double), ctx->stream>>>(
-      norb, pl.T, pl.nsplit, P.partial, ovlp, dm1, dm2);
+      norb, pl.T, pl.nsplit, P.partial, ovlp, ovlp_stride, dm1, dm1_stride, dm2, dm2_stride);
   EVC_CHECK_LAUNCH();
   ctx->last_trdm_flops = static_cast<double>(npairs) * static_cast<double>(na) * pl.ntile * pl.Bt *
                          static_cast<double>(pl.T) * 256.0 * 2.0;
   return 0;
 }
 
+int evc_trans_rdm12_batch(evc_ctx* ctx, int norb, int64_t na, int64_t nb, const double* civecs,
+                          int64_t vec_stride, int nvec, const int32_t* pairs, int npairs,
+                          const uint64_t* link_a, int nlink_a, const uint64_t* link_b, int nlink_b,
+                          double* ovlp, double* dm1, double* dm2, void* workspace,
+                          size_t workspace_bytes) {
+  const int64_t n2 = static_cast<int64_t>(norb) * norb;
+  return evc_trans_rdm12_batch_strided(ctx, norb, na, nb, civecs, vec_stride, nvec, pairs, npairs, link_a, nlink_a,
+                                       link_b, nlink_b, ovlp, 1, dm1, n2, dm2, n2 * n2, workspace, workspace_bytes);
+}
+
 double evc_trans_rdm12_last_issued_flops(const evc_ctx* ctx) { return ctx ? ctx->last_trdm_flops : 0.0; }
+
+int64_t evc_stack_row_len(int norb) {
+  const int64_t n2 = static_cast<int64_t>(norb) * norb;
+  return (n2 * n2 + n2 + 1 + 1) & ~static_cast<int64_t>(1);
+}
+
+int evc_stack_scatter_rows(evc_ctx* ctx, int ntrain, int norb, const double* rows, int64_t row_stride, int nrows,
+                           const int32_t* row_pairs, double* overlap, double* one_rdm, double* two_rdm) {
+  EVC_REQUIRE(ctx && rows && row_pairs && overlap && one_rdm && two_rdm, "evc_stack_scatter_rows: NULL argument");
+  EVC_REQUIRE(ntrain >= 1 && norb >= 1 && row_stride >= evc_stack_row_len(norb) - 1, "evc_stack_scatter_rows: bad sizes");
+  if (nrows <= 0) return 0;
+  const int64_t n2 = static_cast<int64_t>(norb) * norb, len = n2 * n2 + n2 + 1;
+  dim3 grid(static_cast<unsigned>(std::min<int64_t>((len + 255) / 256, 1024)), nrows);
+  stack_scatter_rows_kernel<<<grid, 256, 0, ctx->stream>>>(ntrain, norb, rows, row_stride, row_pairs, overlap, one_rdm,
+                                                           two_rdm);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
 
 }  // extern "C"

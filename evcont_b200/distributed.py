@@ -64,55 +64,68 @@ def _all_gather_rows(local, nitems, group=None):
     return torch.cat(parts, dim=0)
 
 
-def build_stack_sharded(civecs, norb, nelec, pair_fn=None, group=None, device=None):
-    """All-pairs t-RDM stack from ``civecs`` (N, na, nb), pairs sharded over the ranks.
+def stack_row_len(norb):
+    """Doubles of one slab row ``[dm2 (n^4) | dm1 (n^2) | ovlp]`` (rounded up to even: 16-byte rows)."""
+    n2 = norb * norb
+    return (n2 * n2 + n2 + 1 + 1) & ~1
 
-    ``pair_fn(civecs, pairs) -> (ovlp[np], dm1[np, n, n], dm2[np, n, n, n, n])`` as
-    torch tensors computes this rank's pairs; the default is the GPU engine's
-    batched trans-RDM kernel.  Returns tensors ``(overlap (N,N), one_rdm
-    (N,N,n,n), two_rdm (N,N,n,n,n,n))`` identical on every rank, mirror blocks
-    untransposed like the reference (evcont/FCI_EVCont.py:124-127).
+
+def build_stack_sharded(civecs, norb, nelec, pair_fn=None, group=None, device=None):
+    """All-pairs t-RDM stack from ``civecs`` (N, na, nb), pairs sharded over the ranks, assembled with ONE
+    ``all_gather`` of the per-rank slabs.
+
+    Every pair's results form one contiguous row ``[dm2 | dm1 | ovlp]``; a rank's rows are its slab.  On the GPU
+    the trans-RDM kernel writes the rows itself (``Engine.trans_rdm12_rows``) and one small kernel places the
+    gathered rows into the reference's (N, N, ...) layout (``evc_stack_scatter_rows``), mirror blocks untransposed
+    (evcont/FCI_EVCont.py:124-127).  ``pair_fn(civecs, pairs) -> (ovlp, dm1, dm2)`` replaces the kernel in the
+    CPU (gloo) tests of this host logic.  Returns ``(overlap (N,N), one_rdm (N,N,n,n), two_rdm (N,N,n,n,n,n))``,
+    identical on every rank and bit-identical to a single-GPU build: a pair's row does not depend on which rank
+    computed it.
     """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if not isinstance(civecs, torch.Tensor):   # device tensors stay where they are (no re-upload per build)
         civecs = np.asarray(civecs, dtype=np.float64)
     N, n = civecs.shape[0], int(norb)
+    n2 = n * n
     pairs = tril_pairs(N)
     lo, hi = shard_range(len(pairs), rank, world)
-    if pair_fn is None:
-        from .engine import get_engine
-        eng = get_engine(device)
-
-        def pair_fn(vecs, plist):
-            return eng.trans_rdm12_batch(vecs, plist, n, nelec)
     # Every rank computes exactly `slab` pairs -- its share, padded with repeats of pairs[0] -- so that the kernel
-    # outputs ARE the equally sized send buffers of the all_gather (no concatenation / zero-fill copies), and the
-    # gathered rows scatter straight into the (N, N, ...) layout: the padding rows rewrite block [0, 0] with the
+    # output IS the equally sized send buffer of the all_gather; the padding rows rewrite block [0, 0] with the
     # value it already has.
     slab = slab_size(len(pairs), world)
     padded = pairs[lo:hi] + [pairs[0]] * (slab - (hi - lo))
-    ovlp, dm1, dm2 = pair_fn(civecs, padded)
-    ovlp, dm1, dm2 = ovlp.reshape(slab).contiguous(), dm1.reshape(slab, n, n).contiguous(), \
-        dm2.reshape(slab, n, n, n, n).contiguous()
-    g_ov = ovlp.new_empty((world * slab,))
-    g_d1 = dm1.new_empty((world * slab, n, n))
-    g_d2 = dm2.new_empty((world * slab, n, n, n, n))
-    dist.all_gather_into_tensor(g_d2, dm2, group=group)
-    dist.all_gather_into_tensor(g_d1, dm1, group=group)
-    dist.all_gather_into_tensor(g_ov, ovlp, group=group)
-    key = (N, world, str(g_ov.device))
+    width = stack_row_len(n)
+    eng = None
+    if pair_fn is None:
+        from .engine import get_engine
+        eng = get_engine(device)
+        rows = eng.trans_rdm12_rows(civecs, padded, n, nelec)
+    else:
+        ovlp, dm1, dm2 = pair_fn(civecs, padded)
+        rows = dm2.new_zeros((slab, width))
+        rows[:, : n2 * n2] = dm2.reshape(slab, n2 * n2)
+        rows[:, n2 * n2: n2 * n2 + n2] = dm1.reshape(slab, n2)
+        rows[:, n2 * n2 + n2] = ovlp.reshape(slab)
+    gathered = rows.new_empty((world * slab, width))
+    dist.all_gather_into_tensor(gathered, rows.contiguous(), group=group)   # the one collective of the build
+    key = (N, world, str(gathered.device))
     if key not in _SCATTER_INDEX:
-        ia, ib = [], []
+        ab = []
         for r in range(world):
             rlo, rhi = shard_range(len(pairs), r, world)
-            rows = pairs[rlo:rhi] + [pairs[0]] * (slab - (rhi - rlo))
-            ia += [p[0] for p in rows]
-            ib += [p[1] for p in rows]
-        _SCATTER_INDEX[key] = (torch.tensor(ia, device=g_ov.device), torch.tensor(ib, device=g_ov.device))
-    ia, ib = _SCATTER_INDEX[key]
-    overlap = g_ov.new_empty((N, N))
-    one = g_ov.new_empty((N, N, n, n))
-    two = g_ov.new_empty((N, N, n, n, n, n))
+            ab += pairs[rlo:rhi] + [pairs[0]] * (slab - (rhi - rlo))
+        _SCATTER_INDEX[key] = torch.tensor(ab, dtype=torch.int32, device=gathered.device).reshape(-1, 2).contiguous()
+    row_pairs = _SCATTER_INDEX[key]
+    if eng is not None:
+        return eng.stack_scatter_rows(gathered, row_pairs, N, n)
+    # CPU tensors (gloo tests of the host logic): the same placement with index assignments
+    ia, ib = row_pairs[:, 0].long(), row_pairs[:, 1].long()
+    overlap = gathered.new_empty((N, N))
+    one = gathered.new_empty((N, N, n, n))
+    two = gathered.new_empty((N, N, n, n, n, n))
+    g_d2 = gathered[:, : n2 * n2].reshape(-1, n, n, n, n)
+    g_d1 = gathered[:, n2 * n2: n2 * n2 + n2].reshape(-1, n, n)
+    g_ov = gathered[:, n2 * n2 + n2]
     overlap[ia, ib] = g_ov
     overlap[ib, ia] = g_ov
     one[ia, ib] = g_d1
@@ -120,6 +133,17 @@ def build_stack_sharded(civecs, norb, nelec, pair_fn=None, group=None, device=No
     two[ia, ib] = g_d2
     two[ib, ia] = g_d2
     return overlap, one, two
+
+
+def build_stack_single(civecs, norb, nelec, device=None):
+    """The same build on one GPU, through the same row kernel and placement kernel (no collective)."""
+    from .engine import get_engine
+    eng = get_engine(device)
+    N, n = civecs.shape[0], int(norb)
+    pairs = tril_pairs(N)
+    rows = eng.trans_rdm12_rows(civecs, pairs, n, nelec)
+    row_pairs = torch.tensor(pairs, dtype=torch.int32, device=rows.device).reshape(-1, 2).contiguous()
+    return eng.stack_scatter_rows(rows, row_pairs, N, n)
 
 
 def gather_predictions(E_local, grad_local, ngeom, group=None):

@@ -172,6 +172,51 @@ class Engine:
             _ptr(ws), ws.numel()))
         return ovlp, dm1, dm2
 
+    def trans_rdm12_rows(self, civecs, pairs, norb, nelec):
+        """Like :meth:`trans_rdm12_batch`, but every pair's results form one contiguous row
+        ``[dm2 (n^4) | dm1 (n^2) | ovlp]`` of a ``(npairs, evc_stack_row_len(n))`` tensor -- the send buffer of the
+        single all_gather of the multi-GPU stack build (``evc_trans_rdm12_batch_strided``)."""
+        neleca, nelecb = nelec
+        na, nlink_a, la_sm, _ = self.link_tables(norb, neleca)
+        nb, nlink_b, _, lb_lm = self.link_tables(norb, nelecb)
+        civecs = self.to_device(civecs).reshape(-1, na * nb)
+        nvec = civecs.shape[0]
+        stride = na * nb + ((na * nb) & 1)
+        if stride != na * nb:
+            padded = self.empty(nvec, stride)
+            padded[:, : na * nb] = civecs
+            padded[:, na * nb:] = 0
+            civecs = padded
+        pairs_h = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        if pairs_h.min() < 0 or pairs_h.max() >= nvec:
+            raise IndexError("pair index out of range")
+        npairs, n = pairs_h.shape[0], norb
+        pairs_d = torch.from_numpy(pairs_h).to(self.device)
+        width = int(self.lib.evc_stack_row_len(n))
+        rows = self.empty(npairs, width)
+        n2 = n * n
+        nbytes = C.c_size_t()
+        check(self.lib.evc_trans_rdm12_workspace_bytes(n, na, nb, npairs, self.sm_count, C.byref(nbytes)))
+        ws = self.workspace(nbytes.value)
+        self._bind_stream()
+        base = rows.data_ptr()
+        check(self.lib.evc_trans_rdm12_batch_strided(
+            self._ctx, n, na, nb, _ptr(civecs), stride, nvec, _ptr(pairs_d), npairs,
+            _ptr(la_sm), nlink_a, _ptr(lb_lm), nlink_b,
+            C.c_void_p(base + 8 * (n2 * n2 + n2)), width, C.c_void_p(base + 8 * n2 * n2), width,
+            C.c_void_p(base), width, _ptr(ws), ws.numel()))
+        return rows
+
+    def stack_scatter_rows(self, rows, row_pairs, ntrain, norb):
+        """Gathered rows -> ``(overlap, one_rdm, two_rdm)`` in the reference's (N, N, ...) layout
+        (``evc_stack_scatter_rows``); ``row_pairs``: (nrows, 2) int32 device tensor of (a, b)."""
+        N, n = int(ntrain), int(norb)
+        overlap, one, two = self.empty(N, N), self.empty(N, N, n, n), self.empty(N, N, n, n, n, n)
+        self._bind_stream()
+        check(self.lib.evc_stack_scatter_rows(self._ctx, N, n, _ptr(rows), rows.stride(0), rows.shape[0],
+                                              _ptr(row_pairs), _ptr(overlap), _ptr(one), _ptr(two)))
+        return overlap, one, two
+
     def trans_rdm12_issued_flops(self):
         return self.lib.evc_trans_rdm12_last_issued_flops(self._ctx)
 

@@ -36,16 +36,41 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
         nrm = torch.linalg.vector_norm(v)
         return v, float(nrm)
 
-    # initial guesses: unit vectors on the lowest diagonal elements (symmetrised)
-    order = torch.argsort(hdiag)[: max(4 * nroots, 8)].tolist()
+    # Initial space from a small "P space", as pyscf.fci.direct_spin0 starts (pspace_size = 400 there): the P
+    # determinants of lowest diagonal energy (closed under alpha <-> beta exchange), H restricted to them
+    # built with P applications of the device H c, diagonalised on the host; its lowest eigenvectors seed the
+    # iteration.  Unit vectors on the lowest diagonal elements alone let the iteration skip roots that are
+    # weakly coupled to them (H6 at 1.4 bohr, nroots = 2: the second root of the symmetric sector was missed).
+    P = min(nd, 48 + 16 * nroots if nd > 500000 else 96 + 32 * nroots)
+    idx = torch.argsort(hdiag)[:P].tolist()
+    if spin0 and na == nb:   # add the exchange partners (Ib, Ia) of the chosen (Ia, Ib)
+        have = set(idx)
+        for k in list(idx):
+            t = (k % nb) * nb + (k // nb)
+            if t not in have:
+                have.add(t)
+                idx.append(t)
+    P = len(idx)
+    idx_t = torch.tensor(idx, device=hdiag.device)
+    hpp = np.empty((P, P))
+    unit = torch.zeros(nd, dtype=torch.float64, device=hdiag.device)
+    for j, k in enumerate(idx):
+        unit[k] = 1.0
+        hpp[:, j] = ham.contract(unit)[idx_t].cpu().numpy()
+        unit[k] = 0.0
+    hpp = 0.5 * (hpp + hpp.T)
+    _, pv = np.linalg.eigh(hpp)
     V = []
-    for k in order:
+    for k in range(P):
         g = torch.zeros(nd, dtype=torch.float64, device=hdiag.device)
-        g[k] = 1.0
-        g, nrm = orth(sym(g), V)
+        g[idx_t] = torch.from_numpy(np.ascontiguousarray(pv[:, k])).to(hdiag.device)
+        gs = sym(g)
+        if spin0 and na == nb and float(torch.linalg.vector_norm(gs)) < 0.5:
+            continue   # an exchange-antisymmetric P-space state: not in the sector direct_spin0 solves
+        g, nrm = orth(gs, V)
         if nrm > 1e-8:
             V.append(g / nrm)
-        if len(V) == nroots:
+        if len(V) == min(nroots + 2, max(1, max_space * nroots - nroots)):
             break
     if len(V) < nroots:
         raise RuntimeError(f"FCI Davidson: only {len(V)} independent initial guesses for nroots={nroots}")

@@ -105,6 +105,22 @@ int evc_trans_rdm12_batch(evc_ctx *ctx, int norb, int64_t na, int64_t nb,
                           const uint64_t *link_b /* link-major */, int nlink_b,
                           double *ovlp, double *dm1, double *dm2,
                           void *workspace, size_t workspace_bytes);
+/* The same with strided outputs (pair p: ovlp[p * ovlp_stride], dm1 + p * dm1_stride, dm2 + p * dm2_stride), so
+ * that one pair's results can form ONE contiguous row [dm2 | dm1 | ovlp] of evc_stack_row_len(norb) doubles: the
+ * send buffer of the single all_gather of the multi-GPU stack build. */
+int evc_trans_rdm12_batch_strided(evc_ctx *ctx, int norb, int64_t na, int64_t nb,
+                                  const double *civecs, int64_t vec_stride, int nvec,
+                                  const int32_t *pairs, int npairs, const uint64_t *link_a,
+                                  int nlink_a, const uint64_t *link_b, int nlink_b, double *ovlp,
+                                  int64_t ovlp_stride, double *dm1, int64_t dm1_stride, double *dm2,
+                                  int64_t dm2_stride, void *workspace, size_t workspace_bytes);
+int64_t evc_stack_row_len(int norb); /* n^4 + n^2 + 1, rounded up to even */
+/* rows [nrows][row_stride] of pairs row_pairs[nrows][2] = (a, b) (device int32) -> overlap (N,N), one_rdm
+ * (N,N,n,n), two_rdm (N,N,n,n,n,n): block [a,b] and the untransposed copy at [b,a], exactly how
+ * FCI_EVCont_obj.append_to_rdms stores them (evcont/FCI_EVCont.py:117-127). */
+int evc_stack_scatter_rows(evc_ctx *ctx, int ntrain, int norb, const double *rows, int64_t row_stride,
+                           int nrows, const int32_t *row_pairs, double *overlap, double *one_rdm,
+                           double *two_rdm);
 /* issued DMMA flop count of the last evc_trans_rdm12_batch call on this ctx
  * (for tensor-pipe utilisation; the algorithmic count is 2 n^4 ndet per pair) */
 double evc_trans_rdm12_last_issued_flops(const evc_ctx *ctx);

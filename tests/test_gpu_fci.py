@@ -66,6 +66,20 @@ def test_davidson_h6_against_dense_diagonalisation():
     assert all(np.abs(c - c.T).max() < 1e-10 for c in cs)
 
 
+@pytest.mark.parametrize("d", [1.0, 1.4, 1.8, 2.6, 3.0])
+def test_davidson_excited_roots_at_every_training_distance(d):
+    """nroots = 2 and 3 along the H6 scan: no root of the alpha <-> beta symmetric sector may be skipped."""
+    from evcont_b200.fci import B200FCISolver
+    from oracle import trans_rdm as otr
+    mol = _h_chain(6, d)
+    h1, h2 = _oao_integrals(mol)
+    w, v = np.linalg.eigh(otr.hamiltonian_matrix(h1, h2, 6, (3, 3)))
+    symm = [k for k in range(len(w)) if np.abs(v[:, k].reshape(20, 20) - v[:, k].reshape(20, 20).T).max() < 1e-7]
+    for nroots in (2, 3):
+        es, cs = B200FCISolver().kernel(h1, h2, 6, (3, 3), nroots=nroots)
+        assert np.abs(np.array(es) - w[symm[:nroots]]).max() < 1e-8, (d, nroots, es, w[symm[:nroots + 2]])
+
+
 def test_h6_workflow_without_pyscf():
     """append_to_rdms(MolLite) x 3 -> exactness at the training points, PES error inside the
     training range, forces = finite differences of the exact FCI energy at a training point."""
@@ -105,3 +119,53 @@ def test_h6_workflow_without_pyscf():
         cm[A, x] -= h
         fd = (exact(mol.copy().set_geom_(cp)) - exact(mol.copy().set_geom_(cm))) / (2 * h)
         assert abs(grad[A, x] - fd) < 2e-5
+
+
+@pytest.mark.parametrize("roots_train,nroots", [([1], 3), ([0, 1], 6)])
+def test_h6_excited_state_workflow(roots_train, nroots):
+    """scripts/PES_H_chain/H6_PES_excited/H6_continuation_excited.py: roots_train = [1] / [0, 1], three training
+    distances, approximate_multistate_OAO with nroots = 3 / 6 -- against dense diagonalisation of the
+    Slater-Condon Hamiltonian (the alpha <-> beta symmetric sector direct_spin0 solves in).
+    (evcont/FCI_EVCont.py:43-47, 95-131: every trained root becomes its own training state.)"""
+    from evcont_b200.FCI_EVCont import FCI_EVCont_obj
+    from evcont_b200.ab_initio_eigenvector_continuation import approximate_multistate_OAO
+    from oracle import trans_rdm as otr
+
+    def exact_sym(mol, k):
+        h1, h2 = _oao_integrals(mol)
+        w, v = np.linalg.eigh(otr.hamiltonian_matrix(h1, h2, 6, (3, 3)))
+        symm = [q for q in range(len(w)) if np.abs(v[:, q].reshape(20, 20) - v[:, q].reshape(20, 20).T).max() < 1e-7]
+        return w[symm[:k]] + mol.energy_nuc()
+
+    cont = FCI_EVCont_obj(roots_train=roots_train, cibasis="canonical")
+    train = [1.0, 1.8, 2.6]
+    for d in train:
+        cont.append_to_rdms(_h_chain(6, d))
+    nt = len(roots_train)
+    N = nt * len(train)
+    assert cont.overlap.shape == (N, N) and cont.two_rdm.shape == (N, N, 6, 6, 6, 6)
+    assert len(cont.fcivecs) == N and len(cont.ens) == N
+    assert cont.mol_index == [k for k in range(len(train)) for _ in range(nt)]
+    # the stored energies are the FCI energies of the trained roots at their geometry
+    for k, d in enumerate(train):
+        ex = exact_sym(_h_chain(6, d), max(roots_train) + 1)
+        for j, r in enumerate(roots_train):
+            assert abs(cont.ens[k * nt + j] - ex[r]) < 1e-8
+    # training vectors of one geometry are orthonormal; the stack reproduces its own training energies
+    assert np.abs(np.diag(cont.overlap) - 1).max() < 1e-10
+    if nt == 2:
+        assert abs(cont.overlap[0, 1]) < 1e-9
+    nr = min(nroots, N)
+    for k, d in enumerate(train):
+        mol = _h_chain(6, d)
+        en, c = approximate_multistate_OAO(mol, cont.one_rdm, cont.two_rdm, cont.overlap, nroots=nr)
+        assert en.shape == (nr,) and c.shape == (nr, N)
+        ex = exact_sym(mol, max(roots_train) + 1)
+        for r in roots_train:   # every trained root is an exact eigenvalue of the subspace problem there
+            assert np.abs(en - ex[r]).min() < 1e-8
+        assert np.all(np.diff(en) > -1e-12)
+    # between the training points: variational (each Ritz value bounds the matching exact one from above)
+    mol = _h_chain(6, 2.2)
+    en, _ = approximate_multistate_OAO(mol, cont.one_rdm, cont.two_rdm, cont.overlap, nroots=nr)
+    ex = exact_sym(mol, 1)
+    assert en[0] > ex[0] - 1e-10

@@ -54,6 +54,36 @@ def test_oh_against_oracle_and_batch_consistency():
         assert np.array_equal(one[k][0], big[k][0]) and np.array_equal(big[k][0], big[k][699]), k
 
 
+def test_two_oxygens_every_array_against_oracle():
+    """O2 in 6-31G at a general orientation: every quartet class with p shells on DIFFERENT centres (ppps, pppp,
+    psps, ppss across the two atoms) is compared element by element with the oracle."""
+    from oracle import integrals_sp as osp
+    co = np.array([[0.05, 0.10, -0.20], [0.85, -0.60, 2.15]])
+    got, sb = _device(["O", "O"], co[None])
+    ref = osp.ao_arrays(osp.SPBasis([("O", co[0]), ("O", co[1])], "6-31g"))
+    assert sb.nao == 18
+    for k in FIELDS:
+        assert np.abs(got[k][0] - ref[k]).max() < _tol(ref[k]), k
+
+
+def test_ooh_against_golden_fixture():
+    """O, O, H (20 AOs: two p centres and a hydrogen between them, the Zundel motif): the small arrays whole and
+    6000 seeded random elements of int2e / int2e_ip1 against tests/golden/integrals_sp_OOH.npz (written by
+    tests/golden/make_integrals_sp_golden.py from the oracle)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "integrals_sp_OOH.npz"))
+    got, sb = _device([str(x) for x in g["symbols"]], g["coords"][None])
+    assert sb.nao == 20 and np.array_equal(sb.aoslices_host, g["aoslices"][:, 2:])
+    for k in ("ovlp", "hcore", "ipovlp", "hcore_deriv", "e_nuc", "grad_nuc"):
+        assert np.abs(got[k][0] - g[k]).max() < _tol(g[k]), k
+    eri, ip1 = got["eri"][0], got["eri_ip1"][0]
+    assert np.abs(eri[tuple(g["idx_eri"].T)] - g["eri_vals"]).max() < _tol(g["eri_vals"])
+    assert np.abs(ip1[tuple(g["idx_ip1"].T)] - g["ip1_vals"]).max() < _tol(g["ip1_vals"])
+    assert abs(np.abs(eri).sum() - float(g["eri_abs_sum"])) < 1e-10 * float(g["eri_abs_sum"])
+    assert abs(np.abs(ip1).sum() - float(g["ip1_abs_sum"])) < 1e-10 * float(g["ip1_abs_sum"])
+
+
 def test_zundel_sized_invariants():
     """H5O2+ (28 AOs, 7 atoms): permutational symmetry, translational invariance of the derivative
     arrays and rotational invariance of scalar contractions, device only."""

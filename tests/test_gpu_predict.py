@@ -330,3 +330,38 @@ def test_energy_only_mode_matches_the_full_step():
         E2, c2 = eng.energies(stack, ao)
         assert np.array_equal(E.cpu().numpy(), E2.cpu().numpy())
         assert np.array_equal(cvec.cpu().numpy(), c2.cpu().numpy())
+
+
+def test_near_degenerate_overlap_eigenvalues():
+    """An AO overlap with two eigenvalues 2e-6 apart (inside one round(., 5) bucket of
+    evcont/ab_initio_gradients_loewdin.py:55-56).  The reference then treats the pair as exactly degenerate;
+    the device path uses exact divided differences.  Both must agree with the central
+    finite difference of the Loewdin transform; the size of the reference's own deviation is recorded."""
+    from evcont_b200 import ab_initio_gradients_loewdin as agl
+    from evcont_b200.electron_integral_utils import get_loewdin_trafo
+    from evcont_b200.mol import synthetic_mol
+    from oracle import gradients as og
+    n, natm = 6, 3
+    mol = synthetic_mol(n, natm, seed=31)
+    rng = np.random.default_rng(8)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    w = np.array([0.61, 0.8, 0.800002, 1.05, 1.3, 1.45])   # the 2nd and 3rd share the 1e-5 bucket
+    S = (q * w) @ q.T
+    S = 0.5 * (S + S.T)
+    mol._ovlp = np.ascontiguousarray(S)
+    dS = og.get_overlap_grad(mol)                      # (n, n, natm, 3) from the molecule's int1e_ipovlp
+    dev = agl.get_derivative_ao_mo_trafo(mol)          # device: exact divided differences
+    ref = np.einsum("ijkl,ijmn->klmn", og.loewdin_trafo_grad(S), dS)   # the reference's bucketed formula
+    # central finite differences of X(S + h dS_xi)
+    h = 1e-6
+    worst_dev = worst_ref = 0.0
+    for A in range(natm):
+        for x in range(3):
+            d = dS[:, :, A, x]
+            fd = (get_loewdin_trafo(S + h * d) - get_loewdin_trafo(S - h * d)) / (2 * h)
+            worst_dev = max(worst_dev, np.abs(dev[:, :, A, x] - fd).max())
+            worst_ref = max(worst_ref, np.abs(ref[:, :, A, x] - fd).max())
+    assert worst_dev < 5e-8                 # the device derivative is the true derivative
+    # the reference deviates by O(coupling between the two near-degenerate vectors); it is small but not zero
+    assert 1e-8 < worst_ref < 1e-3
+    print(f"near-degenerate S: |dX - FD| device {worst_dev:.2e}, reference formula {worst_ref:.2e}")
