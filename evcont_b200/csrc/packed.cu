@@ -634,117 +634,72 @@ packed_grad_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8
 // contiguous run that is dotted with the n rows (m, b) of W -- no index arithmetic in the loop.
 // Everything is read exactly once; the rows are staged with asynchronous 16-byte copies.
 // ---------------------------------------------------------------------------
-constexpr int kStreamThreads = 256;
+constexpr int kStreamThreads = 128;
 
-__global__ void __launch_bounds__(kStreamThreads, 6)
+// One CTA of 4 warps per (atom, geometry); no shared-memory staging: every thread issues all its loads (a few
+// coalesced 8-byte loads of the three integral runs, the matching entries of W, its share of the core-
+// Hamiltonian derivative) before the first use, so a CTA lives for about two memory round trips and 16 of them
+// are resident per SM.  (The staged forms -- cp.async rows + two block barriers per AO, or one CTA per geometry
+// with W expanded in shared memory -- spent a third of their time in barriers: profiles/r02r.)
+__global__ void __launch_bounds__(kStreamThreads, 10)
 grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const double* __restrict__ Wg,
                    const double* __restrict__ OmS, const double* __restrict__ Pao,
                    const double* __restrict__ ipovlp, const double* __restrict__ hcore_deriv,
                    const double* __restrict__ ip1p, const double* __restrict__ grad_nuc,
                    double* __restrict__ grad) {
-  extern __shared__ __align__(16) double sm[];
+  __shared__ double red[3][kStreamThreads / 32];
   const int np = npair_of(n), n2 = n * n, rl = n * np;  // rl: doubles of one (x, m) run
-  const int rlp = (rl + 1) & ~1, n2p = (n2 + 1) & ~1;
-  double* stage = sm;                    // [3][rlp]  runs (x, m, :, :) of the current m
-  double* hds = stage + 3 * rlp;         // [3][n2p]  d hcore / d(A, x)
-  double* Ws = hds + 3 * n2p;            // [n][np]   W[(m, b), (cd)]
-  double* red = Ws + rlp;                // [3][8]
-  double* facs = red + 24;               // [np]
   const int At = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
-  const int p0 = aoslices[2 * At], p1 = aoslices[2 * At + 1];
+  const int p0 = __ldg(aoslices + 2 * At), p1 = __ldg(aoslices + 2 * At + 1);
   const double* W = Wg + static_cast<int64_t>(g) * np * np;
   const double* ipg = ip1p + static_cast<int64_t>(g) * 3 * n * rl;
+  const int64_t xs = static_cast<int64_t>(n) * rl;  // stride between the x, y, z components
   const double* hd = hcore_deriv + (static_cast<int64_t>(g) * natm + At) * 3 * n2;
-  const bool vec = ((rl & 1) == 0);      // runs start 16-byte aligned iff n * np is even
-
-  // every global input of a row set as asynchronous copies: the three integral runs and the n rows
-  // (m, b) of W (stored as its lower triangle: an 8-byte gather)
-  auto issue_rows = [&](int m) {
-    const double* r0 = ipg + static_cast<int64_t>(m) * rl;
-    const int64_t xs = static_cast<int64_t>(n) * rl;  // stride between the x, y, z components
-    if (vec) {
-      for (int e = 2 * tid; e < rl; e += 2 * kStreamThreads) {
-        cp_async16(stage + e, r0 + e);
-        cp_async16(stage + rlp + e, r0 + xs + e);
-        cp_async16(stage + 2 * rlp + e, r0 + 2 * xs + e);
-      }
-    } else {
-      for (int e = tid; e < rl; e += kStreamThreads) {
-        cp_async8(stage + e, r0 + e);
-        cp_async8(stage + rlp + e, r0 + xs + e);
-        cp_async8(stage + 2 * rlp + e, r0 + 2 * xs + e);
-      }
-    }
-    for (int b = tid >> 5; b < n; b += kStreamThreads / 32) {
-      const int r = m >= b ? tri_idx(m, b) : tri_idx(b, m);
-      for (int C = tid & 31; C < np; C += 32) cp_async8(Ws + b * np + C, W + (r > C ? r * np + C : C * np + r));
-    }
-  };
-  if (p0 < p1) issue_rows(p0);
-  for (int k = tid; k < n2; k += kStreamThreads) {
-    cp_async8(hds + k, hd + k);
-    cp_async8(hds + n2p + k, hd + n2 + k);
-    cp_async8(hds + 2 * n2p + k, hd + 2 * n2 + k);
-  }
-  cp_async_commit_all();
-
-  // weight of the packed pair (c >= d): 2 - delta_cd, as a table over the pair index
-  for (int C = tid; C < np; C += kStreamThreads) facs[C] = 2.0;
-  __syncthreads();
-  if (tid < n) facs[tid * (tid + 3) / 2] = 1.0;   // diagonal pairs (c, c)
-  const int c_first = tid % np, c_step = kStreamThreads % np;  // pair index of element tid + k * kStreamThreads
+  const double* pa = Pao + static_cast<int64_t>(g) * n2;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  {  // overlap term: - sum_{mu in A, nu} <d_x mu|nu> OmS[mu,nu]
-    const double* ipo = ipovlp + static_cast<int64_t>(g) * 3 * n2;
-    const double* om = OmS + static_cast<int64_t>(g) * n2;
-    for (int k = p0 * n + tid; k < p1 * n; k += kStreamThreads) {
-      const double i0 = __ldg(ipo + k), i1 = __ldg(ipo + n2 + k), i2 = __ldg(ipo + 2 * n2 + k), o = __ldg(om + k);
-      a0 = fma(-i0, o, a0);
-      a1 = fma(-i1, o, a1);
-      a2 = fma(-i2, o, a2);
-    }
-  }
+  // (b, C) of element e = tid + k * kStreamThreads of a run, walked incrementally: e = b * np + C
+  const int b_first = tid / np, c_first = tid - b_first * np;
+  const int b_step = kStreamThreads / np, c_step = kStreamThreads - b_step * np;
   for (int m = p0; m < p1; ++m) {
-    if (m > p0) {
-      __syncthreads();  // Ws and stage of the previous m consumed
-      issue_rows(m);
-      cp_async_commit_all();
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    if (m == p0) {  // core-Hamiltonian derivative term (staged with the first rows)
-      const double* pa = Pao + static_cast<int64_t>(g) * n2;
-      for (int k = tid; k < n2; k += kStreamThreads) {
-        const double p = __ldg(pa + k);
-        a0 = fma(hds[k], p, a0);
-        a1 = fma(hds[n2p + k], p, a1);
-        a2 = fma(hds[2 * n2p + k], p, a2);
-      }
-    }
+    const double* r0 = ipg + static_cast<int64_t>(m) * rl;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    int C = c_first;
+    int b = b_first, C = c_first;
+#pragma unroll 4
     for (int e = tid; e < rl; e += kStreamThreads) {
-      const double w = Ws[e] * facs[C];
-      s0 = fma(stage[e], w, s0);
-      s1 = fma(stage[rlp + e], w, s1);
-      s2 = fma(stage[2 * rlp + e], w, s2);
+      const int r = m >= b ? tri_idx(m, b) : tri_idx(b, m);
+      // weight 2 - delta_cd of the packed pair: C is a diagonal pair iff 8 C + 9 is an odd perfect square
+      // ((2 c + 3)^2 = 8 c (c + 3) / 2 + 9); integer check on a float estimate
+      const int q = static_cast<int>(sqrtf(static_cast<float>(8 * C + 9)) + 0.5f);
+      const double fac = (q * q == 8 * C + 9) ? 1.0 : 2.0;
+      const double w = __ldg(W + (r > C ? r * np + C : C * np + r)) * fac;
+      s0 = fma(__ldg(r0 + e), w, s0);
+      s1 = fma(__ldg(r0 + xs + e), w, s1);
+      s2 = fma(__ldg(r0 + 2 * xs + e), w, s2);
+      b += b_step;
       C += c_step;
-      if (C >= np) C -= np;
+      if (C >= np) { C -= np; ++b; }
     }
     a0 -= 0.5 * s0;
     a1 -= 0.5 * s1;
     a2 -= 0.5 * s2;
   }
-  if (p0 >= p1) {  // atom without basis functions: only the core-Hamiltonian derivative term
-    cp_async_wait_all();
-    __syncthreads();
-    const double* pa = Pao + static_cast<int64_t>(g) * n2;
-    for (int k = tid; k < n2; k += kStreamThreads) {
-      const double p = __ldg(pa + k);
-      a0 = fma(hds[k], p, a0);
-      a1 = fma(hds[n2p + k], p, a1);
-      a2 = fma(hds[2 * n2p + k], p, a2);
+  {  // overlap term: - sum_{mu in A, nu} <d_x mu|nu> OmS[mu,nu]
+    const double* ipo = ipovlp + static_cast<int64_t>(g) * 3 * n2;
+    const double* om = OmS + static_cast<int64_t>(g) * n2;
+    for (int k = p0 * n + tid; k < p1 * n; k += kStreamThreads) {
+      const double o = __ldg(om + k);
+      a0 = fma(-__ldg(ipo + k), o, a0);
+      a1 = fma(-__ldg(ipo + n2 + k), o, a1);
+      a2 = fma(-__ldg(ipo + 2 * n2 + k), o, a2);
     }
+  }
+  // core-Hamiltonian derivative term
+#pragma unroll 2
+  for (int k = tid; k < n2; k += kStreamThreads) {
+    const double p = __ldg(pa + k);
+    a0 = fma(__ldg(hd + k), p, a0);
+    a1 = fma(__ldg(hd + n2 + k), p, a1);
+    a2 = fma(__ldg(hd + 2 * n2 + k), p, a2);
   }
   // fixed-order block reduction
   for (int o = 16; o > 0; o >>= 1) {
@@ -753,22 +708,18 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
     a2 += __shfl_xor_sync(0xffffffffu, a2, o);
   }
   const int warp = tid >> 5, lane = tid & 31;
-  if (lane == 0) { red[warp] = a0; red[8 + warp] = a1; red[16 + warp] = a2; }
+  if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = a2; }
   __syncthreads();
   if (tid < 3) {
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < kStreamThreads / 32; ++w) t += red[tid * 8 + w];
+    for (int w = 0; w < kStreamThreads / 32; ++w) t += red[tid][w];
     const int64_t o = (static_cast<int64_t>(g) * natm + At) * 3 + tid;
     grad[o] = t + (grad_nuc ? grad_nuc[o] : 0.0);
   }
 }
 
-size_t grad_stream_smem_bytes(int n) {
-  const size_t n2 = static_cast<size_t>(n) * n, rl = static_cast<size_t>(n) * npair_of(n);
-  const size_t rlp = (rl + 1) & ~static_cast<size_t>(1);
-  return (3 * rlp + 3 * ((n2 + 1) & ~static_cast<size_t>(1)) + rlp + 24 + npair_of(n) + 1) * sizeof(double);
-}
+size_t grad_stream_smem_bytes(int) { return 0; }  // static shared memory only
 
 // ---------------------------------------------------------------------------
 // int2e / int2e_ip1 as full tensors -> the packed arrays (callers that hold libcint-style tensors)
@@ -924,10 +875,6 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
     int rcm = evc_stage_mark(ctx, EVC_STAGE_GRAD_STREAM);
     if (rcm) return rcm;
     const size_t sm2 = grad_stream_smem_bytes(n);
-    EVC_CHECK_CUDA(cudaFuncSetAttribute(grad_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(sm2)));
-    EVC_CHECK_CUDA(cudaFuncSetAttribute(grad_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                        cudaSharedmemCarveoutMaxShared));
     dim3 grid(natm, nbatch);
     grad_stream_kernel<<<grid, kStreamThreads, sm2, ctx->stream>>>(n, natm, aoslices, Wg, OmS, Pao, ipovlp,
                                                                     hcore_deriv, eri_ip1p, grad_nuc, grad);
