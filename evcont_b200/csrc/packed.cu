@@ -819,10 +819,18 @@ __global__ void add_enuc_kernel_p(int G, const double* __restrict__ e0, const do
 }  // namespace
 
 // ---- internal entry points (common.cuh) -------------------------------------
+int evc_packed_ao2oao_percta(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
+                             const double* erip, double* hvec, double* Tout);
+
 int evc_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
                       const double* erip, double* hvec, double* Tout) {
   EVC_REQUIRE(n >= 1 && n <= kPackedMaxNorb, "packed_ao2oao: n=%d unsupported", n);
   if (evc_packed_pipe_supported(n)) return evc_packed_ao2oao_pipe(ctx, nbatch, n, x, hcore, erip, hvec, Tout);
+  return evc_packed_ao2oao_percta(ctx, nbatch, n, x, hcore, erip, hvec, Tout);
+}
+
+int evc_packed_ao2oao_percta(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
+                             const double* erip, double* hvec, double* Tout) {
   const size_t smem = ao2oao_smem_bytes(n);
   EVC_REQUIRE(smem <= ctx->smem_optin, "packed_ao2oao: needs %zu bytes of shared memory", smem);
   const int64_t L8 = packed_len(n);
@@ -922,6 +930,13 @@ int evc_debug_phase_clocks(long long* out_host) {
 }
 
 int64_t evc_packed_row_len(int n) { return n >= 1 ? packed_len(n) : -1; }
+
+// development aid: K4p alone (pipelined kernel if use_pipe != 0 and n <= 10, else the one-CTA-per-geometry kernel)
+int evc_debug_packed_ao2oao(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore, const double* erip,
+                            double* hvec, double* Tout, int use_pipe) {
+  if (use_pipe && n >= 2 && n <= kPackedPipeMaxNorb) return evc_packed_ao2oao_pipe(ctx, nbatch, n, x, hcore, erip, hvec, Tout);
+  return evc_packed_ao2oao_percta(ctx, nbatch, n, x, hcore, erip, hvec, Tout);
+}
 
 int evc_erip_pitch(int n) { return n >= 1 ? pgeom(n).pA : -1; }
 int64_t evc_erip_len(int n) { return n >= 1 ? erip_len(n) : -1; }

@@ -230,16 +230,56 @@ __device__ __forceinline__ void rect_acc(double (&acc)[8][2], const Rect rc, int
 #undef EVC_RECT_CASE
 }
 
-// st(row, col, v0, v1): the accumulator pair of (row, col) and (row, col + 1); col is even
+// st(row, col, v0, v1): the accumulator pair of (row, col) and (row, col + 1); col is even.  Dispatched on the
+// shape like rect_acc, so that the tile coordinates are compile-time offsets (computed at run time they were
+// spilled to local memory and every store waited for a local load: profiles/r02x).
+template <int NR, int NC, typename ST>
+__device__ __forceinline__ void rect_store_fixed(const double (&acc)[8][2], int r0, int c0, ST st) {
+  const int lane = threadIdx.x & 31, row = r0 * 8 + (lane >> 2), col = c0 * 8 + (lane & 3) * 2;
+#pragma unroll
+  for (int i = 0; i < NR; ++i)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) st(row + 8 * i, col + 8 * j, acc[i * NC + j][0], acc[i * NC + j][1]);
+}
+
 template <typename ST>
 __device__ __forceinline__ void rect_store(const double (&acc)[8][2], const Rect rc, ST st) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  int i = 0, j = 0;
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    if (t < rc.nr * rc.nc) st((rc.r0 + i) * 8 + g, (rc.c0 + j) * 8 + tg * 2, acc[t][0], acc[t][1]);
-    if (++j == rc.nc) { j = 0; ++i; }
+#define EVC_RECT_CASE(NR_, NC_) \
+  case NR_ * 16 + NC_: rect_store_fixed<NR_, NC_>(acc, rc.r0, rc.c0, st); break;
+  switch (rc.nr * 16 + rc.nc) {  // warp-uniform
+    EVC_RECT_CASE(1, 1) EVC_RECT_CASE(1, 2) EVC_RECT_CASE(1, 3) EVC_RECT_CASE(1, 4)
+    EVC_RECT_CASE(1, 5) EVC_RECT_CASE(1, 6) EVC_RECT_CASE(1, 7) EVC_RECT_CASE(1, 8)
+    EVC_RECT_CASE(2, 1) EVC_RECT_CASE(2, 2) EVC_RECT_CASE(2, 3) EVC_RECT_CASE(2, 4)
+    EVC_RECT_CASE(3, 1) EVC_RECT_CASE(3, 2) EVC_RECT_CASE(4, 1) EVC_RECT_CASE(4, 2)
+    EVC_RECT_CASE(5, 1) EVC_RECT_CASE(6, 1) EVC_RECT_CASE(7, 1) EVC_RECT_CASE(8, 1)
+    default: break;
   }
+#undef EVC_RECT_CASE
+}
+
+// C = op(P) op(Q) for n x n matrices stored [n][ld], by ONE warp on the tensor cores (tp / tq: use the
+// transpose of P / Q).  The one-electron chain of K8a: a scalar FP64 instruction of a helper warp waits ~50-300
+// cycles for the FP64 datapath behind the streaming DMMAs, so the chain is issued as few, wide instructions.
+__device__ __forceinline__ void warp_mm(int n, int ld, double* C, const double* P, bool tp, const double* Q, bool tq) {
+  const int lane = threadIdx.x & 31, gq = lane >> 2, tq4 = lane & 3;
+  const int n8 = (n + 7) >> 3, k4 = (n + 3) & ~3;
+  for (int mt = 0; mt < n8; ++mt)
+    for (int nt = 0; nt < n8; ++nt) {
+      double c0 = 0.0, c1 = 0.0;
+      const int row = mt * 8 + gq, col = nt * 8 + gq;
+      for (int k0 = 0; k0 < k4; k0 += 4) {
+        const int kk = k0 + tq4;
+        const double av = (row < n && kk < n) ? (tp ? P[kk * ld + row] : P[row * ld + kk]) : 0.0;
+        const double bv = (col < n && kk < n) ? (tq ? Q[col * ld + kk] : Q[kk * ld + col]) : 0.0;
+        dmma8x8x4(c0, c1, av, bv);
+      }
+      const int cc = nt * 8 + tq4 * 2;
+      if (row < n) {
+        if (cc < n) C[row * ld + cc] = c0;
+        if (cc + 1 < n) C[row * ld + cc + 1] = c1;
+      }
+    }
+  __syncwarp();
 }
 
 __device__ __forceinline__ void st2(double* p, double v0, double v1) {  // 16-byte aligned pair
@@ -255,9 +295,17 @@ __device__ int g_pipe_clk_on = 0;
     if (stamp && (it) < 16 && (threadIdx.x & 31) == 0) g_pipe_clk[kern][role][it][ev] = clock64(); \
   } while (0)
 
+struct AoBars {
+  uint64_t load[kAoStages], ready[kAoStages], free_[kAoStages];
+};
+
 struct PipeBars {
   uint64_t load[kStages], ready[kStages], u0[kStages], p0[kStages], free_[kStages];
+  // CHAIN warp c handles every 4th geometry: it gets its own barriers (one phase per geometry it handles), because
+  // a parity wait is only meaningful for a waiter that observes EVERY phase of a barrier
+  uint64_t cready[4], cyz[4];
 };
+static_assert(sizeof(PipeBars) <= 256 && sizeof(AoBars) <= 256, "the barrier block of the pipelined kernels");
 
 template <int NC>
 struct PipeSizes {
@@ -284,7 +332,7 @@ __device__ __forceinline__ void build_pij(int n, unsigned short* pij, int tid, i
 template <int NC>
 struct AoSmem {
   using S = PipeSizes<NC>;
-  static constexpr size_t bars = 128;
+  static constexpr size_t bars = 256;  // >= sizeof(PipeBars)
   static constexpr size_t big = static_cast<size_t>(kAoStages) * 2 * S::SZ * sizeof(double);
   static constexpr size_t smalls = static_cast<size_t>(3) * S::mat * sizeof(double);  // X, Hc, T1 (front-private)
   static constexpr size_t tables = (static_cast<size_t>(S::np) * sizeof(unsigned short) + 15) / 16 * 16;
@@ -299,7 +347,7 @@ ao2oao_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant_
   using S = PipeSizes<NC>;
   constexpr int n = S::n, n2 = S::n2, np = S::np, ld = S::ld, pA = S::pA, pB = S::pB, K4 = S::K4, rows8 = S::rows8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PipeBars* bars = reinterpret_cast<PipeBars*>(smem_raw);
+  AoBars* bars = reinterpret_cast<AoBars*>(smem_raw);
   double* big = reinterpret_cast<double*>(smem_raw + AoSmem<NC>::bars);
   double* Xs = big + static_cast<size_t>(kAoStages) * 2 * S::SZ;
   double* Hs = Xs + S::mat;
@@ -460,20 +508,21 @@ ao2oao_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant_
 template <int NC>
 struct GradSmem {
   using S = PipeSizes<NC>;
-  static constexpr size_t bars = 128;
+  static constexpr int kChainWarps = 4;
+  static constexpr size_t bars = 256;
   static constexpr size_t big = static_cast<size_t>(kStages) * 2 * S::SZ * sizeof(double);
-  // per stage: X, V, Qh, Gs | front-private: Hc, Gam, A1, Z1, rs, sv | mid-private: Z, A2, Bm, A3, Ypart
-  static constexpr size_t per_stage = static_cast<size_t>(4) * S::mat;
-  static constexpr size_t front_priv = static_cast<size_t>(4) * S::mat + 2 * ((S::n + 1) & ~1);
+  // per stage: X, V, Hc, Gam, Ysum, rs, sv | MID-private: Ypart | per CHAIN warp: A, Bm, Z, Qh, Gs, Ps
+  static constexpr size_t vec = (S::n + 1) & ~1;
+  static constexpr size_t per_stage = static_cast<size_t>(5) * S::mat + 2 * vec;
   static constexpr size_t ypart = static_cast<size_t>(2) * S::ncol * 2 * S::n;  // 2 row groups
-  static constexpr size_t mid_priv = static_cast<size_t>(4) * S::mat + ypart;
-  static constexpr size_t smalls = (kStages * per_stage + front_priv + mid_priv) * sizeof(double);
+  static constexpr size_t chain_priv = static_cast<size_t>(6) * S::mat;
+  static constexpr size_t smalls = (kStages * per_stage + ypart + kChainWarps * chain_priv) * sizeof(double);
   static constexpr size_t ntri = static_cast<size_t>(S::np) * (S::np + 1) / 2;
   static constexpr size_t tables = ((S::np + ntri) * sizeof(unsigned short) + 15) / 16 * 16;
   static constexpr size_t total = bars + big + smalls + tables;
 };
 
-constexpr int kGradPipeThreads = 512;  // 8 MMA + 4 FRONT + 4 MID warps
+constexpr int kGradPipeThreads = 640;  // 8 MMA + 4 FRONT + 4 MID + 4 CHAIN warps
 
 template <int NC>
 __global__ void __launch_bounds__(kGradPipeThreads, 1)
@@ -489,16 +538,14 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PipeBars* bars = reinterpret_cast<PipeBars*>(smem_raw);
   double* big = reinterpret_cast<double*>(smem_raw + M::bars);
-  double* stage_small = big + static_cast<size_t>(kStages) * 2 * S::SZ;  // [kStages][4][mat]
-  double* fp = stage_small + kStages * M::per_stage;                     // front-private
-  double* Hc = fp, *Gam = Hc + S::mat, *A1 = Gam + S::mat, *Z1 = A1 + S::mat, *rs = Z1 + S::mat,
-         *sv = rs + ((n + 1) & ~1);
-  double* mp = fp + M::front_priv;                                       // mid-private
-  double* Zm = mp, *A2 = Zm + S::mat, *Bm = A2 + S::mat, *A3 = Bm + S::mat, *Ypart = A3 + S::mat;
-  unsigned short* pij = reinterpret_cast<unsigned short*>(mp + M::mid_priv);
+  double* stage_small = big + static_cast<size_t>(kStages) * 2 * S::SZ;  // [kStages][X, V, Hc, Gam, Ysum, rs, sv]
+  double* Ypart = stage_small + kStages * M::per_stage;                  // MID-private
+  double* chain_small = Ypart + M::ypart;                                // [kChainWarps][A, Bm, Z, Qh, Gs, Ps]
+  unsigned short* pij = reinterpret_cast<unsigned short*>(chain_small + M::kChainWarps * M::chain_priv);
   unsigned short* trc = pij + np;  // (row | col << 8) of packed triangle entry t
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int kFrontWarps = 4, kMidWarps = 4, kFrontThreads = 128, kMidThreads = 128;
+  constexpr int kFrontWarps = 4, kMidWarps = 4, kChainWarps = M::kChainWarps, kFrontThreads = 128, kMidThreads = 128;
+  static_assert(kGradPipeThreads == (kMmaWarps + kFrontWarps + kMidWarps + kChainWarps) * 32, "role split");
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -506,7 +553,11 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
       mbar_init(&bars->ready[s], kFrontWarps);
       mbar_init(&bars->u0[s], kMmaWarps);
       mbar_init(&bars->p0[s], kMidWarps);
-      mbar_init(&bars->free_[s], kMmaWarps + kMidWarps);
+      mbar_init(&bars->free_[s], kMmaWarps + kMidWarps + 1);  // + the CHAIN warp of the geometry
+    }
+    for (int c = 0; c < kChainWarps; ++c) {
+      mbar_init(&bars->cready[c], kFrontWarps);
+      mbar_init(&bars->cyz[c], kMidWarps);
     }
     mbar_init_fence();
   }
@@ -520,28 +571,83 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
                        : 0;
   constexpr unsigned kLoadBytes = static_cast<unsigned>(np) * pA * sizeof(double);
 
-  if (warp >= kMmaWarps + kFrontWarps) {
+  if (warp >= kMmaWarps + kFrontWarps + kMidWarps) {
+    // ------------------------------ CHAIN ------------------------------
+    // The one-electron chain of a geometry, by ONE warp on the tensor cores (warp_mm): Pao = X gamma X^T,
+    // Qh = hcore X (gamma + gamma^T), then, once MID has summed Y, Z = Y/2 + Qh,
+    // Omega = V (G o (V^T Z V)) V^T, OmS = Omega + Omega^T.  Eight dependent small products: ~10 k cycles of
+    // latency under the streaming DMMAs, hidden by giving consecutive geometries to different warps.
+    const int cw = warp - (kMmaWarps + kFrontWarps + kMidWarps);
+    double* A = chain_small + cw * M::chain_priv;
+    double* Bm = A + S::mat, *Z = Bm + S::mat, *Qh = Z + S::mat, *Gs = Qh + S::mat, *Ps = Gs + S::mat;
+    static_assert(kChainWarps == 4, "cready / cyz are indexed with it & 3");
+    for (int it = cw, round = 0; it < nloc; it += kChainWarps, ++round) {
+      const int64_t g = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x;
+      const int s = it % kStages;
+      const double* Xs = stage_small + s * M::per_stage;
+      const double* Vs = Xs + S::mat;
+      const double* Hc = Vs + S::mat;
+      const double* Gam = Hc + S::mat;
+      const double* Ysum = Gam + S::mat;
+      const double* rs = Ysum + S::mat;
+      const double* sv = rs + M::vec;
+      mbar_wait(&bars->cready[cw], round & 1);
+      warp_mm(n, ld, A, Xs, false, Gam, false);      // A = X gamma
+      warp_mm(n, ld, Ps, A, false, Xs, true);        // Pao = A X^T
+      for (int k = lane; k < n2; k += 32) {
+        const int i = k / n, j = k - i * n;
+        PaoOut[g * n2 + k] = Ps[i * ld + j];
+        Bm[i * ld + j] = Gam[i * ld + j] + Gam[j * ld + i];
+        // G_pq = -1/(sqrt(s_p) sqrt(s_q) (sqrt(s_p) + sqrt(s_q))), exact divided differences of s^-1/2
+        const double rp = rs[i], rq = rs[j];
+        double gpq = 0.0;
+        if (rp > 0.0 && rq > 0.0) {
+          gpq = -1.0 / (rp * rq * (rp + rq));
+        } else if ((rp > 0.0) != (rq > 0.0)) {
+          const double sp = sv[i], sq = sv[j];
+          if (sp != sq) gpq = ((rp > 0.0 ? 1.0 / rp : 0.0) - (rq > 0.0 ? 1.0 / rq : 0.0)) / (sp - sq);
+        }
+        Gs[i * ld + j] = gpq;
+      }
+      __syncwarp();
+      warp_mm(n, ld, A, Xs, false, Bm, false);       // A = X (gamma + gamma^T)
+      warp_mm(n, ld, Qh, Hc, false, A, false);       // Qh = hcore A
+      mbar_wait(&bars->cyz[cw], round & 1);          // MID has summed Y
+      for (int k = lane; k < n2; k += 32) {
+        const int i = k / n, j = k - i * n;
+        Z[i * ld + j] = Ysum[i * ld + j] + Qh[i * ld + j];
+      }
+      __syncwarp();
+      warp_mm(n, ld, A, Vs, true, Z, false);         // A = V^T Z
+      warp_mm(n, ld, Bm, A, false, Vs, false);       // Bm = A V
+      for (int k = lane; k < n2; k += 32) {
+        const int i = k / n, j = k - i * n;
+        Bm[i * ld + j] *= Gs[i * ld + j];
+      }
+      __syncwarp();
+      warp_mm(n, ld, A, Vs, false, Bm, false);       // A = V Bm
+      warp_mm(n, ld, Z, A, false, Vs, true);         // Omega = A V^T
+      for (int k = lane; k < n2; k += 32) {
+        const int i = k / n, j = k - i * n;
+        OmSout[g * n2 + k] = Z[i * ld + j] + Z[j * ld + i];
+      }
+      mbar_arrive_warp(&bars->free_[s]);
+    }
+  } else if (warp >= kMmaWarps + kFrontWarps) {
     // ------------------------------ MID ------------------------------
-    // between the GEMMs of a geometry: Y from U0, the P0 operand, Z, and the second half of the one-electron
-    // chain.  Scalar FP64 instructions of these warps queue behind the DMMAs of the MMA warps (one FP64
-    // datapath; ~50 cycles each when the tensor pipe streams, profiles/r02g): as few of them as possible,
-    // in short dependency chains (two threads per matrix element, one shuffle).
+    // between the GEMMs of a geometry: Y from U0, then the P0 operand (the MMA warps wait for it), then the
+    // sum of the Y partials for the CHAIN warp.
     const int mtid = tid - (kMmaWarps + kFrontWarps) * 32, mwarp = warp - (kMmaWarps + kFrontWarps);
     const int col = (mwarp & 1) * 32 + lane, rg = mwarp >> 1;  // pair column; pair rows AB with (AB & 1) == rg
     const bool active = col < np;
     const int ci = active ? (pij[col] & 0xff) : 0, cj = active ? (pij[col] >> 8) : 0;
     const bool stamp = g_pipe_clk_on && blockIdx.x == 0 && mwarp == 0;
     const int e = mtid >> 1, half = mtid & 1;
-    constexpr int h0 = NC / 2;
-    const int r_lo = half ? h0 : 0, r_hi = half ? NC : h0;
     for (int it = 0; it < nloc; ++it) {
-      const int64_t g = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x;
       const int s = it % kStages, use = it / kStages;
       double* B1 = big + static_cast<size_t>(s) * 2 * S::SZ;  // U0 -> P0 (A-type)
-      const double* Xs = stage_small + s * M::per_stage;
-      const double* Vs = Xs + S::mat;
-      const double* Qh = Vs + S::mat;
-      const double* Gs = Qh + S::mat;
+      double* Xs = stage_small + s * M::per_stage;
+      double* Ysum = Xs + 4 * S::mat;
       PIPE_STAMP(1, 2, it, 0);
       mbar_wait(&bars->ready[s], use & 1);
       mbar_wait(&bars->u0[s], use & 1);
@@ -593,7 +699,7 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
       }
       mbar_arrive_warp(&bars->p0[s]);
       PIPE_STAMP(1, 2, it, 3);
-      // Z = Y/2 + hcore X (gamma + gamma^T), in a fixed summation order; thread `half` sums row group `half`
+      // Y = sum of the partials in a fixed order (thread `half` sums row group `half`, one shuffle)
       for (int e0 = 0; e0 < n2; e0 += kMidThreads / 2) {
         const int ee = e0 + e, ea = ee < n2 ? ee / n : 0, ec = ee < n2 ? ee - ea * n : 0;
         const double* yh = Ypart + static_cast<size_t>(half) * S::ncol * (2 * n);
@@ -605,49 +711,18 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
         }
         double t = t0 + t1;
         t += __shfl_xor_sync(0xffffffffu, t, 1);
-        if (ee < n2 && half == 0) Zm[ea * ld + ec] = t + Qh[ea * ld + ec];
+        if (ee < n2 && half == 0) Ysum[ea * ld + ec] = t;
       }
+      mbar_arrive_warp(&bars->cyz[it & 3]);
       PIPE_STAMP(1, 2, it, 4);
-      named_sync(3, kMidThreads);
-      // Omega = V (G o (V^T Z V)) V^T;  OmS = Omega + Omega^T
-      for (int e0 = 0; e0 < n2; e0 += kMidThreads / 2) {
-        const int ee = e0 + e, ea = ee < n2 ? ee / n : 0, ec = ee < n2 ? ee - ea * n : 0;
-        double t = 0.0;
-        for (int r = r_lo; r < r_hi; ++r) t = fma(Vs[r * ld + ea], Zm[r * ld + ec], t);
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        if (ee < n2 && half == 0) A2[ea * ld + ec] = t;
-      }
-      named_sync(3, kMidThreads);
-      for (int e0 = 0; e0 < n2; e0 += kMidThreads / 2) {
-        const int ee = e0 + e, ea = ee < n2 ? ee / n : 0, ec = ee < n2 ? ee - ea * n : 0;
-        double t = 0.0;
-        for (int r = r_lo; r < r_hi; ++r) t = fma(A2[ea * ld + r], Vs[r * ld + ec], t);
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        if (ee < n2 && half == 0) Bm[ea * ld + ec] = t * Gs[ea * ld + ec];
-      }
-      named_sync(3, kMidThreads);
-      for (int e0 = 0; e0 < n2; e0 += kMidThreads / 2) {
-        const int ee = e0 + e, ea = ee < n2 ? ee / n : 0, ec = ee < n2 ? ee - ea * n : 0;
-        double t = 0.0;
-        for (int r = r_lo; r < r_hi; ++r) t = fma(Vs[ea * ld + r], Bm[r * ld + ec], t);
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        if (ee < n2 && half == 0) A3[ea * ld + ec] = t;
-      }
-      named_sync(3, kMidThreads);
-      for (int e0 = 0; e0 < n2; e0 += kMidThreads / 2) {
-        const int ee = e0 + e, ea = ee < n2 ? ee / n : 0, ec = ee < n2 ? ee - ea * n : 0;
-        const int i = half ? ec : ea, j = half ? ea : ec;  // half 0: Omega[ea][ec], half 1: Omega[ec][ea]
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < NC; ++q) t = fma(A3[i * ld + q], Vs[j * ld + q], t);
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        if (ee < n2 && half == 0) OmSout[g * n2 + ee] = t;
-      }
+      named_sync(3, kMidThreads);  // the Y partials are consumed before the next geometry overwrites them
       mbar_arrive_warp(&bars->free_[s]);
       PIPE_STAMP(1, 2, it, 5);
     }
   } else if (warp >= kMmaWarps) {
     // ------------------------------ FRONT ------------------------------
+    // the inputs of geometry it: T by one bulk copy, the small matrices and the packed pair block of out7 by
+    // ordinary loads (all issued before the first dependent store: one round trip), Gm expanded to its image.
     const int ftid = tid - kMmaWarps * 32;
     const bool stamp = g_pipe_clk_on && blockIdx.x == 0 && warp == kMmaWarps;
     for (int it = 0; it < nloc; ++it) {
@@ -657,8 +732,10 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
       double* B2 = B1 + S::SZ;                                // Gm (A-type)
       double* Xs = stage_small + s * M::per_stage;
       double* Vs = Xs + S::mat;
-      double* Qh = Vs + S::mat;
-      double* Gs = Qh + S::mat;
+      double* Hc = Vs + S::mat;
+      double* Gam = Hc + S::mat;
+      double* rs = Gam + 2 * S::mat;
+      double* sv = rs + M::vec;
       PIPE_STAMP(1, 1, it, 0);
       if (use > 0) mbar_wait(&bars->free_[s], (use - 1) & 1);
       PIPE_STAMP(1, 1, it, 1);
@@ -668,8 +745,6 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
         bulk_g2s(B1, Timg + g * (static_cast<int64_t>(np) * pA), kLoadBytes, &bars->load[s]);
       }
       const double* o7 = out7 + g * L8;
-      named_sync(2, kFrontThreads);  // the previous geometry's readers of the front-private matrices are done
-      // every global load of this geometry is issued before the first dependent store: one round trip
       {
         constexpr int kPer = (ntri + kFrontThreads - 1) / kFrontThreads;
         double v[kPer], sx = 0.0, sv_ = 0.0, sh = 0.0, sg = 0.0, se = 0.0;
@@ -717,45 +792,7 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
         for (int k = np * pA + ftid; k < rows8 * pA; k += kFrontThreads) B2[k] = 0.0;
       }
       PIPE_STAMP(1, 1, it, 2);
-      named_sync(2, kFrontThreads);
-      PIPE_STAMP(1, 1, it, 3);
-      // first half of the one-electron chain: Pao = X gamma X^T, Qh = hcore X (gamma + gamma^T),
-      // G_pq = -1/(sqrt(s_p) sqrt(s_q) (sqrt(s_p) + sqrt(s_q)))  (exact divided differences of s^-1/2)
-      for (int k = ftid; k < n2; k += kFrontThreads) {
-        const int i = k / n, j = k - i * n;
-        double a1 = 0.0, z1 = 0.0;
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-          const double xr = Xs[i * ld + r];
-          a1 = fma(xr, Gam[r * ld + j], a1);
-          z1 = fma(xr, Gam[r * ld + j] + Gam[j * ld + r], z1);
-        }
-        A1[i * ld + j] = a1;
-        Z1[i * ld + j] = z1;
-        const double rp = rs[i], rq = rs[j];
-        double gpq = 0.0;
-        if (rp > 0.0 && rq > 0.0) {
-          gpq = -1.0 / (rp * rq * (rp + rq));
-        } else if ((rp > 0.0) != (rq > 0.0)) {
-          const double sp = sv[i], sq = sv[j];
-          if (sp != sq) gpq = ((rp > 0.0 ? 1.0 / rp : 0.0) - (rq > 0.0 ? 1.0 / rq : 0.0)) / (sp - sq);
-        }
-        Gs[i * ld + j] = gpq;
-      }
-      named_sync(2, kFrontThreads);
-      for (int k = ftid; k < n2; k += kFrontThreads) {
-        const int i = k / n, j = k - i * n;
-        double pao = 0.0, qh = 0.0;
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-          pao = fma(A1[i * ld + r], Xs[j * ld + r], pao);
-          qh = fma(Hc[i * ld + r], Z1[r * ld + j], qh);
-        }
-        PaoOut[g * n2 + k] = pao;
-        Qh[i * ld + j] = qh;
-      }
       // the bulk copy has landed: zero the padding of the T image (the array in HBM has none)
-      PIPE_STAMP(1, 1, it, 4);
       mbar_wait(&bars->load[s], use & 1);
       PIPE_STAMP(1, 1, it, 5);
       {
@@ -768,6 +805,7 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
         for (int k = np * pA + ftid; k < rows8 * pA; k += kFrontThreads) B1[k] = 0.0;
       }
       mbar_arrive_warp(&bars->ready[s]);
+      mbar_arrive_warp(&bars->cready[it & 3]);
       PIPE_STAMP(1, 1, it, 6);
     }
   } else {

@@ -126,3 +126,62 @@ def test_step_from_coordinates_uses_packed_arrays():
     E0, g0, _, _, _ = eng.energy_with_grad(stack, eng.ao_integrals(sb, co))      # full tensors, packed by the step
     assert np.array_equal(E0.cpu().numpy(), E1.cpu().numpy())
     assert np.array_equal(g0.cpu().numpy(), g1.cpu().numpy())
+
+
+@pytest.mark.parametrize("norb", list(range(2, 11)))
+def test_k4p_every_orbital_count_repeated(norb):
+    """K4p alone (hvec = [h1 | tril h2p] and the T image), pipelined kernel vs the one-CTA-per-geometry
+    kernel of packed.cu, for EVERY template instance n = 2..10, one geometry per CTA (3) and several ring
+    revolutions (700), each launched repeatedly: a scheduling-dependent fault of one instance (n = 5 once
+    dropped a k-step of one tile in most launches) does not hide behind a single lucky run."""
+    import ctypes as C
+    import torch
+    from evcont_b200.engine import get_engine, _ptr
+    from evcont_b200.mol import ao_bundle, synthetic_mol
+    eng = get_engine()
+    lib = eng.lib
+    fn = lib.evc_debug_packed_ao2oao
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+    fn.restype = C.c_int
+    b = [ao_bundle(synthetic_mol(norb, 2, seed=10 + k)) for k in range(8)]
+    L8, el = int(lib.evc_packed_row_len(norb)), int(lib.evc_erip_len(norb))
+    for G, reps in ((3, 12), (700, 4)):
+        S = eng.to_device(np.stack([b[k % 8]["ovlp"] for k in range(G)]))
+        X, _, _ = eng.loewdin(S)
+        hc = eng.to_device(np.stack([b[k % 8]["hcore"] for k in range(G)]))
+        erip, _ = eng.ao_pack8(eng.to_device(np.stack([b[k % 8]["eri"] for k in range(G)])), None)
+
+        def run(pipe):
+            hv = torch.zeros(G, L8, dtype=torch.float64, device=eng.device)
+            T = torch.zeros(G, el, dtype=torch.float64, device=eng.device)
+            eng._bind_stream()
+            assert fn(eng._ctx, G, norb, _ptr(X), _ptr(hc), _ptr(erip), _ptr(hv), _ptr(T), pipe) == 0
+            torch.cuda.synchronize()
+            npk, pitch = norb * (norb + 1) // 2, int(lib.evc_erip_pitch(norb))
+            return hv.cpu().numpy(), T.cpu().numpy().reshape(G, npk, pitch)[:, :, :npk]
+
+        hv0, T0 = run(0)
+        scale = max(1.0, np.abs(hv0).max())
+        for _ in range(reps):
+            hv1, T1 = run(1)
+            assert np.abs(hv1 - hv0).max() < 1e-11 * scale
+            assert np.abs(T1 - T0).max() < 1e-11 * scale
+
+
+@pytest.mark.parametrize("norb", list(range(2, 11)))
+def test_step_every_orbital_count_against_oracle(norb):
+    """The whole packed step (every template instance of K4p AND K8a, n = 2..10) against the numpy oracle of the
+    reference, one geometry per CTA and with the rings wrapping, three launches each."""
+    from oracle import gradients as og
+    natm = 2 if norb < 4 else 3
+    stack, mols, bundles, (ovlp, one, two), DeviceAO = _setup(norb, natm, 3, 6, 3, seed=4321 + norb)
+    eng = stack.engine
+    ref = [og.get_energy_with_grad(m, one, two, ovlp) for m in mols]
+    for G in (3, 600):
+        ao = DeviceAO.from_bundles(eng, [bundles[k % 3] for k in range(G)]).to_packed()
+        for _ in range(3):
+            E, g, _, _, _ = eng.energy_with_grad(stack, ao)
+            E, g = E.cpu().numpy(), g.cpu().numpy()
+            for k in range(G):
+                assert abs(E[k] - ref[k % 3][0]) < 1e-10, (G, k)
+                assert np.abs(g[k] - ref[k % 3][1]).max() < 1e-8, (G, k)
