@@ -68,6 +68,10 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
                     double* grad);
 // packed_pipe.cu
 bool evc_packed_pipe_supported(int n);
+// loewdin_reg.cu: K3 with the Jacobi eigensolver in registers (2 <= n <= 16), several matrices per warp
+bool evc_loewdin_reg_supported(int n);
+int evc_loewdin_reg_min_batch();
+int evc_loewdin_reg(evc_ctx* ctx, int nbatch, int n, const double* s_ao, double* x, double* evals, double* evecs);
 int evc_packed_ao2oao_pipe(evc_ctx* ctx, int nbatch, int n, const double* x, const double* hcore,
                            const double* erip, double* hvec, double* Tout);
 int evc_packed_grad_pipe(evc_ctx* ctx, int nbatch, int n, const double* x, const double* evals,

@@ -551,6 +551,9 @@ int evc_loewdin(evc_ctx* ctx, int nbatch, int n, const double* s_ao, double* x, 
   EVC_REQUIRE(ctx && s_ao && x && evals && evecs, "evc_loewdin: NULL argument");
   EVC_REQUIRE(n >= 1 && n <= 32, "evc_loewdin: n=%d unsupported (1..32)", n);
   if (nbatch <= 0) return 0;
+  // batches: the register-resident form (loewdin_reg.cu, several matrices per warp)
+  if (evc_loewdin_reg_supported(n) && nbatch >= evc_loewdin_reg_min_batch())
+    return evc_loewdin_reg(ctx, nbatch, n, s_ao, x, evals, evecs);
   const size_t smem = loewdin_smem_bytes(n);
   // many small problems (>= 16 per SM): one warp per geometry (0.136 ms per 4096 H10-size geometries against
   // 0.177 ms with 128 threads, whose barriers and idle lanes dominate); fewer problems: wider teams for latency
