@@ -55,12 +55,54 @@ def get_scanner(mol, one_rdm, two_rdm, overlap, hermitian=True):
     return Scanner()
 
 
+def write_xyz_trajectory(out, symbols, traj, times):
+    """Frames in the xyz form ``pyscf.md`` integrators write to ``trajectory_output`` (``_write_coord``: the
+    atom count, ``MD Time <t>``, then ``mol.tostring(format="raw")``: symbol and Cartesian coordinates in
+    Angstrom).  ``traj`` (nframes, natm, 3) in bohr, ``times`` in atomic units.  [Format from recollection of
+    pyscf/md/integrators.py -- PySCF is not installed here; any xyz reader parses it.]"""
+    from .mol import BOHR
+    close = isinstance(out, (str, os.PathLike))
+    fl = open(out, "w") if close else out
+    try:
+        for frame, t in zip(np.asarray(traj) * BOHR, times):
+            fl.write("%s\nMD Time %.2f\n" % (len(symbols), t))
+            for sym, (x, y, z) in zip(symbols, frame):
+                fl.write("%-4s %17.8f %17.8f %17.8f\n" % (sym, x, y, z))
+        fl.flush()
+    finally:
+        if close:
+            fl.close()
+
+
+def write_md_energies(out, times, epot, ekin):
+    """The table ``pyscf.md`` integrators write to ``energy_output`` / ``data_output`` (``_write_energy``): a
+    header line, then ``time  Epot  Ekin  Etot`` per step as ``%8.2f  %.12E  %.12E  %.12E`` (atomic units).
+    [Format from recollection of pyscf/md/integrators.py.]  Read it back with :func:`read_md_energies`."""
+    close = isinstance(out, (str, os.PathLike))
+    fl = open(out, "w") if close else out
+    try:
+        fl.write("   time          Epot                 Ekin                 Etot\n")
+        for t, ep, ek in zip(times, epot, ekin):
+            fl.write("%8.2f  %.12E  %.12E  %.12E\n" % (t, ep, ek, ep + ek))
+        fl.flush()
+    finally:
+        if close:
+            fl.close()
+
+
+def read_md_energies(path):
+    """(nsteps, 4) table ``time, Epot, Ekin, Etot`` of an energy file, with or without the header line (the
+    reference reads column 1 with ``np.genfromtxt``, evcont/MD_utils.py:208)."""
+    tab = np.atleast_2d(np.genfromtxt(path))
+    return tab[~np.isnan(tab).any(axis=1)]
+
+
 def get_trajectory(init_mol, overlap, one_rdm, two_rdm, dt=10.0, steps=10, init_veloc=None, hermitian=True,
                    trajectory_output=None, energy_output=None):
     """MD trajectory from the continuation, ``(steps, natm, 3)`` in bohr (evcont/MD_utils.py:60-125:
     ``pyscf.md.NVE`` with ``frames=[]``; frame 0 is the initial geometry).  The integrator runs on
-    the device; ``trajectory_output`` / ``energy_output`` (file names or file objects) receive plain
-    text tables (step, coordinates) / (step, E_pot, E_kin, E_tot) instead of PySCF's formats."""
+    the device; ``trajectory_output`` / ``energy_output`` (file names or file objects) receive the files
+    ``pyscf.md.NVE`` writes: xyz frames headed ``MD Time <t>`` and the ``time Epot Ekin Etot`` table."""
     if hermitian is not True:
         raise NotImplementedError("hermitian=False is not implemented on the device")
     from .md import DeviceNVE
@@ -73,11 +115,12 @@ def get_trajectory(init_mol, overlap, one_rdm, two_rdm, dt=10.0, steps=10, init_
                     max_frames=steps)
     nve.run(steps - 1)
     traj, epot, ekin = nve.frames()
+    times = dt * np.arange(len(traj))
     if trajectory_output is not None:
-        np.savetxt(trajectory_output, np.column_stack([np.arange(len(traj)), traj[:, 0].reshape(len(traj), -1)]))
+        write_xyz_trajectory(trajectory_output, [init_mol.atom_symbol(i) for i in range(init_mol.natm)], traj[:, 0],
+                             times)
     if energy_output is not None:
-        np.savetxt(energy_output, np.column_stack([np.arange(len(traj)), epot[:, 0], ekin[:, 0],
-                                                   epot[:, 0] + ekin[:, 0]]))
+        write_md_energies(energy_output, times, epot[:, 0], ekin[:, 0])
     return traj[:, 0]
 
 
@@ -141,7 +184,7 @@ def _run_trajectory(obj, init_mol, i, steps, dt, workdir):
                           trajectory_output=os.path.join(workdir, "traj_EVCont_{}.xyz".format(i)),
                           energy_output=os.path.join(workdir, "ens_EVCont_{}.xyz".format(i)))
     np.save(os.path.join(workdir, "traj_EVCont_{}.npy".format(i)), traj)
-    ens = np.ascontiguousarray(np.atleast_2d(np.genfromtxt(os.path.join(workdir, "ens_EVCont_{}.xyz".format(i))))[:, 1])
+    ens = np.ascontiguousarray(read_md_energies(os.path.join(workdir, "ens_EVCont_{}.xyz".format(i)))[:, 1])
     return traj, ens
 
 
@@ -193,7 +236,7 @@ def converge_EVCont_MD(EVCont_obj, init_mol, steps=100, dt=1, convergence_thresh
         if os.path.exists(path("traj_EVCont_{}.npy".format(i))):
             trajectory = np.load(path("traj_EVCont_{}.npy".format(i)))
             updated_ens = np.ascontiguousarray(
-                np.atleast_2d(np.genfromtxt(path("ens_EVCont_{}.xyz".format(i))))[:, 1])
+                read_md_energies(path("ens_EVCont_{}.xyz".format(i)))[:, 1])
         else:
             trajectory, updated_ens = _run_trajectory(EVCont_obj, init_mol, i, steps, dt, workdir)
         if i > 0:

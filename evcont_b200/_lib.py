@@ -130,6 +130,12 @@ SIGNATURES = {
     "evc_ao_integrals_sp_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, c_sz_p]),
     "evc_ao_integrals_sp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9 +
                             [C.c_void_p, C.c_size_t]),
+    "evc_aotable_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "evc_aotable_destroy": (C.c_int, [C.c_void_p]),
+    "evc_center_of_mass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_double_p]),
+    "evc_int1e_r": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]),
+    "evc_rdm1_observables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [c_double_p] * 9),
     "evc_fci_hdiag": (C.c_int, [C.c_void_p, C.c_int, c_i64, c_i64, C.c_void_p, C.c_void_p, c_double_p,
                                 c_double_p, c_double_p]),
     "evc_fci_contract_workspace_bytes": (C.c_int, [C.c_int, c_i64, c_i64, c_sz_p]),

@@ -57,6 +57,7 @@ class Engine:
         self.sm_count = self.lib.evc_ctx_sm_count(handle)
         self._links = {}
         self._sbases = {}
+        self._aotables = {}
         self._ws = {}            # shared scratch, one Workspace per CUDA stream
         self._ws_private = None  # a caller-owned Workspace (using_workspace)
 
@@ -354,6 +355,57 @@ class Engine:
             self._sbases[key] = SBasis(self, symbols, basis)
         return self._sbases[key]
 
+    # -- f4: observables of the predicted one-body density matrix ---------------------------
+    def aotable(self, symbols, basis, masses=None):
+        """Device AO table (:class:`AOTable`) of the atoms ``symbols``: basis functions + nuclear charges + masses
+        (atomic mass units; default: most common isotope, ``mol.atom_mass_list()``)."""
+        from .md import COMMON_ISOTOPE_MASSES
+        syms = tuple(s.capitalize() for s in symbols)
+        m = tuple(COMMON_ISOTOPE_MASSES[s] for s in syms) if masses is None else tuple(float(v) for v in masses)
+        key = (syms, basis.lower(), m)
+        if key not in self._aotables:
+            self._aotables[key] = AOTable(self, syms, basis, np.asarray(m, dtype=np.float64))
+        return self._aotables[key]
+
+    def center_of_mass(self, table, coords):
+        coords = self.to_device(coords).reshape(-1, table.natm, 3)
+        out = self.empty(coords.shape[0], 3)
+        self._bind_stream()
+        check(self.lib.evc_center_of_mass(self._ctx, table.handle, coords.shape[0], _ptr(coords), _ptr(out)))
+        return out
+
+    def int1e_r(self, table, coords, origin=None):
+        """``<i| r - origin |j>`` (G, 3, n, n); ``origin`` (G, 3) or (3,), default: the centre of mass."""
+        coords = self.to_device(coords).reshape(-1, table.natm, 3)
+        G = coords.shape[0]
+        if origin is None:
+            origin = self.center_of_mass(table, coords)
+        else:
+            origin = self.to_device(np.broadcast_to(np.asarray(origin, dtype=np.float64).reshape(-1, 3), (G, 3)).copy()
+                                    if not torch.is_tensor(origin) else origin).reshape(G, 3).contiguous()
+        out = self.empty(G, 3, table.nao, table.nao)
+        self._bind_stream()
+        check(self.lib.evc_int1e_r(self._ctx, table.handle, G, _ptr(coords), _ptr(origin), _ptr(out)))
+        return out
+
+    def rdm1_observables(self, table, coords, x, gamma, ovlp=None, method="mulliken", want_dm_ao=False):
+        """Dipole moment about the centre of mass (G, 3), atomic units, and atomic charges (G, natm) of the
+        one-body density matrices ``gamma`` (G, n, n) given in the orthogonalised basis ``x`` (G, n, n)."""
+        meth = {"mulliken": 0, "loewdin": 1, "lowdin": 1}[method.lower()]
+        coords = self.to_device(coords).reshape(-1, table.natm, 3)
+        G, n = coords.shape[0], table.nao
+        x, gamma = self.to_device(x).reshape(G, n, n), self.to_device(gamma).reshape(G, n, n)
+        ovlp = None if ovlp is None else self.to_device(ovlp).reshape(G, n, n)
+        origin = self.center_of_mass(table, coords)
+        rint = self.int1e_r(table, coords, origin)
+        dm = self.empty(G, n, n) if want_dm_ao else None
+        dip, chg = self.empty(G, 3), self.empty(G, table.natm)
+        self._bind_stream()
+        check(self.lib.evc_rdm1_observables(self._ctx, table.handle, G, meth, _ptr(coords), _ptr(origin), _ptr(x),
+                                            _ptr(gamma), _ptr(ovlp) if ovlp is not None else None, _ptr(rint),
+                                            _ptr(dm) if dm is not None else None, _ptr(dip), _ptr(chg)))
+        return (dip, chg, dm) if want_dm_ao else (dip, chg)
+
     def ao_integrals(self, sbasis, coords, out=None, packed=False):
         """AO integrals of a batch of geometries on the device: ``coords`` (G, natm, 3) in
         bohr (device tensor or numpy) -> :class:`DeviceAO` (filled in place if given).
@@ -596,6 +648,34 @@ class FCIHamiltonian:
                                           _ptr(self.link_b), self.nlink_b, _ptr(self.h1eff), _ptr(self.w2),
                                           _ptr(c), _ptr(out), _ptr(ws), ws.numel()))
         return out
+
+
+class AOTable:
+    """Device copy of a basis description with nuclear charges and masses (``evc_aotable``): what the
+    observables of the predicted density matrix need."""
+
+    def __init__(self, engine, symbols, basis, masses):
+        from .basis import has_p_shells, s_basis_tables, sp_basis_tables
+        self.engine, self.symbols, self.basis = engine, tuple(symbols), basis.lower()
+        general = has_p_shells(self.symbols, self.basis)
+        t = sp_basis_tables(self.symbols, self.basis) if general else s_basis_tables(self.symbols, self.basis)
+        self.tables, self.masses = t, np.ascontiguousarray(masses, dtype=np.float64)
+        self.natm, self.nao = len(self.symbols), len(t["ao_atom"])
+        handle = C.c_void_p()
+        with torch.cuda.device(engine.device):
+            check(engine.lib.evc_aotable_create(
+                engine._ctx, self.natm, t["charges"].ctypes.data, self.masses.ctypes.data, self.nao,
+                t["ao_atom"].ctypes.data, t["ao_pow"].ctypes.data if general else None, t["ao_nprim"].ctypes.data,
+                t["prim_exp"].ctypes.data, t["prim_wt"].ctypes.data, C.byref(handle)))
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.engine.lib.evc_aotable_destroy(self.handle)
+                self.handle = None
+        except Exception:  # interpreter shutdown
+            pass
 
 
 class SBasis:

@@ -130,6 +130,32 @@ class MolLite:
     def atom_charges(self):
         return self._tables["charges"].astype(int)
 
+    def atom_mass_list(self, isotope_avg=False):
+        """Masses in atomic mass units (most common isotope, PySCF's default)."""
+        if isotope_avg:
+            raise NotImplementedError("isotope-averaged masses are not tabulated")
+        from .md import COMMON_ISOTOPE_MASSES
+        return np.array([COMMON_ISOTOPE_MASSES[s] for s in self._symbols])
+
+    def with_common_orig(self, origin):
+        """Context manager: origin of the ``int1e_r`` operator (``pyscf.gto.Mole.with_common_orig``)."""
+        mol = self
+
+        class _Ctx:
+            def __enter__(self):
+                self.old = getattr(mol, "_common_orig", None)
+                mol._common_orig = np.asarray(origin, dtype=np.float64).reshape(3)
+                return mol
+
+            def __exit__(self, *exc):
+                mol._common_orig = self.old
+                return False
+
+        return _Ctx()
+
+    def intor_symmetric(self, name, comp=None):
+        return self.intor(name, comp=comp)
+
     def set_geom_(self, coords, unit="Bohr", inplace=True):
         mol = self if inplace else self.copy()
         scale = 1.0 if unit.lower().startswith(("b", "au")) else 1.0 / BOHR
@@ -167,6 +193,12 @@ class MolLite:
         return self._cache
 
     def intor(self, name, comp=None):
+        if name == "int1e_r":
+            from .engine import get_engine
+            eng = get_engine()
+            origin = getattr(self, "_common_orig", None)
+            origin = np.zeros(3) if origin is None else origin
+            return eng.int1e_r(eng.aotable(self._symbols, self.basis), self._coords[None], origin)[0].cpu().numpy()
         key = {"int1e_ovlp": "ovlp", "int1e_ipovlp": "ipovlp", "int2e": "eri", "int2e_ip1": "eri_ip1"}.get(name)
         if key is None:
             raise KeyError(f"MolLite serves {_INTOR_NAMES}, not {name!r}")

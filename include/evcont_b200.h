@@ -399,6 +399,33 @@ int evc_ao_integrals_sp(evc_ctx *ctx, const evc_gbasis *basis, int nbatch, const
                         double *hcore_deriv, double *eri_ip1, double *e_nuc, double *grad_nuc,
                         void *workspace, size_t workspace_bytes);
 
+/* ---- f4: observables of the predicted one-body density matrix ---------------------------
+ * What the reference's MD callback evaluates from scanner.base.predicted_one_rdm
+ * (scripts/MD/Zundel_thermodynamics/continuation/04_Zundel_continuation_MD.py:71-92 dip_moment,
+ * :140-159 callback), batched over geometries.  The AO table is the basis description of
+ * evc_gbasis_create (ao_pow_host may be NULL: s functions only) plus the atomic masses.
+ *   evc_center_of_mass     origin [G][3] from coords [G][natm][3]
+ *   evc_int1e_r            r [G][3][n][n] = <i| r - origin |j>: mol.intor_symmetric("int1e_r", comp=3)
+ *                          inside mol.with_common_orig(origin)
+ *   evc_rdm1_observables   dm_ao = X gamma X^T (written when dm_ao != NULL), dipole [G][3] =
+ *                          sum_A Z_A (R_A - origin) - sum_ij r_ij dm_ji (atomic units), atom_charges
+ *                          [G][natm] = Z_A - sum_{mu on A} n_mu with method 0: Mulliken n_mu = (dm S)_mu,mu
+ *                          (needs ovlp), 1: Loewdin n_mu = gamma_mu,mu (x symmetric: x = S^-1/2). */
+typedef struct evc_aotable evc_aotable;
+int evc_aotable_create(evc_ctx *ctx, int natm, const double *charges_host, const double *masses_host,
+                       int nao, const int32_t *ao_atom_host, const int32_t *ao_pow_host,
+                       const int32_t *ao_nprim_host, const double *prim_exp_host,
+                       const double *prim_wt_host, evc_aotable **out);
+int evc_aotable_destroy(evc_aotable *table);
+int evc_center_of_mass(evc_ctx *ctx, const evc_aotable *table, int nbatch, const double *coords,
+                       double *origin);
+int evc_int1e_r(evc_ctx *ctx, const evc_aotable *table, int nbatch, const double *coords,
+                const double *origin, double *r);
+int evc_rdm1_observables(evc_ctx *ctx, const evc_aotable *table, int nbatch, int method,
+                         const double *coords, const double *origin, const double *x,
+                         const double *gamma, const double *ovlp, const double *rint, double *dm_ao,
+                         double *dipole, double *atom_charges);
+
 /* ---- FCI Hamiltonian action (training side) ------------------------------------------
  * What cisolver.kernel (evcont/FCI_EVCont.py:70; PySCF direct_spin0 Davidson:
  * contract_2e + make_hdiag) needs from the Hamiltonian, on the device with the K0 link
