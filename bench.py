@@ -479,6 +479,56 @@ def run_stream_legs(args, eng, torch, hbm_peak):
     return out
 
 
+def run_pair_sharded_leg(args, eng, torch, world, rank):
+    """e3: ONE trajectory against a Zundel-size stack (n = 28, N = 100, 12.4 GB in
+    the exchange-compressed lower-triangular layout) sharded by training pairs over the ranks: per step every rank
+    streams its slab twice (K5, K7), the ranks all_gather 5050 H entries and all_reduce one compressed two-body
+    density matrix (2.4 MB).  At N = 1 the same code runs on the whole stack (the latency the sharding cuts)."""
+    from evcont_b200 import distributed as evd
+    from evcont_b200.engine import DeviceAO
+    from evcont_b200.mol import ao_bundle, synthetic_mol
+    n, N, natm = 28, 100, 7
+    n2 = n * n
+    L, P = n2 * (n2 + 1) // 2, N * (N + 1) // 2
+    lo, hi = evd.shard_range(P, rank, world)
+    gen = torch.Generator(device=eng.device)
+    gen.manual_seed(11 + rank)
+    rows = torch.randn(hi - lo, L, generator=gen, dtype=torch.float64, device=eng.device) / n2
+    g0 = torch.Generator(device=eng.device)
+    g0.manual_seed(5)
+    one = torch.randn(N, N, n, n, generator=g0, dtype=torch.float64, device=eng.device)
+    one = one + one.transpose(0, 1)
+    b = torch.randn(N, N, generator=g0, dtype=torch.float64, device=eng.device)
+    S = torch.eye(N, dtype=torch.float64, device=eng.device) + 0.001 * (b + b.T)
+    shard = evd.PairShardedStack(S, one, rows, lo, hi, engine=eng)
+    ao = DeviceAO.from_bundles(eng, [ao_bundle(synthetic_mol(n, natm, seed=77))])
+    step = (lambda: evd.sharded_energy_with_grad(shard, ao)) if world > 1 else \
+           (lambda: evd.sharded_energy_with_grad([shard], ao))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    slab_bytes = rows.numel() * 8
+    del shard, rows
+    torch.cuda.empty_cache()
+    return {"workload": "one trajectory, Zundel / 6-31G sizes: n = 28, N = 100, layout (N(N+1)/2, n^2(n^2+1)/2)",
+            "stack_GB": P * L * 8 / 1e9, "slab_GB_per_gpu": slab_bytes / 1e9, "ms_per_step": ms,
+            "steps_per_s": 1e3 / ms, "collectives_per_step": "all_gather of %d H entries + all_reduce of %d doubles"
+            % (P, L) if world > 1 else "none (one slab)",
+            "slab_stream_GBps": 2 * slab_bytes / (ms * 1e-3) / 1e9}
+
+
 def run_trdm_sizes(args, eng, torch, dgemm_tf):
     """trans_rdm12 pairs/s at the other BASELINE sizes: H6 / STO-6G (configs[0]: 6 orbitals, 400 determinants,
     3 states -> 6 pairs) and H2O / 6-31G (configs[2]: 13 orbitals, 1 656 369 determinants, 4 states -> 10 pairs)."""
@@ -720,6 +770,14 @@ def run_b200(args):
             if world > 1:
                 raise          # ranks must stay in step inside the collectives of timed()
             sp_legs = {"error": f"{type(exc).__name__}: {exc}"}
+    pair_sharded = None
+    if not args.no_extra:
+        try:
+            pair_sharded = run_pair_sharded_leg(args, eng, torch, world, rank)
+        except Exception as exc:  # noqa: BLE001 -- reported in the JSON line
+            if world > 1:
+                raise
+            pair_sharded = {"error": f"{type(exc).__name__}: {exc}"}
     t1 = time.time()
     if world == 1 and not args.no_extra:   # single-GPU diagnostics (no collectives inside)
         for name, fn in (("latency", lambda: run_latency_leg(args, eng, stack, torch)),
@@ -819,6 +877,7 @@ def run_b200(args):
         "from_coordinates_sp": sp_legs,
         "latency": latency,
         "stack_streaming": stream_legs,
+        "pair_sharded_stack": pair_sharded,
         "trans_rdm12_sizes": trdm_sizes,
     }
     print(json.dumps(line), flush=True)

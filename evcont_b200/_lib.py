@@ -130,6 +130,13 @@ SIGNATURES = {
     "evc_ao_integrals_sp_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, c_sz_p]),
     "evc_ao_integrals_sp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9 +
                             [C.c_void_p, C.c_size_t]),
+    "evc_exchange_compress": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]),
+    "evc_exchange_restore": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]),
+    "evc_stack_rows_workspace_bytes": (C.c_int, [c_i64, C.c_int, C.c_int, c_sz_p]),
+    "evc_stack_rows_dot": (C.c_int, [C.c_void_p, c_double_p, c_i64, C.c_int, c_double_p, C.c_int, c_double_p,
+                                     C.c_void_p, C.c_size_t]),
+    "evc_stack_rows_axpy": (C.c_int, [C.c_void_p, c_double_p, c_i64, C.c_int, c_double_p, C.c_int, c_double_p,
+                                      C.c_void_p, C.c_size_t]),
     "evc_aotable_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "evc_aotable_destroy": (C.c_int, [C.c_void_p]),

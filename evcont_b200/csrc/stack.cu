@@ -391,7 +391,7 @@ size_t evc_rows_dot_ws_bytes(int64_t L, int P, int G) {
 
 int evc_rows_dot(evc_ctx* ctx, const double* rows, int64_t L, int P, const double* hv, int G, double* out,
                  void* workspace, size_t workspace_bytes) {
-  EVC_REQUIRE(L < (int64_t(1) << 31) && (L & 1) == 0, "rows_dot: bad row length %lld", (long long)L);
+  EVC_REQUIRE(L < (int64_t(1) << 31) && L >= 1, "rows_dot: bad row length %lld", (long long)L);
   EVC_REQUIRE(workspace_bytes >= evc_rows_dot_ws_bytes(L, P, G), "rows_dot: workspace too small");
   double* partial = static_cast<double*>(workspace);
   if (G > kGemvMaxBatch) {
@@ -408,7 +408,8 @@ int evc_rows_dot(evc_ctx* ctx, const double* rows, int64_t L, int P, const doubl
   const int gb = stream_gb(G), rb = stream_rb(gb);
   dim3 grid((P + rb - 1) / rb, nchunk, (G + gb - 1) / gb);
   EVC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "rows_dot: batch/stack too large for one launch");
-  const bool vec2 = ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) && ((reinterpret_cast<uintptr_t>(hv) & 15) == 0);
+  const bool vec2 = (L % 2 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(hv) & 15) == 0);
 #define EVC_DOT(RB, GB)                                                                                  \
   do {                                                                                                   \
     if (vec2) stack_dot_kernel<RB, GB, true><<<grid, 256, 0, ctx->stream>>>(rows, L, P, hv, G, nchunk, partial); \
@@ -437,7 +438,7 @@ size_t evc_rows_axpy_ws_bytes(int64_t L, int P, int G) {
 
 int evc_rows_axpy(evc_ctx* ctx, const double* rows, int64_t L, int P, const double* w, int G, double* out,
                   void* workspace, size_t workspace_bytes) {
-  EVC_REQUIRE(L < (int64_t(1) << 31) && (L & 1) == 0, "rows_axpy: bad row length %lld", (long long)L);
+  EVC_REQUIRE(L < (int64_t(1) << 31) && L >= 1, "rows_axpy: bad row length %lld", (long long)L);
   EVC_REQUIRE(workspace_bytes >= evc_rows_axpy_ws_bytes(L, P, G), "rows_axpy: workspace too small");
   if (G > kGemvMaxBatch) {
     evc_gemm::Plan pl;
@@ -447,7 +448,7 @@ int evc_rows_axpy(evc_ctx* ctx, const double* rows, int64_t L, int P, const doub
   }
   double* part = static_cast<double*>(workspace);
   const int nsplit = axpy_nsplit(L, P, G);
-  const bool vec2 = (reinterpret_cast<uintptr_t>(rows) & 15) == 0;
+  const bool vec2 = (L % 2 == 0) && (reinterpret_cast<uintptr_t>(rows) & 15) == 0;
   const int64_t per_block = vec2 ? 512 : 256;
   const int gb = stream_gb(G);
   dim3 grid(static_cast<unsigned>((L + per_block - 1) / per_block), nsplit, (G + gb - 1) / gb);
@@ -630,6 +631,48 @@ int evc_predict_rdm(evc_ctx* ctx, int layout, int N, int n, const double* one_rd
     EVC_CHECK_LAUNCH();
   }
   return 0;
+}
+
+// ---- e3: the row operations of K5 / K7 on a SLAB of training pairs (pair-sharded stack) ----------------
+int evc_exchange_compress(evc_ctx* ctx, int n, int nbatch, const double* h2, double* h2c) {
+  EVC_REQUIRE(ctx && h2 && h2c && n >= 1, "evc_exchange_compress: bad argument");
+  if (nbatch <= 0) return 0;
+  const int64_t L = exch_len(n);
+  dim3 grid(static_cast<unsigned>((L + 255) / 256), nbatch);
+  pack_exchange_kernel<<<grid, 256, 0, ctx->stream>>>(n * n, L, h2, h2c);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_exchange_restore(evc_ctx* ctx, int n, int nbatch, const double* gc, double* Gamma) {
+  EVC_REQUIRE(ctx && gc && Gamma && n >= 1, "evc_exchange_restore: bad argument");
+  if (nbatch <= 0) return 0;
+  const int64_t n4 = static_cast<int64_t>(n) * n * n * n;
+  dim3 grid(static_cast<unsigned>((n4 + 255) / 256), nbatch);
+  gamma2_finalize_kernel<<<grid, 256, 0, ctx->stream>>>(n * n, 1, exch_len(n), nbatch, 1, gc, Gamma);
+  EVC_CHECK_LAUNCH();
+  return 0;
+}
+
+int evc_stack_rows_workspace_bytes(int64_t row_len, int nrows, int nbatch, size_t* bytes) {
+  EVC_REQUIRE(bytes && row_len >= 2 && nrows >= 1 && nbatch >= 1, "evc_stack_rows_workspace_bytes: bad argument");
+  const size_t a = evc_rows_dot_ws_bytes(row_len, nrows, nbatch), b = evc_rows_axpy_ws_bytes(row_len, nrows, nbatch);
+  *bytes = a > b ? a : b;
+  return 0;
+}
+
+int evc_stack_rows_dot(evc_ctx* ctx, const double* rows, int64_t row_len, int nrows, const double* hv, int nbatch,
+                       double* out, void* workspace, size_t workspace_bytes) {
+  EVC_REQUIRE(ctx && rows && hv && out && workspace, "evc_stack_rows_dot: NULL argument");
+  if (nbatch <= 0 || nrows <= 0) return 0;
+  return evc_rows_dot(ctx, rows, row_len, nrows, hv, nbatch, out, workspace, workspace_bytes);
+}
+
+int evc_stack_rows_axpy(evc_ctx* ctx, const double* rows, int64_t row_len, int nrows, const double* w, int nbatch,
+                        double* out, void* workspace, size_t workspace_bytes) {
+  EVC_REQUIRE(ctx && rows && w && out && workspace, "evc_stack_rows_axpy: NULL argument");
+  if (nbatch <= 0 || nrows <= 0) return 0;
+  return evc_rows_axpy(ctx, rows, row_len, nrows, w, nbatch, out, workspace, workspace_bytes);
 }
 
 }  // extern "C"

@@ -189,6 +189,27 @@ int evc_predict_rdm(evc_ctx *ctx, int layout, int ntrain, int n, const double *o
                     const double *two_rdm, int nbatch, const double *C, int64_t c_stride,
                     double *gamma, double *Gamma, void *workspace, size_t workspace_bytes);
 
+/* ---- e3: K5 / K7 on a slab of training pairs (pair-sharded stack, one trajectory) -------
+ * for a stack too large or too slow to stream on one GPU
+ * (Zundel, N = 100: 12.5 GB per step) every rank keeps a contiguous slab of the lower-triangular
+ * pair list of the exchange-compressed layouts (np.tril_indices order, the per-pair directories of
+ * scripts/MD/Zundel_thermodynamics/continuation/04_Zundel_continuation_MD.py:99-128), computes
+ * its entries of H, and its share of the predicted two-body density matrix; the entries are
+ * all-gathered, the shares all-reduced (evcont_b200/distributed.py).
+ *   evc_exchange_compress   h2c [G][n2 (n2+1)/2] = lower triangle of h2 [G][n2][n2], diagonal halved
+ *                           (compress_electron_exchange_symmetry(h2, 0.5), electron_integral_utils.py:38-66)
+ *   evc_exchange_restore    Gamma [G][n^4] from its compressed form (restore_..., :69-88)
+ *   evc_stack_rows_dot      out [G][nrows] = sum_l rows[p][l] hv[g][l]
+ *   evc_stack_rows_axpy     out [G][row_len] = sum_p w[g][p] rows[p][l]
+ * Few geometries stream the rows once at HBM speed; more than 16 run on the FP64 tensor cores. */
+int evc_exchange_compress(evc_ctx *ctx, int n, int nbatch, const double *h2, double *h2c);
+int evc_exchange_restore(evc_ctx *ctx, int n, int nbatch, const double *gamma2c, double *Gamma);
+int evc_stack_rows_workspace_bytes(int64_t row_len, int nrows, int nbatch, size_t *bytes);
+int evc_stack_rows_dot(evc_ctx *ctx, const double *rows, int64_t row_len, int nrows, const double *hv,
+                       int nbatch, double *out, void *workspace, size_t workspace_bytes);
+int evc_stack_rows_axpy(evc_ctx *ctx, const double *rows, int64_t row_len, int nrows, const double *w,
+                        int nbatch, double *out, void *workspace, size_t workspace_bytes);
+
 /* ---- K8: electronic gradient in the Loewdin basis -------------------------
  * Replaces get_grad_elec_OAO and its callees
  * (evcont/ab_initio_gradients_loewdin.py:13-305) in the adjoint form of

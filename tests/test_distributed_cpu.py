@@ -91,3 +91,52 @@ def test_shard_ranges_cover_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
             assert evd.slab_size(n, w) == max(h - l for l, h in spans)
+
+
+# ---- e3: the pair-sharded prediction step (host logic: slab ranges, all_gather order, pair weights) ----
+def _sharded_step_worker(rank, world, port, ntrain, norb, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conftest import synthetic_stack
+    from evcont_b200 import distributed as evd
+    from oracle import subspace as osub
+    ovlp, one, two = synthetic_stack(norb, ntrain, 5, 2)           # (N(N+1)/2, n2(n2+1)/2) rows
+    rng = np.random.default_rng(1)
+    h1 = rng.standard_normal((norb, norb)); h1 = h1 + h1.T
+    h2 = rng.standard_normal((norb * norb, norb * norb)); h2 = (h2 + h2.T).reshape((norb,) * 4)
+    npairs = two.shape[0]
+    lo, hi = evd.shard_range(npairs, rank, world)
+    rows = two[lo:hi]                                              # this rank's slab; numpy stands in for the row kernels
+    hv = osub.compress_exchange(h2, 0.5)
+    part = torch.from_numpy(rows @ hv).reshape(-1, 1)
+    h_two = evd.gather_pair_entries(part, npairs).numpy()[:, 0]
+    il = np.tril_indices(ntrain)
+    H = np.zeros((ntrain, ntrain))
+    H[il] = np.einsum("abij,ij->ab", one, h1)[il] + h_two
+    H = np.tril(H) + np.tril(H, -1).T
+    E, vec = osub._solve(H, ovlp, True)
+    c = vec[:, 0] if vec.ndim == 2 else vec
+    a, b = il[0][lo:hi], il[1][lo:hi]
+    w = c[a] * c[b] * np.where(a == b, 1.0, 2.0)
+    g2c = torch.from_numpy(w @ rows)
+    dist.all_reduce(g2c)
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), H=H, g2c=g2c.numpy(), c=c, h1=h1, h2=h2)
+    dist.destroy_process_group()
+
+
+def test_pair_sharded_step_matches_the_unsharded_formulas(tmp_path):
+    from conftest import synthetic_stack
+    from oracle import gradients as og
+    from oracle import subspace as osub
+    ntrain, norb, world = 5, 3, 2
+    mp.spawn(_sharded_step_worker, args=(world, _free_port(), ntrain, norb, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(os.path.join(tmp_path, f"s{k}.npz")) for k in range(world)]
+    for k in ("H", "g2c", "c"):
+        assert np.array_equal(r[0][k], r[1][k]), k
+    ovlp, one, two = synthetic_stack(norb, ntrain, 5, 2)
+    Href = osub.subspace_hamiltonian(r[0]["h1"], r[0]["h2"], one, two)
+    assert np.abs(np.tril(r[0]["H"]) - np.tril(Href)).max() < 1e-12
+    _, Gamma = og.predict_rdms(r[0]["c"], one, two, norb)
+    assert np.abs(osub.restore_exchange(r[0]["g2c"], norb) - Gamma).max() < 1e-12
