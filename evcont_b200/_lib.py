@@ -130,6 +130,7 @@ SIGNATURES = {
     "evc_ao_integrals_sp_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, c_sz_p]),
     "evc_ao_integrals_sp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [c_double_p] * 9 +
                             [C.c_void_p, C.c_size_t]),
+    "evc_trans_rdm12_plan_pairs": (C.c_int, [C.c_void_p, C.c_int]),
     "evc_exchange_compress": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     "evc_exchange_restore": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     "evc_stack_rows_workspace_bytes": (C.c_int, [c_i64, C.c_int, C.c_int, c_sz_p]),

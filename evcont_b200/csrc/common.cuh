@@ -24,6 +24,7 @@ struct evc_ctx {
   int sm_count;
   size_t smem_optin;
   double last_trdm_flops;
+  int trdm_plan_pairs;  // evc_trans_rdm12_plan_pairs: pair count the alpha-slice plan is made for (0: the call's own)
   // optional per-stage timing of evc_energy_with_grad (evc_ctx_stage_timing)
   int stage_timing;
   cudaEvent_t stage_ev[EVC_NSTAGE + 1];

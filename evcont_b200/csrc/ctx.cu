@@ -38,6 +38,7 @@ int evc_ctx_create(int device, void* stream, evc_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->last_trdm_flops = 0.0;
+  c->trdm_plan_pairs = 0;
   c->stage_timing = 0;
   c->stage_calls = 0;
   c->stage_pending = 0;

@@ -405,7 +405,11 @@ int evc_trans_rdm12_batch_strided(evc_ctx* ctx, int norb, int64_t na, int64_t nb
   EVC_REQUIRE((reinterpret_cast<uintptr_t>(civecs) & 15) == 0 && (vec_stride & 1) == 0,
               "evc_trans_rdm12_batch: civecs must be 16-byte aligned with an even stride");
   TrdmPlan pl;
-  EVC_REQUIRE(plan_trdm(norb, na, nb, npairs, ctx->sm_count, &pl) == 0,
+  // the alpha-slice count fixes the summation order of a pair's result: planned for the pair count of the WHOLE
+  // build when the caller computes only a share of it (evc_trans_rdm12_plan_pairs), so that a pair's bits do not
+  // depend on how many ranks share the build
+  const int plan_pairs = ctx->trdm_plan_pairs > npairs ? ctx->trdm_plan_pairs : npairs;
+  EVC_REQUIRE(plan_trdm(norb, na, nb, plan_pairs, ctx->sm_count, &pl) == 0,
               "evc_trans_rdm12_batch: no launch plan for norb=%d nb=%lld", norb, (long long)nb);
   const size_t need = static_cast<size_t>(npairs) * pl.nsplit * pl.T * 256 * sizeof(double);
   EVC_REQUIRE(workspace_bytes >= need, "evc_trans_rdm12_batch: workspace %zu < %zu bytes", workspace_bytes, need);
@@ -460,6 +464,12 @@ int evc_trans_rdm12_batch(evc_ctx* ctx, int norb, int64_t na, int64_t nb, const 
 }
 
 double evc_trans_rdm12_last_issued_flops(const evc_ctx* ctx) { return ctx ? ctx->last_trdm_flops : 0.0; }
+
+int evc_trans_rdm12_plan_pairs(evc_ctx* ctx, int total_pairs) {
+  EVC_REQUIRE(ctx && total_pairs >= 0, "evc_trans_rdm12_plan_pairs: bad argument");
+  ctx->trdm_plan_pairs = total_pairs;
+  return 0;
+}
 
 int64_t evc_stack_row_len(int norb) {
   const int64_t n2 = static_cast<int64_t>(norb) * norb;

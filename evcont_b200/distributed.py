@@ -111,7 +111,7 @@ def build_stack_sharded(civecs, norb, nelec, pair_fn=None, group=None, device=No
     if pair_fn is None:
         from .engine import get_engine
         eng = get_engine(device)
-        rows = eng.trans_rdm12_rows(civecs, padded, n, nelec)
+        rows = eng.trans_rdm12_rows(civecs, padded, n, nelec, plan_pairs=len(pairs))
     else:
         ovlp, dm1, dm2 = pair_fn(civecs, padded)
         rows = dm2.new_zeros((slab, width))

@@ -173,10 +173,11 @@ class Engine:
             _ptr(ws), ws.numel()))
         return ovlp, dm1, dm2
 
-    def trans_rdm12_rows(self, civecs, pairs, norb, nelec):
+    def trans_rdm12_rows(self, civecs, pairs, norb, nelec, plan_pairs=0):
         """Like :meth:`trans_rdm12_batch`, but every pair's results form one contiguous row
         ``[dm2 (n^4) | dm1 (n^2) | ovlp]`` of a ``(npairs, evc_stack_row_len(n))`` tensor -- the send buffer of the
-        single all_gather of the multi-GPU stack build (``evc_trans_rdm12_batch_strided``)."""
+        single all_gather of the multi-GPU stack build (``evc_trans_rdm12_batch_strided``).  ``plan_pairs``: pair
+        count of the whole build when ``pairs`` is one rank's share of it (``evc_trans_rdm12_plan_pairs``)."""
         neleca, nelecb = nelec
         na, nlink_a, la_sm, _ = self.link_tables(norb, neleca)
         nb, nlink_b, _, lb_lm = self.link_tables(norb, nelecb)
@@ -201,11 +202,13 @@ class Engine:
         ws = self.workspace(nbytes.value)
         self._bind_stream()
         base = rows.data_ptr()
+        check(self.lib.evc_trans_rdm12_plan_pairs(self._ctx, int(plan_pairs)))
         check(self.lib.evc_trans_rdm12_batch_strided(
             self._ctx, n, na, nb, _ptr(civecs), stride, nvec, _ptr(pairs_d), npairs,
             _ptr(la_sm), nlink_a, _ptr(lb_lm), nlink_b,
             C.c_void_p(base + 8 * (n2 * n2 + n2)), width, C.c_void_p(base + 8 * n2 * n2), width,
             C.c_void_p(base), width, _ptr(ws), ws.numel()))
+        check(self.lib.evc_trans_rdm12_plan_pairs(self._ctx, 0))
         return rows
 
     def stack_scatter_rows(self, rows, row_pairs, ntrain, norb):

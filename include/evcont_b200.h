@@ -114,6 +114,11 @@ int evc_trans_rdm12_batch_strided(evc_ctx *ctx, int norb, int64_t na, int64_t nb
                                   int nlink_a, const uint64_t *link_b, int nlink_b, double *ovlp,
                                   int64_t ovlp_stride, double *dm1, int64_t dm1_stride, double *dm2,
                                   int64_t dm2_stride, void *workspace, size_t workspace_bytes);
+/* A pair's result is a sum over alpha-string slices whose number the kernel plans from the pair count of
+ * the call.  A rank that computes only its share of a build (evcont_b200/distributed.py) announces the pair
+ * count of the WHOLE build here (0 restores the default), so that every pair's bits are the same at any
+ * number of ranks.  Workspace sizes computed for the call's own pair count remain sufficient. */
+int evc_trans_rdm12_plan_pairs(evc_ctx *ctx, int total_pairs);
 int64_t evc_stack_row_len(int norb); /* n^4 + n^2 + 1, rounded up to even */
 /* rows [nrows][row_stride] of pairs row_pairs[nrows][2] = (a, b) (device int32) -> overlap (N,N), one_rdm
  * (N,N,n,n), two_rdm (N,N,n,n,n,n): block [a,b] and the untransposed copy at [b,a], exactly how

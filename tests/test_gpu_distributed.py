@@ -44,7 +44,7 @@ def _worker(rank, world, port, ntrain, norb, nocc, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ntrain,norb,nocc", [(5, 6, 3), (7, 8, 4)])
+@pytest.mark.parametrize("ntrain,norb,nocc", [(5, 6, 3), (7, 8, 4), (6, 10, 5)])
 def test_nccl_sharded_build_equals_single_gpu_bitwise(tmp_path, ntrain, norb, nocc):
     import torch
     import torch.multiprocessing as mp
@@ -75,3 +75,27 @@ def test_single_gpu_rows_and_scatter_against_batch_entry():
     assert np.array_equal(S.cpu().numpy(), ref.overlap)
     assert np.array_equal(one.cpu().numpy(), ref.one_rdm)
     assert np.array_equal(two.cpu().numpy(), ref.two_rdm)
+
+
+def test_a_share_of_the_pairs_has_the_bits_of_the_whole_build():
+    """One GPU: the rows a rank computes for its share (planned for the pair count of the whole build,
+    evc_trans_rdm12_plan_pairs) are bit-identical to the same rows of the full call -- at H10 sizes, where the
+    alpha-slice count would otherwise follow the number of pairs in the call."""
+    from math import comb
+    from evcont_b200 import distributed as evd
+    from evcont_b200.engine import get_engine
+    eng = get_engine()
+    ntrain, norb, nocc = 6, 10, 5
+    na = comb(norb, nocc)
+    vecs = eng.to_device(np.stack([random_civec(na, na, 70 + k, symmetric=True) for k in range(ntrain)]))
+    pairs = evd.tril_pairs(ntrain)
+    used = norb ** 4 + norb ** 2 + 1          # [dm2 | dm1 | ovlp]; the row is padded to an even length
+    full = eng.trans_rdm12_rows(vecs, pairs, norb, (nocc, nocc)).cpu().numpy()[:, :used]
+    for world in (2, 4, 8):
+        for rank in range(world):
+            lo, hi = evd.shard_range(len(pairs), rank, world)
+            part = eng.trans_rdm12_rows(vecs, pairs[lo:hi], norb, (nocc, nocc), plan_pairs=len(pairs)).cpu().numpy()
+            assert np.array_equal(part[:, :used], full[lo:hi]), (world, rank)
+            if hi - lo < len(pairs) // 2:         # without the announcement the slice count follows the call
+                own = eng.trans_rdm12_rows(vecs, pairs[lo:hi], norb, (nocc, nocc)).cpu().numpy()[:, :used]
+                assert np.abs(own - full[lo:hi]).max() < 1e-12
