@@ -267,7 +267,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------
-STAGE_KERNEL = {"loewdin": "loewdin_kernel", "ao2oao": "ao2oao_pipe_kernel", "subspace_H": "dgemm_kernel (NT)",
+STAGE_KERNEL = {"loewdin": "loewdin_reg_kernel", "ao2oao": "ao2oao_pipe_kernel", "subspace_H": "dgemm_kernel (NT)",
                 "geneig": "geneig_lowest_kernel", "predict_rdm": "dgemm_kernel (NN)", "grad": "grad_pipe_kernel",
                 "grad_stream": "grad_stream_kernel"}
 
@@ -301,7 +301,8 @@ def stage_work(n, natm, ntrain, G, pitch):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of 4096 geometries (H10 sizes, N = 20) from the
 # `ncu --set full` capture of the kernels of THIS commit: profiles/r02_packed_step_ncu_full.txt
-NCU_TRAFFIC_4096 = {}
+NCU_TRAFFIC_4096 = {"loewdin": 3.336e6, "ao2oao": 223.2e6, "subspace_H": 59.07e6, "geneig": 6.964e6,
+                    "predict_rdm": 13.38e6, "grad": 227.5e6, "grad_stream": 737.8e6}
 
 
 def h10_geometries(G, seed):

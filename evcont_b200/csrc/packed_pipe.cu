@@ -678,9 +678,11 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
               }
             }
           }
-        double* yp = Ypart + (static_cast<size_t>(rg) * S::ncol + col) * (2 * n);
+        // layout [row group][yi | yj][a][pair column]: a warp's lanes store to consecutive words (with the pair
+        // column outermost every store was an 8-way bank conflict: profiles/r02_pipe_ncu_full.txt)
+        double* yp = Ypart + static_cast<size_t>(rg) * (2 * n) * S::ncol + col;
 #pragma unroll
-        for (int a = 0; a < NC; ++a) { yp[a] = yi[a]; yp[n + a] = yj[a]; }
+        for (int a = 0; a < NC; ++a) { yp[a * S::ncol] = yi[a]; yp[(n + a) * S::ncol] = yj[a]; }
       }
       PIPE_STAMP(1, 2, it, 2);
       named_sync(3, kMidThreads);  // every reader of U0 is done; the Y partials are visible
@@ -706,7 +708,7 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
         double t0 = 0.0, t1 = 0.0;
 #pragma unroll
         for (int q = 0; q < NC; ++q) {  // q <= ec: column (ec, q) holds Y[:, ec] in its yi; else column (q, ec) in its yj
-          const int off = (q <= ec ? tri_idx(ec, q) * (2 * n) : tri_idx(q, ec) * (2 * n) + n) + ea;
+          const int off = q <= ec ? ea * S::ncol + tri_idx(ec, q) : (n + ea) * S::ncol + tri_idx(q, ec);
           if (q & 1) t1 += yh[off]; else t0 += yh[off];
         }
         double t = t0 + t1;
