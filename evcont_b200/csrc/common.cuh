@@ -69,6 +69,10 @@ int evc_packed_grad(evc_ctx* ctx, int nbatch, int n, int natm, const int32_t* ao
                     double* grad);
 // packed_pipe.cu
 bool evc_packed_pipe_supported(int n);
+// geneig_reg.cu: K6 (lowest root) with the eigensolver of one problem in the registers of one warp (2 <= N <= 24)
+bool evc_geneig_reg_supported(int N);
+int evc_geneig_reg(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H, const double* Linv, double* E,
+                   double* C);
 // loewdin_reg.cu: K3 with the Jacobi eigensolver in registers (2 <= n <= 16), several matrices per warp
 bool evc_loewdin_reg_supported(int n);
 int evc_loewdin_reg_min_batch();

@@ -12,6 +12,7 @@
 // About 15x fewer instructions than the cyclic Jacobi sweep, which is kept for
 // nroots > 1 (approximate_multistate) in dense.cu.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -482,6 +483,13 @@ extern "C" int evc_debug_geneig_clocks(long long* out_host) {   // development a
 
 int evc_launch_geneig_lowest(evc_ctx* ctx, int nbatch, int N, int packed_lower, const double* H,
                              const double* Linv, double* E, double* C) {
+  // N <= 24: the register-resident form (geneig_reg.cu); EVC_GENEIG_REG=0 in the environment keeps the
+  // shared-memory kernels (A/B timing of the two forms in one build; development aid)
+  static const bool use_reg = [] {
+    const char* e = getenv("EVC_GENEIG_REG");
+    return !(e && e[0] == '0');
+  }();
+  if (use_reg && evc_geneig_reg_supported(N)) return evc_geneig_reg(ctx, nbatch, N, packed_lower, H, Linv, E, C);
   const size_t per_warp = lowest_warp_doubles(N) * sizeof(double);
   const size_t per_warp32 = lowest_warp_doubles(N, true) * sizeof(double);
   EVC_REQUIRE(per_warp <= ctx->smem_optin, "geneig: N=%d needs %zu bytes of shared memory", N, per_warp);
