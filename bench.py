@@ -268,7 +268,7 @@ def run_reference(args):
 # this repo's arm
 # ---------------------------------------------------------------------------------
 STAGE_KERNEL = {"loewdin": "loewdin_reg_kernel", "ao2oao": "ao2oao_pipe_kernel", "subspace_H": "dgemm_kernel (NT)",
-                "geneig": "geneig_lowest_kernel", "predict_rdm": "dgemm_kernel (NN)", "grad": "grad_pipe_kernel",
+                "geneig": "geneig_reg_kernel", "predict_rdm": "dgemm_kernel (NN)", "grad": "grad_pipe_kernel",
                 "grad_stream": "grad_stream_kernel"}
 
 
