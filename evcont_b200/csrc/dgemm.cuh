@@ -159,15 +159,27 @@ struct Plan {
   int kchunk;
 };
 
-// split-K so that the grid covers the SMs about twice (never below 4 k-steps a split)
+// split-K: the number of splits that minimises (waves of CTAs) x (k-steps per CTA), two CTAs resident per SM, never
+// below 4 k-steps a split.  (Covering the SMs "about twice" left 384 CTAs on 296 slots for the K5p product of the bench:
+// a second wave that is 30 % full; three splits = 288 CTAs run as one wave and finish 1.5x sooner.)  A small term per
+// split accounts for the reduction of the partial results.
 inline Plan plan_split(int tiles, int K, int sm_count, int max_split) {
   Plan p;
-  int s = (2 * sm_count + tiles - 1) / tiles;
   const int ksteps = (K + BK - 1) / BK;
-  if (s > ksteps / 4) s = ksteps / 4;
-  if (s > max_split) s = max_split;
-  if (s < 1) s = 1;
-  int per = (ksteps + s - 1) / s;
+  const int slots = 2 * sm_count;
+  int smax = ksteps / 4;
+  if (smax > max_split) smax = max_split;
+  if (smax < 1) smax = 1;
+  int best = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= smax; ++s) {
+    const long long ctas = static_cast<long long>(tiles) * s;
+    const long long waves = (ctas + slots - 1) / slots;
+    const int per = (ksteps + s - 1) / s;
+    const double cost = static_cast<double>(waves) * (per + 2) + 0.25 * s;
+    if (cost < best_cost) { best_cost = cost; best = s; }
+  }
+  const int per = (ksteps + best - 1) / best;
   p.kchunk = per * BK;
   p.nsplit = (K + p.kchunk - 1) / p.kchunk;
   return p;
