@@ -368,8 +368,16 @@ __global__ void reduce_slabs_kernel(int64_t cols, int nz, int64_t sz, int64_t sg
 constexpr int kRdBM = 128, kRdBN = 80;   // rows_dot GEMM tile (G x P)
 constexpr int kRaBM = 64, kRaBN = 128;   // rows_axpy GEMM tile (G x L)
 
+// column tile of the rows_dot GEMM: 80 (4 x 2 warps) or 72 (8 x 1 warps), whichever pads the P pair columns less
+// (N = 20 training states: 210 columns run as 3 x 72 = 216 instead of 3 x 80 = 240)
+inline int rows_dot_bn(int P) {
+  const int p80 = (P + 79) / 80 * 80, p72 = (P + 71) / 72 * 72;
+  return p72 < p80 ? 72 : kRdBN;
+}
+
 evc_gemm::Plan rows_dot_plan(int G, int P, int64_t L) {
-  const int tiles = ((G + kRdBM - 1) / kRdBM) * ((P + kRdBN - 1) / kRdBN);
+  const int bn = rows_dot_bn(P);
+  const int tiles = ((G + kRdBM - 1) / kRdBM) * ((P + bn - 1) / bn);
   return evc_gemm::plan_split(tiles, static_cast<int>(L), kPlanSms, 128);
 }
 
@@ -396,8 +404,11 @@ int evc_rows_dot(evc_ctx* ctx, const double* rows, int64_t L, int P, const doubl
   double* partial = static_cast<double*>(workspace);
   if (G > kGemvMaxBatch) {
     const evc_gemm::Plan pl = rows_dot_plan(G, P, L);
-    int rc = evc_gemm::launch<kRdBM, kRdBN, 4, 2, false>(ctx->stream, G, P, static_cast<int>(L), pl, hv, L, rows, L,
-                                                          partial, P, static_cast<int64_t>(G) * P);
+    int rc = rows_dot_bn(P) == 72
+                 ? evc_gemm::launch<kRdBM, 72, 8, 1, false>(ctx->stream, G, P, static_cast<int>(L), pl, hv, L, rows, L,
+                                                            partial, P, static_cast<int64_t>(G) * P)
+                 : evc_gemm::launch<kRdBM, kRdBN, 4, 2, false>(ctx->stream, G, P, static_cast<int>(L), pl, hv, L, rows, L,
+                                                               partial, P, static_cast<int64_t>(G) * P);
     if (rc) return rc;
     dim3 grid((P + 127) / 128, G);
     reduce_slabs_kernel<<<grid, 128, 0, ctx->stream>>>(P, pl.nsplit, static_cast<int64_t>(G) * P, P, 1, partial, out);
