@@ -23,6 +23,7 @@ collective).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -70,7 +71,9 @@ def civecs(ntrain):
     for k in range(ntrain):
         c = np.random.default_rng(1000 + k).standard_normal((NA, NB))
         c = c + c.T  # spin0-like
-        out.append(c / np.linalg.norm(c))
+        # exactly rounded norm (no BLAS: its summation order follows the host's thread count and SIMD width, and
+        # the stack checksum below is compared across runs with different OMP settings -- torchrun sets 1 thread)
+        out.append(c / math.sqrt(math.fsum((c * c).ravel().tolist())))
     return np.stack(out)
 
 
