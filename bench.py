@@ -619,7 +619,14 @@ def run_sp_legs(args, eng, timed, world, rank, torch):
                      "geometries_per_step_per_gpu": G, "norb": n, "natm": natm, "ntrain": N, "layout": layout,
                      "integrals_ms_per_step": ints_ms, "integrals_geometries_per_s": G / (ints_ms * 1e-3),
                      "h2d_bytes_per_step": int(co_h.numel() * 8),
-                     "d2h_bytes_per_step": int((E_h.numel() + g_h.numel()) * 8)}
+                     "d2h_bytes_per_step": int((E_h.numel() + g_h.numel()) * 8),
+                     # K9g has no closed-form flop count (six shell-quartet classes, Hermite recursions of different
+                     # depth, primitive screening): its roofline evidence is the measured pipe activity
+                     "integrals_roofline": {"kernel": "gclass kernels (K9g, 16 two-electron + 4 one-electron launches)",
+                                            "bound": "fp64 fma pipe", "achieved": None, "peak": None, "frac": None,
+                                            "fp64_pipe_active_pct_ncu": {"two_electron_classes": [30, 39],
+                                                                         "one_electron_classes": [19, 26]},
+                                            "source": "profiles/r01e_gclass_ncu_full.txt (Zundel sizes, 64 geometries)"}}
         del stack, two, one, ao
         torch.cuda.empty_cache()
     return out
