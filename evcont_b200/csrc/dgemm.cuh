@@ -116,8 +116,12 @@ dgemm_kernel(int M, int N, int K, int kchunk, const double* __restrict__ A, int6
     cp_async_commit();
     const double* as = As + (kt % STAGES) * S::A_STAGE;
     const double* bs = Bs + (kt % STAGES) * S::B_STAGE;
+    // k-steps of this tile that hold data: the last tile of a K extent that is no multiple of BK (K7p: 210 =
+    // 13 x 16 + 2) runs one k-step instead of four (the rest of the tile is zero padding)
+    const int kvalid = kend - (kbeg + kt * BK);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
+      if (kk >= kvalid) break;  // block-uniform
       double af[MI], bf[NI];
 #pragma unroll
       for (int i = 0; i < MI; ++i) af[i] = as[(wm0 + i * 8 + g) * S::A_PITCH + kk + tg];
