@@ -114,13 +114,24 @@ loewdin_reg_kernel(int nbatch, const double* __restrict__ s_ao, double* __restri
       for (int j = 0; j < N; ++j) arow = j == partner ? a[j] : arow;
       const double dother = shfl_d(dii, plane), aother = shfl_d(arow, plane);
       const double app = is_p ? dii : dother, aqq = is_p ? dother : dii, apq = is_p ? arow : aother;
+      // Rotation angle without divisions (the dependent chain of a round is what a warp waits for): with d = aqq - app,
+      // b = 2 apq and theta = d / b the classical t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) is tan(phi) with
+      // cos(2 phi) = |d| / r, sin(2 phi) = |b| / r, r = sqrt(d^2 + b^2):  c = sqrt((1 + cos 2phi) / 2),
+      // |s| = sin(2 phi) / (2 c) -- two reciprocal square roots and a few products.
       double c = 1.0, s = 0.0, dnew = dii;
-      if (active && !bye && fabs(apq) > 1.0e-300) {
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-        c = rsqrt(fma(t, t, 1.0));
-        s = t * c;
-        dnew = is_p ? app - t * apq : aqq + t * apq;
+      {
+        const double d = aqq - app, bq = 2.0 * apq;
+        const double r2 = fma(d, d, bq * bq);
+        if (active && !bye && fabs(apq) > 1.0e-300 && r2 > 1.0e-290) {
+          const double rinv = rsqrt(r2);
+          const double h = fma(0.5 * fabs(d), rinv, 0.5);   // (1 + cos 2phi) / 2 = c^2, in [1/2, 1]
+          const double cinv = rsqrt(h);
+          c = h * cinv;
+          const double sabs = 0.5 * fabs(bq) * rinv * cinv;
+          s = ((d >= 0.0) == (bq >= 0.0)) ? sabs : -sabs;   // sgn(theta), theta = 0 counts as positive
+          const double t = s * cinv;
+          dnew = is_p ? app - t * apq : aqq + t * apq;
+        }
       }
       dii = dnew;
       // rows: row p <- c row p - s row q, row q <- s row p + c row q; for the q lane that is
