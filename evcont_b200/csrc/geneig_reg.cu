@@ -9,7 +9,8 @@
 // is warp shuffles, and shared memory is touched three times (two transposes of the product phase, the
 // tridiagonal for the Sturm counts).  The shared-memory kernel needs 28.6 k warp instructions and ~260 k
 // cycles per N = 20 problem, most of them dependent shared-memory round trips with run-time addressing
-// (profiles/r01d_geneig_phase_clocks.txt); this one ~9 k instructions.
+// (profiles/r01d_geneig_phase_clocks.txt); this one 15.7 k instructions and 0.046 ms for one problem
+// (profiles/r02_packed_step_ncu_full.txt).
 //
 // Symmetry is kept EXACT through the reduction (lower triangle mirrored after the products, rank-2 update as
 // the commutative sum of two rounded products): lane j reads the component of the Householder vector that
