@@ -132,16 +132,16 @@ geneig_reg_kernel(int packed_lower, int nbatch, const double* __restrict__ H, co
     const bool act = in && lane > k;
     // p = taup A22 u (column sums are local), own component of u from the own register a[k]
     p = taup * fma(a[k + 1], u0, p);
-    const double uo = (lane == k + 1) ? u0 : a[k];
-    const double pu = wsum(act ? p * uo : 0.0);
+    // (zero in the lanes that take no part: their updates below subtract an exact zero, no select per element)
+    const double uo = act ? ((lane == k + 1) ? u0 : a[k]) : 0.0;
+    const double pu = wsum(p * uo);
     const double q = act ? fma(-0.5 * taup * pu, uo, p) : 0.0;
     // A22 <- A22 - u q^T - q u^T, as the commutative sum of two rounded products (exactly symmetric)
 #pragma unroll
     for (int i = k + 1; i < N; ++i) {
       const double ui = (i == k + 1) ? u0 : bc(a[i], k);
       const double qi = bc(q, i);
-      const double t = __dadd_rn(__dmul_rn(ui, q), __dmul_rn(qi, uo));
-      a[i] = act ? a[i] - t : a[i];
+      a[i] -= __dadd_rn(__dmul_rn(ui, q), __dmul_rn(qi, uo));
     }
     a[k] = act ? uo : a[k];
   }
@@ -165,32 +165,48 @@ geneig_reg_kernel(int packed_lower, int nbatch, const double* __restrict__ H, co
       ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
       emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
     }
-    if (in) { ds[lane] = dj; e2s[lane] = ek * ek; }
-    __syncwarp();
     tnorm = fmax(fabs(glo), fabs(ghi));
-    const double pivmin = DBL_MIN * fmax(1.0, emax);
-    double lo = glo - 2.0 * DBL_EPSILON * tnorm * N - 2.0 * pivmin;
-    double hi = ghi + 2.0 * DBL_EPSILON * tnorm * N + 2.0 * pivmin;
+    // The counts run on T scaled by an exact power of two to a norm in [1/2, 1): the determinant recurrence
+    //   p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}      (sign changes = eigenvalues below x)
+    // then cannot overflow within N <= 24 steps (|p_i| <= 3^i), and only underflow has to be watched.  Signs and
+    // magnitudes are read off the high word with integer instructions: FP64 compares share the FP64 pipe with the
+    // arithmetic, and this loop is 40 % of the kernel's instructions.
+    int ex2 = 0;
+    (void)frexp(tnorm, &ex2);
+    const double sc = tnorm > 0.0 ? ldexp(1.0, -ex2) : 1.0, sci = tnorm > 0.0 ? ldexp(1.0, ex2) : 1.0;
+    if (in) { ds[lane] = dj * sc; e2s[lane] = -(ek * sc) * (ek * sc); }
+    __syncwarp();
+    const double tn = tnorm * sc;
+    const double pivmin = DBL_MIN * fmax(1.0, emax * sc * sc);
+    double lo = glo * sc - 2.0 * DBL_EPSILON * tn * N - 2.0 * pivmin;
+    double hi = ghi * sc + 2.0 * DBL_EPSILON * tn * N + 2.0 * pivmin;
+#pragma unroll 1
     for (int it = 0; it < 16; ++it) {
       const double width = hi - lo;
       if (width <= 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) break;
       const double h = width / 33.0;
       const double xs = lo + (lane + 1) * h;
-      // determinant recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}; sign changes = eigenvalues below x;
-      // rescaled by 2^-+500, an exact zero takes the sign opposite to its predecessor
       double pm = 1.0, pc = ds[0] - xs;
-      if (pc == 0.0) pc = -1.0e-100;
-      int cnt = pc < 0.0;
+      if (pc == 0.0) pc = -1.0e-100;  // an exact zero takes the sign opposite to its predecessor (p_{-1} = 1)
+      int hc = __double2hiint(pc);
+      int cnt = static_cast<unsigned>(hc) >> 31;
 #pragma unroll
       for (int i = 1; i < N; ++i) {
-        double pn = fma(ds[i] - xs, pc, -e2s[i - 1] * pm);
-        if (pn == 0.0) pn = -pc * 1.0e-100;
-        cnt += (pn < 0.0) != (pc < 0.0);
+        double pn = fma(ds[i] - xs, pc, e2s[i - 1] * pm);
+        int hn = __double2hiint(pn);
+        if (((hn >> 20) & 0x7ff) < 523) {  // |p| < 2^-500 (or zero): rare
+          if (pn == 0.0) {
+            pn = -pc * 1.0e-100;
+          } else {
+            pn *= 3.2733906078961419e150;  // 2^500
+            pc *= 3.2733906078961419e150;
+          }
+          hn = __double2hiint(pn);
+        }
+        cnt += static_cast<unsigned>(hn ^ hc) >> 31;
         pm = pc;
         pc = pn;
-        const double mag = fabs(pc);
-        if (mag > 3.2733906078961419e150) { pc *= 3.0549363634996047e-151; pm *= 3.0549363634996047e-151; }
-        else if (mag < 3.0549363634996047e-151) { pc *= 3.2733906078961419e150; pm *= 3.2733906078961419e150; }
+        hc = hn;
       }
       const unsigned ball = __ballot_sync(0xffffffffu, cnt >= 1);
       const int f = ball ? __ffs(ball) - 1 : 32;  // first sample point with an eigenvalue below it
@@ -198,7 +214,7 @@ geneig_reg_kernel(int packed_lower, int nbatch, const double* __restrict__ H, co
       hi = (f < 32) ? lo + (f + 1) * h : hi;
       lo = nlo;
     }
-    lam = 0.5 * (lo + hi);
+    lam = 0.5 * (lo + hi) * sci;
   }
 
   // ---- eigenvector of T by inverse iteration: pivoted LU of T - lam I (dgttrf / dgttrs form), element i of
