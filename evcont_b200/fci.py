@@ -17,7 +17,13 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
     Vectors live on the device as torch tensors (dot products and axpys are torch calls -- plumbing);
     the small projected eigenproblem is solved on the host.  Diagonal preconditioner, two passes of
     Gram-Schmidt, restart with the current Ritz vectors when the space exceeds
-    ``max_space * nroots``.  Converged when every residual norm is below ``tol``.
+    ``max_space * nblock``.  Converged when the residual norms of the lowest ``nroots`` are below ``tol``.
+
+    For ``nroots > 1`` the iteration carries a block of ``nroots + 2`` Ritz vectors (corrections and restarts keep
+    all of them) and starts from ``4 nroots + 4`` P-space states: a symmetry sector that is absent from the search
+    space can never enter it in exact arithmetic, and the lowest few P-space states alone do not always cover the
+    sectors of the lowest roots (H6 at 1.4 bohr: the second root of the alpha <-> beta symmetric sector has the
+    other inversion parity and was skipped or found depending on rounding noise).
     """
     import torch
     na, nb, nd = ham.na, ham.nb, ham.ndet
@@ -41,6 +47,7 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
     # built with P applications of the device H c, diagonalised on the host; its lowest eigenvectors seed the
     # iteration.  Unit vectors on the lowest diagonal elements alone let the iteration skip roots that are
     # weakly coupled to them (H6 at 1.4 bohr, nroots = 2: the second root of the symmetric sector was missed).
+    ninit = nroots + 2 if nroots == 1 else 4 * nroots + 4
     P = min(nd, 48 + 16 * nroots if nd > 500000 else 96 + 32 * nroots)
     idx = torch.argsort(hdiag)[:P].tolist()
     if spin0 and na == nb:   # add the exchange partners (Ib, Ia) of the chosen (Ia, Ib)
@@ -70,11 +77,12 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
         g, nrm = orth(gs, V)
         if nrm > 1e-8:
             V.append(g / nrm)
-        if len(V) == min(nroots + 2, max(1, max_space * nroots - nroots)):
+        if len(V) == ninit:
             break
     if len(V) < nroots:
         raise RuntimeError(f"FCI Davidson: only {len(V)} independent initial guesses for nroots={nroots}")
     W = [ham.contract(v) for v in V]
+    nblock = nroots if nroots == 1 else min(nroots + 2, len(V))
     theta, X = None, None
     for _cycle in range(max_cycle):
         m = len(V)
@@ -82,22 +90,23 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
         hsub = (Vm @ Wm.T).cpu().numpy()
         hsub = 0.5 * (hsub + hsub.T)
         w, s = np.linalg.eigh(hsub)
-        theta = w[:nroots]
-        S = torch.from_numpy(np.ascontiguousarray(s[:, :nroots].T)).to(Vm.device)
-        X = S @ Vm            # Ritz vectors (nroots, nd)
+        theta = w[:nblock]
+        S = torch.from_numpy(np.ascontiguousarray(s[:, :nblock].T)).to(Vm.device)
+        X = S @ Vm            # Ritz vectors (nblock, nd)
         HX = S @ Wm
         R = HX - torch.from_numpy(theta).to(Vm.device)[:, None] * X
         rn = torch.linalg.vector_norm(R, dim=1).cpu().numpy()
-        if rn.max() < tol:
+        if rn[:nroots].max() < tol:
             break
-        if m + nroots > max_space * nroots:   # restart from the Ritz vectors
+        if m + nblock > max_space * nblock:   # restart from the Ritz vectors
             V, W = [], []
-            for k in range(nroots):
+            for k in range(nblock):
                 v, nrm = orth(X[k].clone(), V)
-                V.append(v / nrm)
+                if nrm > 1e-10:
+                    V.append(v / nrm)
             W = [ham.contract(v) for v in V]
         added = 0
-        for k in range(nroots):
+        for k in range(nblock):
             if rn[k] < tol:
                 continue
             den = theta[k] - hdiag
@@ -112,10 +121,11 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
             # every correction vector was linearly dependent on the space although a residual is still above
             # tol: collapse onto the Ritz vectors plus the (unpreconditioned) residuals instead of giving up
             V, W = [], []
-            for k in range(nroots):
+            for k in range(nblock):
                 v, nrm = orth(X[k].clone(), V)
-                V.append(v / nrm)
-            for k in range(nroots):
+                if nrm > 1e-10:
+                    V.append(v / nrm)
+            for k in range(nblock):
                 if rn[k] >= tol:
                     t, nrm = orth(sym(R[k].clone()), V)
                     if nrm > 1e-12:
@@ -130,7 +140,7 @@ def davidson(ham, nroots=1, tol=1e-10, max_cycle=200, max_space=12, spin0=False)
     for k in range(nroots):
         v = sym(X[k])
         out.append(v / torch.linalg.vector_norm(v))
-    return np.asarray(theta, dtype=np.float64), out
+    return np.asarray(theta[:nroots], dtype=np.float64), out
 
 
 def _unpack_nelec(nelec):

@@ -66,6 +66,26 @@ def test_davidson_h6_against_dense_diagonalisation():
     assert all(np.abs(c - c.T).max() < 1e-10 for c in cs)
 
 
+def test_davidson_does_not_depend_on_rounding_noise_to_find_a_root():
+    """H6 at 1.4 bohr: the second root of the alpha <-> beta symmetric sector has the other inversion parity than the
+    ground state.  A search space without that parity can only acquire it through rounding noise, so whether the
+    root was found used to follow the last bits of the integrals.  Perturbing them at the 1e-14 level (different
+    rounding paths, same spectrum to 1e-12) must not change which roots come back."""
+    from evcont_b200.fci import B200FCISolver
+    from oracle import trans_rdm as otr
+    mol = _h_chain(6, 1.4)
+    h1, h2 = _oao_integrals(mol)
+    w, v = np.linalg.eigh(otr.hamiltonian_matrix(h1, h2, 6, (3, 3)))
+    symm = [k for k in range(len(w)) if np.abs(v[:, k].reshape(20, 20) - v[:, k].reshape(20, 20).T).max() < 1e-7]
+    rng = np.random.default_rng(0)
+    for trial in range(6):
+        e1 = rng.standard_normal(h1.shape) * 1e-14
+        h1p = h1 + e1 + e1.T
+        for nroots in (2, 3, 4):
+            es, _ = B200FCISolver().kernel(h1p, h2, 6, (3, 3), nroots=nroots)
+            assert np.abs(np.array(es) - w[symm[:nroots]]).max() < 1e-8, (trial, nroots, es, w[symm[:nroots + 2]])
+
+
 @pytest.mark.parametrize("d", [1.0, 1.4, 1.8, 2.6, 3.0])
 def test_davidson_excited_roots_at_every_training_distance(d):
     """nroots = 2 and 3 along the H6 scan: no root of the alpha <-> beta symmetric sector may be skipped."""
