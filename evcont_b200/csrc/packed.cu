@@ -641,7 +641,7 @@ constexpr int kStreamThreads = 128;
 // Hamiltonian derivative) before the first use, so a CTA lives for about two memory round trips and 16 of them
 // are resident per SM.  (The staged forms -- cp.async rows + two block barriers per AO, or one CTA per geometry
 // with W expanded in shared memory -- spent a third of their time in barriers: profiles/r02r.)
-__global__ void __launch_bounds__(kStreamThreads, 10)
+__global__ void __launch_bounds__(kStreamThreads, 12)
 grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const double* __restrict__ Wg,
                    const double* __restrict__ OmS, const double* __restrict__ Pao,
                    const double* __restrict__ ipovlp, const double* __restrict__ hcore_deriv,
