@@ -543,7 +543,7 @@ class Engine:
             _ptr(cvec), _ptr(ws), ws.numel()))
         return E, grad, gamma, Gamma, cvec
 
-    def energy_with_grad_host(self, stack, host_ao, chunk=256, sync=True, packed=None):
+    def energy_with_grad_host(self, stack, host_ao, chunk=512, sync=True, packed=None):
         """The prediction step on HOST arrays (:class:`HostAO`): chunked host->device
         copies, kernels and read-back overlap on three streams.  Results land in
         ``host_ao.E`` / ``host_ao.grad`` (returned); with ``sync=False`` the caller
