@@ -608,12 +608,10 @@ packed_grad_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8
     warp_mm(Z, A, false, V, true);
   }
   {
-    double* Wg = Wout + static_cast<int64_t>(g) * np * np;
+    const int npw = w_pitch_of(n);
+    double* Wg = Wout + static_cast<int64_t>(g) * np * npw;
     gemm_store<MAXI>(acc, mlow, pg.M8, pg.M8, true, [&](int m, int c, double v0, double v1) {
-      if (m < np) {
-        if (c < np) Wg[m * np + c] = v0;
-        if (c + 1 < np) Wg[m * np + c + 1] = v1;
-      }
+      if (m < np && c < np) *reinterpret_cast<double2*>(Wg + m * npw + c) = make_double2(v0, v1);
     });
   }
   __syncthreads();
@@ -651,7 +649,8 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
   const int np = npair_of(n), n2 = n * n, rl = n * np;  // rl: doubles of one (x, m) run
   const int At = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
   const int p0 = __ldg(aoslices + 2 * At), p1 = __ldg(aoslices + 2 * At + 1);
-  const double* W = Wg + static_cast<int64_t>(g) * np * np;
+  const int npw = w_pitch_of(n);
+  const double* W = Wg + static_cast<int64_t>(g) * np * npw;
   const double* ipg = ip1p + static_cast<int64_t>(g) * 3 * n * rl;
   const int64_t xs = static_cast<int64_t>(n) * rl;  // stride between the x, y, z components
   const double* hd = hcore_deriv + (static_cast<int64_t>(g) * natm + At) * 3 * n2;
@@ -671,7 +670,7 @@ grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const 
       // ((2 c + 3)^2 = 8 c (c + 3) / 2 + 9); integer check on a float estimate
       const int q = static_cast<int>(sqrtf(static_cast<float>(8 * C + 9)) + 0.5f);
       const double fac = (q * q == 8 * C + 9) ? 1.0 : 2.0;
-      const double w = __ldg(W + (r > C ? r * np + C : C * np + r)) * fac;
+      const double w = __ldg(W + (r > C ? r * npw + C : C * npw + r)) * fac;
       s0 = fma(__ldg(r0 + e), w, s0);
       s1 = fma(__ldg(r0 + xs + e), w, s1);
       s2 = fma(__ldg(r0 + 2 * xs + e), w, s2);
@@ -996,7 +995,7 @@ int evc_energy_with_grad_packed_workspace_bytes(int N, int n, int natm, int nbat
   tot += evc_align_up(evc_rows_axpy_ws_bytes(L8, P, nbatch), 256);
   if (n <= kPackedMaxNorb) {
     tot += evc_align_up(G * erip_len(n) * 8, 256);  // T ([np][pA], like erip)
-    tot += evc_align_up(G * np * np * 8, 256);      // W
+    tot += evc_align_up(G * np * w_pitch_of(n) * 8, 256);  // W
     tot += 2 * evc_align_up(G * n2 * 8, 256);       // OmS, Pao
     // room for the packed copies of int2e / int2e_ip1 when the caller passes the full tensors
     tot += evc_align_up(G * erip_len(n) * 8, 256) + evc_align_up(G * ip1p_len(n) * 8, 256);
@@ -1056,7 +1055,7 @@ int evc_energy_with_grad_packed(evc_ctx* ctx, int N, int n, int natm, const doub
   const double* ip1p = ao->eri_ip1p;
   if (small) {
     T = ar.take<double>(G * erip_len(n));
-    Wg = ar.take<double>(G * np * np);
+    Wg = ar.take<double>(G * np * w_pitch_of(n));
     OmS = ar.take<double>(G * n2);
     Pao = ar.take<double>(G * n2);
     EVC_REQUIRE(T && Wg && OmS && Pao, "evc_energy_with_grad_packed: workspace too small (%zu bytes)", workspace_bytes);

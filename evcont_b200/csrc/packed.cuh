@@ -8,6 +8,10 @@ namespace evcp {
 
 __host__ __device__ inline int tri_idx(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
 __host__ __device__ inline int npair_of(int n) { return n * (n + 1) / 2; }
+// row pitch of W (K8a -> K8b): np rounded up to even, so that the accumulator pairs of a DMMA tile are 16-byte
+// stores (np = 55 at n = 10: with 8-byte stores every 32-byte sector was written half full and the W store took a
+// tenth of K8a's period, profiles/r02_pipe_clock_stamps.txt)
+__host__ __device__ inline int w_pitch_of(int n) { return (npair_of(n) + 1) & ~1; }
 __host__ __device__ inline int64_t packed_len(int n) {
   const int64_t np = npair_of(n);
   const int64_t l = static_cast<int64_t>(n) * n + np * (np + 1) / 2;

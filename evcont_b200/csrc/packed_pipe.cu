@@ -855,13 +855,12 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
         PIPE_STAMP(1, 0, it, 5);
         // W = P0 R  (symmetric: lower triangle only, the reader takes (max, min))
         rect_acc(acc, rl, K4, Opnd{B1, pA, 1}, Opnd{B2, 1, pB});
+        PIPE_STAMP(1, 0, it, 7);
         mbar_arrive_warp(&bars->free_[s]);
-        double* Wg = Wout + g * (static_cast<int64_t>(np) * np);
+        constexpr int npw = (np + 1) & ~1;  // w_pitch_of(n): the pair (c, c + 1), c even, always fits the padded row
+        double* Wg = Wout + g * (static_cast<int64_t>(np) * npw);
         rect_store(acc, rl, [&](int m, int c, double v0, double v1) {
-          if (m < np) {
-            if (c < np) Wg[m * np + c] = v0;
-            if (c + 1 < np) Wg[m * np + c + 1] = v1;
-          }
+          if (m < np && c < np) st2(Wg + m * npw + c, v0, v1);
         });
         PIPE_STAMP(1, 0, it, 6);
       }

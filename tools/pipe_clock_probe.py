@@ -36,7 +36,7 @@ fn(0, buf)
 a = np.array(list(buf), dtype=np.int64).reshape(2, 3, 16, 8)
 names = {0: {0: ("MMA", ["top", "ready", "M1acc", "sync", "Tstored", "sync2", "M2acc", "hv"]),
              1: ("FRONT", ["top", "free", "smalls", "Qbuilt", "h1", "loadwait", "arrive", "-"])},
-         1: {0: ("MMA", ["m1top", "m1ready", "u0arr", "m23top", "p0ok", "Rstored", "Wdone", "-"]),
+         1: {0: ("MMA", ["m1top", "m1ready", "u0arr", "m23top", "p0ok", "Rstored", "Wdone", "M3acc"]),
              1: ("FRONT", ["top", "free", "Gm", "sync", "chain1", "loadwait", "arrive", "-"]),
              2: ("MID", ["top", "u0ok", "Ydone", "P0arr", "Zdone", "free", "-", "-"])}}
 for kern in (0, 1):
