@@ -287,8 +287,8 @@ __device__ __forceinline__ void st2(double* p, double v0, double v1) {  // 16-by
 }
 
 // development aid: clock64 stamps of CTA 0's roles (evc_debug_pipe_clocks); slot layout
-// [kernel 0/1][role 0..2][iteration 0..15][event 0..7]
-__device__ long long g_pipe_clk[2][3][16][8];
+// [kernel 0/1][role 0..3][iteration 0..15][event 0..7]
+__device__ long long g_pipe_clk[2][4][16][8];  // role 3: further stamps of the MMA role
 __device__ int g_pipe_clk_on = 0;
 #define PIPE_STAMP(kern, role, it, ev)                                                   \
   do {                                                                                   \
@@ -829,7 +829,9 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
         PIPE_STAMP(1, 0, it, 1);
         // U0 = T Gm  (Gm symmetric: B(k, c) = Gm[c][k])
         rect_acc(acc, rf, K4, Opnd{B1, pA, 1}, Opnd{B2, pA, 1});
+        PIPE_STAMP(1, 3, it, 0);
         named_sync(1, kMmaThreads);  // every warp is done reading T: U0 may overwrite it
+        PIPE_STAMP(1, 3, it, 1);
         rect_store(acc, rf, [&](int m, int c, double v0, double v1) {
           if (c < K4) st2(B1 + m * pA + c, v0, v1);
         });
@@ -847,10 +849,13 @@ grad_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant__ 
         PIPE_STAMP(1, 0, it, 4);
         // R = Gm P0^T
         rect_acc(acc, rf, K4, Opnd{B2, pA, 1}, Opnd{B1, pA, 1});
+        PIPE_STAMP(1, 3, it, 2);
         named_sync(1, kMmaThreads);  // every warp is done reading Gm: R may overwrite it (B-type)
+        PIPE_STAMP(1, 3, it, 3);
         rect_store(acc, rf, [&](int m, int c, double v0, double v1) {
           if (m < K4) st2(B2 + m * pB + c, v0, v1);
         });
+        PIPE_STAMP(1, 3, it, 4);
         named_sync(1, kMmaThreads);
         PIPE_STAMP(1, 0, it, 5);
         // W = P0 R  (symmetric: lower triangle only, the reader takes (max, min))
@@ -956,7 +961,7 @@ int evc_debug_pipe_occupancy(int* ao2oao_ctas, int* grad_ctas) {
 }
 // development aid: switch the clock64 stamps of CTA 0 on/off, read them back ([2][3][16][8] int64)
 int evc_debug_pipe_clocks(int enable, long long* out_host) {
-  if (out_host) EVC_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_pipe_clk, sizeof(long long) * 2 * 3 * 16 * 8));
+  if (out_host) EVC_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_pipe_clk, sizeof(long long) * 2 * 4 * 16 * 8));
   EVC_CHECK_CUDA(cudaMemcpyToSymbol(g_pipe_clk_on, &enable, sizeof(int)));
   return 0;
 }

@@ -31,14 +31,15 @@ fn.argtypes = [C.c_int, C.c_void_p]
 fn(1, None)
 eng.energy_with_grad(stack, ao)
 torch.cuda.synchronize()
-buf = (C.c_longlong * (2 * 3 * 16 * 8))()
+buf = (C.c_longlong * (2 * 4 * 16 * 8))()
 fn(0, buf)
-a = np.array(list(buf), dtype=np.int64).reshape(2, 3, 16, 8)
+a = np.array(list(buf), dtype=np.int64).reshape(2, 4, 16, 8)
 names = {0: {0: ("MMA", ["top", "ready", "M1acc", "sync", "Tstored", "sync2", "M2acc", "hv"]),
              1: ("FRONT", ["top", "free", "smalls", "Qbuilt", "h1", "loadwait", "arrive", "-"])},
          1: {0: ("MMA", ["m1top", "m1ready", "u0arr", "m23top", "p0ok", "Rstored", "Wdone", "M3acc"]),
              1: ("FRONT", ["top", "free", "Gm", "sync", "chain1", "loadwait", "arrive", "-"]),
-             2: ("MID", ["top", "u0ok", "Ydone", "P0arr", "Zdone", "free", "-", "-"])}}
+             2: ("MID", ["top", "u0ok", "Ydone", "P0arr", "Zdone", "free", "-", "-"]),
+             3: ("MMA+", ["M1acc", "M1sync", "M2acc", "M2sync", "Rst", "-", "-", "-"])}}
 for kern in (0, 1):
     t0 = a[kern][a[kern] > 0].min() if (a[kern] > 0).any() else 0
     print("kernel", "K4p" if kern == 0 else "K8a", "(cycles since the first stamp of CTA 0)")
