@@ -290,6 +290,7 @@ __device__ __forceinline__ void st2(double* p, double v0, double v1) {  // 16-by
 // [kernel 0/1][role 0..3][iteration 0..15][event 0..7]
 __device__ long long g_pipe_clk[2][4][16][8];  // role 3: further stamps of the MMA role
 __device__ int g_pipe_clk_on = 0;
+__device__ long long g_pipe_cta[2][512][3];  // development aid: (smid, globaltimer at start, at end) of every CTA
 #define PIPE_STAMP(kern, role, it, ev)                                                   \
   do {                                                                                   \
     if (stamp && (it) < 16 && (threadIdx.x & 31) == 0) g_pipe_clk[kern][role][it][ev] = clock64(); \
@@ -367,6 +368,14 @@ ao2oao_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant_
   }
   build_pij(n, pij, tid, kAoPipeThreads);
   __syncthreads();
+  if (g_pipe_clk_on && tid == 0 && blockIdx.x < 512) {
+    unsigned smid;
+    long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_pipe_cta[0][blockIdx.x][0] = smid;
+    g_pipe_cta[0][blockIdx.x][1] = t;
+  }
 
   const int nloc = (nbatch > static_cast<int>(blockIdx.x))
                        ? (nbatch - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
@@ -498,6 +507,11 @@ ao2oao_pipe_kernel(const __grid_constant__ RectMap mfull, const __grid_constant_
         }
       });
       PIPE_STAMP(0, 0, it, 7);
+    }
+    if (g_pipe_clk_on && tid == 0 && blockIdx.x < 512) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      g_pipe_cta[0][blockIdx.x][2] = t;
     }
   }
 }
@@ -960,6 +974,10 @@ int evc_debug_pipe_occupancy(int* ao2oao_ctas, int* grad_ctas) {
   return 0;
 }
 // development aid: switch the clock64 stamps of CTA 0 on/off, read them back ([2][3][16][8] int64)
+int evc_debug_pipe_ctas(long long* out_host) {  // [2][512][3]
+  EVC_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_pipe_cta, sizeof(long long) * 2 * 512 * 3));
+  return 0;
+}
 int evc_debug_pipe_clocks(int enable, long long* out_host) {
   if (out_host) EVC_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_pipe_clk, sizeof(long long) * 2 * 4 * 16 * 8));
   EVC_CHECK_CUDA(cudaMemcpyToSymbol(g_pipe_clk_on, &enable, sizeof(int)));

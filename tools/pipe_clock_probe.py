@@ -49,3 +49,20 @@ for kern in (0, 1):
             if not row.any():
                 continue
             print(f"  {rname:5s} it={it:2d} " + " ".join(f"{e}={int(v - t0) if v else -1}" for e, v in zip(evs, row) if e != "-"))
+
+cb = (C.c_longlong * (2 * 512 * 3))()
+eng.lib.evc_debug_pipe_ctas.argtypes = [C.c_void_p]
+eng.lib.evc_debug_pipe_ctas(cb)
+ct = np.array(list(cb), dtype=np.int64).reshape(2, 512, 3)[0]
+ct = ct[ct[:, 1] > 0]
+t0 = ct[:, 1].min()
+print("K4p CTAs:", len(ct), "span of the kernel (ns):", int(ct[:, 2].max() - t0))
+print("  start offsets (ns): min %d median %d max %d" % (0, int(np.median(ct[:, 1] - t0)), int((ct[:, 1] - t0).max())))
+dur = ct[:, 2] - ct[:, 1]
+print("  CTA lifetimes (ns): min %d median %d max %d" % (int(dur.min()), int(np.median(dur)), int(dur.max())))
+print("  end offsets (ns): min %d median %d max %d" % (int((ct[:, 2] - t0).min()), int(np.median(ct[:, 2] - t0)), int((ct[:, 2] - t0).max())))
+per_sm = {}
+for smid, a, b in ct:
+    per_sm.setdefault(int(smid), []).append((int(a - t0), int(b - t0)))
+cnt = np.bincount([len(v) for v in per_sm.values()])
+print("  SMs by number of CTAs:", {k: int(v) for k, v in enumerate(cnt) if v})
