@@ -632,14 +632,14 @@ packed_grad_kernel(const ItemMap mfull, const ItemMap mlow, int n_rt, int64_t L8
 // contiguous run that is dotted with the n rows (m, b) of W -- no index arithmetic in the loop.
 // Everything is read exactly once; the rows are staged with asynchronous 16-byte copies.
 // ---------------------------------------------------------------------------
-constexpr int kStreamThreads = 128;
+constexpr int kStreamThreads = 32;
 
-// One CTA of 4 warps per (atom, geometry); no shared-memory staging: every thread issues all its loads (a few
-// coalesced 8-byte loads of the three integral runs, the matching entries of W, its share of the core-
-// Hamiltonian derivative) before the first use, so a CTA lives for about two memory round trips and 16 of them
-// are resident per SM.  (The staged forms -- cp.async rows + two block barriers per AO, or one CTA per geometry
+// One single-warp CTA per (atom, geometry); no shared-memory staging: every thread issues its loads (coalesced
+// 8-byte loads of the three integral runs, the matching entries of W, its share of the core-Hamiltonian
+// derivative) ahead of their use, 32 CTAs are resident per SM.  Smaller CTAs were faster every time: 256 threads
+// 0.265 ms, 128 threads 0.181 ms, 64 threads 0.161 ms, 32 threads 0.161 ms for 4096 H10-size geometries.  (The staged forms -- cp.async rows + two block barriers per AO, or one CTA per geometry
 // with W expanded in shared memory -- spent a third of their time in barriers: profiles/r02r.)
-__global__ void __launch_bounds__(kStreamThreads, 12)
+__global__ void __launch_bounds__(kStreamThreads, 32)
 grad_stream_kernel(int n, int natm, const int32_t* __restrict__ aoslices, const double* __restrict__ Wg,
                    const double* __restrict__ OmS, const double* __restrict__ Pao,
                    const double* __restrict__ ipovlp, const double* __restrict__ hcore_deriv,
