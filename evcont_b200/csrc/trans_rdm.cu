@@ -60,50 +60,19 @@ __device__ __forceinline__ void unpack_link(uint64_t rec, int& addr, int& a, int
 // by block barriers: zero + stage c[Ia,:]; alpha links (pure stores, every
 // (column, x) is written by exactly one link); beta links (read-modify-write,
 // again one link per (column, x)).
-__device__ __forceinline__ void alpha_phase(const TrdmParams& P, const double* __restrict__ c,
-                                            const uint64_t* __restrict__ la, int b0, int width,
-                                            bool swap, double* __restrict__ tile,
-                                            const double* __restrict__ crow, int nthreads) {
-  const int tid = threadIdx.x;
-  const int n = P.norb, Bp = P.Bt;
-  const int nb = static_cast<int>(P.nb);
-  const bool vec2 = ((nb & 1) == 0) && ((b0 & 1) == 0);
-  if (vec2) {
-    const int half = (width + 1) >> 1;
-    const int tot = P.nlink_a * half;
-    for (int k = tid; k < tot; k += nthreads) {
-      const int l = k / half, x = (k - l * half) * 2;
-      int Ja, a, i; double sg;
-      unpack_link(__ldg(la + l), Ja, a, i, sg);
-      const int col = swap ? (a * n + i) : (i * n + a);
-      const double* src = c + static_cast<int64_t>(Ja) * P.nb + b0 + x;
-      if (x + 1 < width) {
-        const double2 v = __ldg(reinterpret_cast<const double2*>(src));
-        *reinterpret_cast<double2*>(tile + col * Bp + x) = make_double2(sg * v.x, sg * v.y);
-      } else {
-        tile[col * Bp + x] = sg * __ldg(src);
-      }
-    }
-  } else {
-    const int tot = P.nlink_a * width;
-    for (int k = tid; k < tot; k += nthreads) {
-      const int l = k / width, x = k - l * width;
-      int Ja, a, i; double sg;
-      unpack_link(__ldg(la + l), Ja, a, i, sg);
-      const int col = swap ? (a * n + i) : (i * n + a);
-      tile[col * Bp + x] = sg * __ldg(c + static_cast<int64_t>(Ja) * P.nb + b0 + x);
-    }
-  }
-  // identity column: the CI coefficients themselves
-  for (int x = tid; x < width; x += nthreads) tile[P.n2 * Bp + x] = crow[b0 + x];
-}
-
+// Thread map of the link phases: one link per warp iteration, the lanes cover the
+// beta strings of the tile.  The link record of an alpha link is warp-uniform (one
+// decode serves the bra and the ket row copy) and no index is split by a division
+// (the flat (link, x) map spent most of the kernel's instructions on that).
+template <int NWARPS>
 __device__ __forceinline__ void build_tiles(const TrdmParams& P, const double* __restrict__ cbra,
                                             const double* __restrict__ cket, int64_t Ia, int b0,
                                             double* __restrict__ braT, double* __restrict__ ketT,
                                             double* __restrict__ crow_bra,
-                                            double* __restrict__ crow_ket, int nthreads) {
+                                            double* __restrict__ crow_ket) {
+  constexpr int nthreads = NWARPS * 32;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const int n = P.norb, Bp = P.Bt;
   const int nb = static_cast<int>(P.nb);
   {
@@ -123,26 +92,54 @@ __device__ __forceinline__ void build_tiles(const TrdmParams& P, const double* _
   __syncthreads();
   const int width = min(P.Bt, nb - b0);
   const uint64_t* la = P.link_a + Ia * P.nlink_a;
-  alpha_phase(P, cbra, la, b0, width, true, braT, crow_bra, nthreads);
-  alpha_phase(P, cket, la, b0, width, false, ketT, crow_ket, nthreads);
+  const bool vec2 = ((nb & 1) == 0) && ((b0 & 1) == 0);
+  for (int l = warp; l < P.nlink_a; l += NWARPS) {
+    int Ja, a, i; double sg;
+    unpack_link(__ldg(la + l), Ja, a, i, sg);
+    const double* sb = cbra + static_cast<int64_t>(Ja) * P.nb + b0;
+    const double* sk = cket + static_cast<int64_t>(Ja) * P.nb + b0;
+    double* db = braT + (a * n + i) * Bp;
+    double* dk = ketT + (i * n + a) * Bp;
+    if (vec2) {
+      for (int x = 2 * lane; x < width; x += 64) {
+        if (x + 1 < width) {
+          const double2 vb = __ldg(reinterpret_cast<const double2*>(sb + x));
+          const double2 vk = __ldg(reinterpret_cast<const double2*>(sk + x));
+          *reinterpret_cast<double2*>(db + x) = make_double2(sg * vb.x, sg * vb.y);
+          *reinterpret_cast<double2*>(dk + x) = make_double2(sg * vk.x, sg * vk.y);
+        } else {
+          db[x] = sg * __ldg(sb + x);
+          dk[x] = sg * __ldg(sk + x);
+        }
+      }
+    } else {
+      for (int x = lane; x < width; x += 32) {
+        db[x] = sg * __ldg(sb + x);
+        dk[x] = sg * __ldg(sk + x);
+      }
+    }
+  }
+  // identity column: the CI coefficients themselves
+  for (int x = tid; x < width; x += nthreads) {
+    braT[P.n2 * Bp + x] = crow_bra[b0 + x];
+    ketT[P.n2 * Bp + x] = crow_ket[b0 + x];
+  }
   __syncthreads();
-  {
-    const int tot = P.nlink_b * width;
-    for (int k = tid; k < tot; k += nthreads) {
-      const int l = k / width, x = k - l * width;
+  for (int l = warp; l < P.nlink_b; l += NWARPS) {
+    const uint64_t* lb = P.link_b + static_cast<int64_t>(l) * P.nb + b0;
+    for (int x = lane; x < width; x += 32) {
       int Jb, a, i; double sg;
-      unpack_link(__ldg(P.link_b + static_cast<int64_t>(l) * P.nb + b0 + x), Jb, a, i, sg);
+      unpack_link(__ldg(lb + x), Jb, a, i, sg);
       braT[(a * n + i) * Bp + x] += sg * crow_bra[Jb];
       ketT[(i * n + a) * Bp + x] += sg * crow_ket[Jb];
     }
   }
 }
 
-template <int NWARPS, int MAXBLK>
-__global__ void __launch_bounds__(NWARPS * 32)
+template <int NWARPS, int MAXBLK, int MINCTA>
+__global__ void __launch_bounds__(NWARPS * 32, MINCTA)
 trdm_fused_kernel(const __grid_constant__ TrdmParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nthreads = NWARPS * 32;
   const int Bp = P.Bt;
   const int nbpad = (static_cast<int>(P.nb) + 1) & ~1;
   double* braT = reinterpret_cast<double*>(smem_raw);
@@ -184,7 +181,7 @@ trdm_fused_kernel(const __grid_constant__ TrdmParams P) {
     for (int tile = 0; tile < P.ntile; ++tile) {
       const int b0 = tile * P.Bt;
       __syncthreads();  // previous MMA phase done with the tiles
-      build_tiles(P, cbra, cket, Ia, b0, braT, ketT, crow_bra, crow_ket, nthreads);
+      build_tiles<NWARPS>(P, cbra, cket, Ia, b0, braT, ketT, crow_bra, crow_ket);
       __syncthreads();
 #pragma unroll 1
       for (int k0 = 0; k0 < P.Bt; k0 += 4) {
@@ -302,6 +299,11 @@ int plan_trdm(int norb, int64_t na, int64_t nb, int npairs, int sm_count, TrdmPl
   pl->T = pl->nblk * (pl->nblk + 1) / 2;
   if (pl->nblk > 11) return -1;
   pl->nwarps = pl->nblk >= 9 ? 16 : 8;
+  // 5 macro-block rows (norb = 8): 16 warps with one macro-block each fit 64 registers, so two such CTAs stay
+  // resident and the link phases (latency-bound) have twice the warps: 0.623 -> 0.597 ms for 210 pairs.  With two
+  // macro-blocks per warp (norb = 9, 10) the 64-register build spills and loses (11.33 against 10.78 ms at norb = 10).
+  const bool wide16 = pl->nblk >= 5 && pl->T <= 16;
+  if (wide16) pl->nwarps = 16;
   const int per_smsp = (pl->T + 3) / 4;
   const int warps_per_smsp = pl->nwarps / 4;
   pl->maxblk = (per_smsp + warps_per_smsp - 1) / warps_per_smsp;
@@ -309,7 +311,7 @@ int plan_trdm(int norb, int64_t na, int64_t nb, int npairs, int sm_count, TrdmPl
   const size_t smem_cap = 227 * 1024;
   const int nbpad = (static_cast<int>(nb) + 1) & ~1;
   const size_t crow_bytes = 2 * static_cast<size_t>(nbpad) * 8;
-  const int want_occ = pl->nwarps == 8 ? 2 : 1;
+  const int want_occ = (pl->nwarps == 8 || wide16) ? 2 : 1;
   const size_t budget = smem_cap / want_occ - 1024;  // 1 KB reserved per CTA
   int best = -1;
   double best_cost = 1e300;
@@ -365,9 +367,9 @@ void assign_blocks(const TrdmPlan& pl, TrdmParams* P) {
   }
 }
 
-template <int NWARPS, int MAXBLK>
+template <int NWARPS, int MAXBLK, int MINCTA = (NWARPS == 8 ? 2 : 1)>
 int launch_fused(const TrdmParams& P, const TrdmPlan& pl, int nitems, cudaStream_t stream) {
-  auto kern = trdm_fused_kernel<NWARPS, MAXBLK>;
+  auto kern = trdm_fused_kernel<NWARPS, MAXBLK, MINCTA>;
   EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(pl.smem)));
   kern<<<nitems, NWARPS * 32, pl.smem, stream>>>(P);
@@ -435,6 +437,7 @@ int evc_trans_rdm12_batch_strided(evc_ctx* ctx, int norb, int64_t na, int64_t nb
     }
   } else {
     switch (pl.maxblk) {
+      case 1: rc = launch_fused<16, 1, 2>(P, pl, nitems, ctx->stream); break;
       case 3: rc = launch_fused<16, 3>(P, pl, nitems, ctx->stream); break;
       case 4: rc = launch_fused<16, 4>(P, pl, nitems, ctx->stream); break;
       case 5: rc = launch_fused<16, 5>(P, pl, nitems, ctx->stream); break;
