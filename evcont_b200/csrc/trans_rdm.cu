@@ -22,6 +22,7 @@
 // = 2x2 DMMA tiles) with accumulators in registers.  Partial sums per CTA go to
 // the workspace and are reduced in slice order => deterministic.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -136,6 +137,32 @@ __device__ __forceinline__ void build_tiles(const TrdmParams& P, const double* _
   }
 }
 
+// DMMA phase of one tile: NB macro-blocks of this warp, straight-line (all fragment loads of a k-step ahead of its
+// DMMAs; a per-block `s < my_count` branch kept every block's loads next to its own DMMAs, their latency exposed).
+template <int NB, int MAXBLK>
+__device__ __forceinline__ void mma_tile(double (&acc)[MAXBLK][4][2], const double* __restrict__ braT,
+                                         const double* __restrict__ ketT, const int (&xoff)[MAXBLK],
+                                         const int (&yoff)[MAXBLK], int Bt, int Bp) {
+#pragma unroll 1
+  for (int k0 = 0; k0 < Bt; k0 += 4) {
+    double a0[NB > 0 ? NB : 1], a1[NB > 0 ? NB : 1], b0v[NB > 0 ? NB : 1], b1v[NB > 0 ? NB : 1];
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+      a0[s] = braT[xoff[s] + k0];
+      a1[s] = braT[xoff[s] + 8 * Bp + k0];
+      b0v[s] = ketT[yoff[s] + k0];
+      b1v[s] = ketT[yoff[s] + 8 * Bp + k0];
+    }
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+      dmma8x8x4(acc[s][0][0], acc[s][0][1], a0[s], b0v[s]);
+      dmma8x8x4(acc[s][1][0], acc[s][1][1], a0[s], b1v[s]);
+      dmma8x8x4(acc[s][2][0], acc[s][2][1], a1[s], b0v[s]);
+      dmma8x8x4(acc[s][3][0], acc[s][3][1], a1[s], b1v[s]);
+    }
+  }
+}
+
 template <int NWARPS, int MAXBLK, int MINCTA>
 __global__ void __launch_bounds__(NWARPS * 32, MINCTA)
 trdm_fused_kernel(const __grid_constant__ TrdmParams P) {
@@ -183,25 +210,203 @@ trdm_fused_kernel(const __grid_constant__ TrdmParams P) {
       __syncthreads();  // previous MMA phase done with the tiles
       build_tiles<NWARPS>(P, cbra, cket, Ia, b0, braT, ketT, crow_bra, crow_ket);
       __syncthreads();
-#pragma unroll 1
-      for (int k0 = 0; k0 < P.Bt; k0 += 4) {
+      // a warp has MAXBLK or MAXBLK - 1 macro-blocks (fewer: its spare slots repeat block 0 and are never stored)
+      if (my_count == MAXBLK) mma_tile<MAXBLK, MAXBLK>(acc, braT, ketT, xoff, yoff, P.Bt, Bp);
+      else mma_tile<MAXBLK - 1, MAXBLK>(acc, braT, ketT, xoff, yoff, P.Bt, Bp);
+    }
+  }
+  // write partial sums: [item][t][tile(2x2)][8x8 row-major]
+  double* out = P.partial + static_cast<int64_t>(item) * P.T * 256;
 #pragma unroll
-        for (int s = 0; s < MAXBLK; ++s) {
-          if (s < my_count) {
-            const double a0 = braT[xoff[s] + k0];
-            const double a1 = braT[xoff[s] + 8 * Bp + k0];
-            const double b0v = ketT[yoff[s] + k0];
-            const double b1v = ketT[yoff[s] + 8 * Bp + k0];
-            dmma8x8x4(acc[s][0][0], acc[s][0][1], a0, b0v);
-            dmma8x8x4(acc[s][1][0], acc[s][1][1], a0, b1v);
-            dmma8x8x4(acc[s][2][0], acc[s][2][1], a1, b0v);
-            dmma8x8x4(acc[s][3][0], acc[s][3][1], a1, b1v);
+  for (int s = 0; s < MAXBLK; ++s) {
+    if (s < my_count) {
+      double* blk = out + (my_start + s) * 256;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<double2*>(blk + q * 64)[lane] = make_double2(acc[s][q][0], acc[s][q][1]);
+    }
+  }
+}
+
+// ---- producer / consumer form of the fused kernel (7 or 8 macro-block rows: norb = 10, 11) ------------------------
+// The fused kernel above alternates a t1 tile build (latency-bound gathers) and a DMMA phase in every warp, two
+// CTAs per SM filling each other's gaps: the DMMA pipe is busy 51 % of the time.  Here ONE 16-warp CTA per SM holds
+// two tile stages: warps 8..15 build stage (it + 1) while warps 0..7 multiply stage it.  The builders hold no
+// accumulators, so they keep four link records and their eight gathers in flight per lane.  Hand-over by named
+// barriers (bar.arrive by the side that is done, bar.sync by the side that waits; the PTX producer / consumer
+// pattern).  Same tiles, same k order and same alpha slices as the fused kernel => bit-identical results.
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+constexpr int kPipeMma = 8, kPipeBuild = 8;                      // warps per role
+constexpr int kBarFull = 1, kBarEmpty = 3, kBarBuild = 5;        // named barriers: full[2], empty[2], builders
+
+__device__ __forceinline__ void pipe_build(const TrdmParams& P, const double* __restrict__ cbra,
+                                           const double* __restrict__ cket, int64_t Ia, int b0,
+                                           double* __restrict__ braT, double* __restrict__ ketT,
+                                           double* __restrict__ crow_bra, double* __restrict__ crow_ket) {
+  constexpr int nthreads = kPipeBuild * 32;
+  const int tid = threadIdx.x - kPipeMma * 32;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n = P.norb, Bp = P.Bt;
+  const int nb = static_cast<int>(P.nb);
+  if (b0 == 0) {  // c[Ia, :] rows change only with Ia; the beta phase of the previous step still reads them
+    bar_sync_n(kBarBuild, nthreads);
+    const double* sb = cbra + Ia * P.nb;
+    const double* sk = cket + Ia * P.nb;
+    for (int k = tid; k < nb; k += nthreads) {
+      crow_bra[k] = __ldg(sb + k);
+      crow_ket[k] = __ldg(sk + k);
+    }
+  }
+  {
+    double2* t2 = reinterpret_cast<double2*>(braT);  // braT and ketT of a stage are contiguous
+    const int tot = P.W * Bp;
+    for (int k = tid; k < tot; k += nthreads) t2[k] = make_double2(0.0, 0.0);
+  }
+  bar_sync_n(kBarBuild, nthreads);
+  const int width = min(P.Bt, nb - b0);
+  const uint64_t* la = P.link_a + Ia * P.nlink_a;
+  const bool vec2 = ((nb & 1) == 0) && ((b0 & 1) == 0) && ((width & 1) == 0);
+  // alpha links: four links per warp pass, all records then all gathers in flight before the first store
+  for (int l0 = warp; l0 < P.nlink_a; l0 += 4 * kPipeBuild) {
+    uint64_t rec[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = l0 + j * kPipeBuild;
+      rec[j] = l < P.nlink_a ? __ldg(la + l) : ~0ull;
+    }
+    if (vec2) {
+      for (int x = 2 * lane; x < width; x += 64) {
+        double2 vb[4], vk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rec[j] != ~0ull) {
+            const int64_t off = static_cast<int64_t>(rec[j] & 0xffffffffu) * P.nb + b0 + x;
+            vb[j] = __ldg(reinterpret_cast<const double2*>(cbra + off));
+            vk[j] = __ldg(reinterpret_cast<const double2*>(cket + off));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rec[j] != ~0ull) {
+            int Ja, a, i; double sg;
+            unpack_link(rec[j], Ja, a, i, sg);
+            *reinterpret_cast<double2*>(braT + (a * n + i) * Bp + x) = make_double2(sg * vb[j].x, sg * vb[j].y);
+            *reinterpret_cast<double2*>(ketT + (i * n + a) * Bp + x) = make_double2(sg * vk[j].x, sg * vk[j].y);
+          }
+        }
+      }
+    } else {
+      for (int x = lane; x < width; x += 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rec[j] != ~0ull) {
+            int Ja, a, i; double sg;
+            unpack_link(rec[j], Ja, a, i, sg);
+            const int64_t off = static_cast<int64_t>(Ja) * P.nb + b0 + x;
+            braT[(a * n + i) * Bp + x] = sg * __ldg(cbra + off);
+            ketT[(i * n + a) * Bp + x] = sg * __ldg(cket + off);
           }
         }
       }
     }
   }
-  // write partial sums: [item][t][tile(2x2)][8x8 row-major]
+  // identity column: the CI coefficients themselves
+  for (int x = tid; x < width; x += nthreads) {
+    braT[P.n2 * Bp + x] = crow_bra[b0 + x];
+    ketT[P.n2 * Bp + x] = crow_ket[b0 + x];
+  }
+  bar_sync_n(kBarBuild, nthreads);
+  // beta links: four link rows per warp pass, the lanes over the beta strings of the tile
+  for (int l0 = warp; l0 < P.nlink_b; l0 += 4 * kPipeBuild) {
+    for (int x = lane; x < width; x += 32) {
+      uint64_t rec[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int l = l0 + j * kPipeBuild;
+        rec[j] = l < P.nlink_b ? __ldg(P.link_b + static_cast<int64_t>(l) * P.nb + b0 + x) : ~0ull;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (rec[j] != ~0ull) {
+          int Jb, a, i; double sg;
+          unpack_link(rec[j], Jb, a, i, sg);
+          braT[(a * n + i) * Bp + x] += sg * crow_bra[Jb];
+          ketT[(i * n + a) * Bp + x] += sg * crow_ket[Jb];
+        }
+      }
+    }
+  }
+}
+
+template <int MAXBLK>
+__global__ void __launch_bounds__((kPipeMma + kPipeBuild) * 32, 1)
+trdm_pipe_kernel(const __grid_constant__ TrdmParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int Bp = P.Bt;
+  const int nbpad = (static_cast<int>(P.nb) + 1) & ~1;
+  const int tile_elems = P.W * Bp;
+  double* stage0 = reinterpret_cast<double*>(smem_raw);          // stage s: braT | ketT
+  double* crow_bra = stage0 + 4 * tile_elems;
+  double* crow_ket = crow_bra + nbpad;
+
+  const int item = blockIdx.x;
+  const int pair = item / P.nsplit;
+  const int split = item - pair * P.nsplit;
+  const int ibra = P.pairs[2 * pair], iket = P.pairs[2 * pair + 1];
+  const double* cbra = P.civecs + ibra * P.vec_stride;
+  const double* cket = P.civecs + iket * P.vec_stride;
+  const int64_t ia_lo = P.na * split / P.nsplit;
+  const int64_t ia_hi = P.na * (split + 1) / P.nsplit;
+  const int nsteps = static_cast<int>(ia_hi - ia_lo) * P.ntile;
+  constexpr int kAll = (kPipeMma + kPipeBuild) * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp >= kPipeMma) {
+    // ---- builders ----
+    int64_t Ia = ia_lo;
+    int tile = 0;
+    for (int it = 0; it < nsteps; ++it) {
+      const int s = it & 1;
+      if (it >= 2) bar_sync_n(kBarEmpty + s, kAll);  // the MMA warps are done with this stage
+      double* braT = stage0 + 2 * s * tile_elems;
+      pipe_build(P, cbra, cket, Ia, tile * P.Bt, braT, braT + tile_elems, crow_bra, crow_ket);
+      __threadfence_block();
+      bar_arrive_n(kBarFull + s, kAll);
+      if (++tile == P.ntile) { tile = 0; ++Ia; }
+    }
+    return;
+  }
+
+  // ---- MMA warps ----
+  const int g = lane >> 2, tg = lane & 3;
+  const int my_start = P.blk_start[warp], my_count = P.blk_count[warp];
+  int xoff[MAXBLK], yoff[MAXBLK];
+#pragma unroll
+  for (int s = 0; s < MAXBLK; ++s) {
+    int t = my_start + (s < my_count ? s : 0);
+    int r = 0;
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    const int cc = t - r * (r + 1) / 2;
+    xoff[s] = (r * 16 + g) * Bp + tg;
+    yoff[s] = (cc * 16 + g) * Bp + tg;
+  }
+  double acc[MAXBLK][4][2];
+#pragma unroll
+  for (int s = 0; s < MAXBLK; ++s)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[s][q][0] = acc[s][q][1] = 0.0;
+
+  for (int it = 0; it < nsteps; ++it) {
+    const int st = it & 1;
+    const double* braT = stage0 + 2 * st * tile_elems;
+    const double* ketT = braT + tile_elems;
+    bar_sync_n(kBarFull + st, kAll);
+    if (my_count == MAXBLK) mma_tile<MAXBLK, MAXBLK>(acc, braT, ketT, xoff, yoff, P.Bt, Bp);
+    else mma_tile<MAXBLK - 1, MAXBLK>(acc, braT, ketT, xoff, yoff, P.Bt, Bp);
+    if (it + 2 < nsteps) bar_arrive_n(kBarEmpty + st, kAll);
+  }
   double* out = P.partial + static_cast<int64_t>(item) * P.T * 256;
 #pragma unroll
   for (int s = 0; s < MAXBLK; ++s) {
@@ -290,6 +495,8 @@ __global__ void stack_scatter_rows_kernel(int N, int norb, const double* __restr
 struct TrdmPlan {
   int W, nblk, T, nwarps, maxblk, Bt, ntile, nsplit, occupancy;
   size_t smem;
+  bool pipe;         // producer / consumer kernel (two tile stages, one CTA per SM)
+  size_t smem_pipe;
 };
 
 int plan_trdm(int norb, int64_t na, int64_t nb, int npairs, int sm_count, TrdmPlan* pl) {
@@ -347,6 +554,10 @@ int plan_trdm(int norb, int64_t na, int64_t nb, int npairs, int sm_count, TrdmPl
   if (s < 1) s = 1;
   if (s > 4096) s = 4096;
   pl->nsplit = static_cast<int>(s);
+  // the producer / consumer kernel keeps the tile width and the alpha slices of the fused plan (same bits)
+  static const int use_pipe = [] { const char* e = getenv("EVC_TRDM_PIPE"); return e ? atoi(e) : 1; }();
+  pl->smem_pipe = 2 * (pl->smem - crow_bytes) + crow_bytes;
+  pl->pipe = use_pipe && pl->nwarps == 8 && pl->nblk >= 7 && pl->smem_pipe + 1024 <= smem_cap;
   return 0;
 }
 
@@ -365,6 +576,16 @@ void assign_blocks(const TrdmPlan& pl, TrdmParams* P) {
     P->blk_count[w] = static_cast<unsigned char>(w < pl.nwarps ? count[w] : 0);
     if (w < pl.nwarps) start += count[w];
   }
+}
+
+template <int MAXBLK>
+int launch_pipe(const TrdmParams& P, const TrdmPlan& pl, int nitems, cudaStream_t stream) {
+  auto kern = trdm_pipe_kernel<MAXBLK>;
+  EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(pl.smem_pipe)));
+  kern<<<nitems, (kPipeMma + kPipeBuild) * 32, pl.smem_pipe, stream>>>(P);
+  EVC_CHECK_LAUNCH();
+  return 0;
 }
 
 template <int NWARPS, int MAXBLK, int MINCTA = (NWARPS == 8 ? 2 : 1)>
@@ -426,7 +647,17 @@ int evc_trans_rdm12_batch_strided(evc_ctx* ctx, int norb, int64_t na, int64_t nb
   assign_blocks(pl, &P);
   const int nitems = npairs * pl.nsplit;
   int rc = -1;
-  if (pl.nwarps == 8) {
+  if (pl.pipe && pl.smem_pipe <= ctx->smem_optin) {
+    switch (pl.maxblk) {
+      case 3: rc = launch_pipe<3>(P, pl, nitems, ctx->stream); break;
+      case 4: rc = launch_pipe<4>(P, pl, nitems, ctx->stream); break;
+      case 5: rc = launch_pipe<5>(P, pl, nitems, ctx->stream); break;
+      default: break;
+    }
+  }
+  if (rc != -1) {
+    // launched above
+  } else if (pl.nwarps == 8) {
     switch (pl.maxblk) {
       case 1: rc = launch_fused<8, 1>(P, pl, nitems, ctx->stream); break;
       case 2: rc = launch_fused<8, 2>(P, pl, nitems, ctx->stream); break;
