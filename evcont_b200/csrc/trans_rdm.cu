@@ -56,11 +56,18 @@ __device__ __forceinline__ void unpack_link(uint64_t rec, int& addr, int& a, int
   sgn = static_cast<double>(static_cast<signed char>((rec >> 48) & 0xff));
 }
 
+// sign of a link as a mask on the IEEE sign bit (the sign byte is +1 or -1): v ^ mask == sgn * v bit for bit, and no
+// FP64 instruction (a scalar FP64 operation waits behind the DMMAs that stream through the same datapath)
+__device__ __forceinline__ unsigned long long link_sign_mask(uint64_t rec) { return ((rec >> 55) & 1ull) << 63; }
+__device__ __forceinline__ double flip(double v, unsigned long long m) {
+  return __longlong_as_double(static_cast<long long>(static_cast<unsigned long long>(__double_as_longlong(v)) ^ m));
+}
+
 // Build the two [W x Bp] tiles (bra: E_pq stored in column (q,p); ket: column
 // (p,q)) for alpha string Ia and beta strings [b0, b0+Bt).  Three phases separated
-// by block barriers: zero + stage c[Ia,:]; alpha links (pure stores, every
-// (column, x) is written by exactly one link); beta links (read-modify-write,
-// again one link per (column, x)).
+// by block barriers: zero + stage c[Ia,:]; beta links (pure stores of +-c[Ia, Jb],
+// every (column, x) is written by at most one link); alpha links (added to their
+// rows with contiguous 16-byte accesses, again one link per (column, x)).
 // Thread map of the link phases: one link per warp iteration, the lanes cover the
 // beta strings of the tile.  The link record of an alpha link is warp-uniform (one
 // decode serves the bra and the ket row copy) and no index is split by a division
@@ -92,11 +99,33 @@ __device__ __forceinline__ void build_tiles(const TrdmParams& P, const double* _
   }
   __syncthreads();
   const int width = min(P.Bt, nb - b0);
+  // beta links first, as pure stores into the zeroed tiles (one link per (column, x)); the alpha links then ADD
+  // their rows with contiguous 16-byte accesses.  (beta as read-modify-write cost four scattered shared-memory
+  // accesses per element instead of two; tile = alpha + beta either way, one rounding.)
+  for (int l = warp; l < P.nlink_b; l += NWARPS) {
+    const uint64_t* lb = P.link_b + static_cast<int64_t>(l) * P.nb + b0;
+    for (int x = lane; x < width; x += 32) {
+      const uint64_t rec = __ldg(lb + x);
+      int Jb, a, i; double sg;
+      unpack_link(rec, Jb, a, i, sg);
+      const unsigned long long m = link_sign_mask(rec);
+      braT[(a * n + i) * Bp + x] = flip(crow_bra[Jb], m);
+      ketT[(i * n + a) * Bp + x] = flip(crow_ket[Jb], m);
+    }
+  }
+  // identity column: the CI coefficients themselves
+  for (int x = tid; x < width; x += nthreads) {
+    braT[P.n2 * Bp + x] = crow_bra[b0 + x];
+    ketT[P.n2 * Bp + x] = crow_ket[b0 + x];
+  }
+  __syncthreads();
   const uint64_t* la = P.link_a + Ia * P.nlink_a;
   const bool vec2 = ((nb & 1) == 0) && ((b0 & 1) == 0);
   for (int l = warp; l < P.nlink_a; l += NWARPS) {
+    const uint64_t rec = __ldg(la + l);
     int Ja, a, i; double sg;
-    unpack_link(__ldg(la + l), Ja, a, i, sg);
+    unpack_link(rec, Ja, a, i, sg);
+    const unsigned long long m = link_sign_mask(rec);
     const double* sb = cbra + static_cast<int64_t>(Ja) * P.nb + b0;
     const double* sk = cket + static_cast<int64_t>(Ja) * P.nb + b0;
     double* db = braT + (a * n + i) * Bp;
@@ -106,33 +135,20 @@ __device__ __forceinline__ void build_tiles(const TrdmParams& P, const double* _
         if (x + 1 < width) {
           const double2 vb = __ldg(reinterpret_cast<const double2*>(sb + x));
           const double2 vk = __ldg(reinterpret_cast<const double2*>(sk + x));
-          *reinterpret_cast<double2*>(db + x) = make_double2(sg * vb.x, sg * vb.y);
-          *reinterpret_cast<double2*>(dk + x) = make_double2(sg * vk.x, sg * vk.y);
+          const double2 tb = *reinterpret_cast<const double2*>(db + x);
+          const double2 tk = *reinterpret_cast<const double2*>(dk + x);
+          *reinterpret_cast<double2*>(db + x) = make_double2(tb.x + flip(vb.x, m), tb.y + flip(vb.y, m));
+          *reinterpret_cast<double2*>(dk + x) = make_double2(tk.x + flip(vk.x, m), tk.y + flip(vk.y, m));
         } else {
-          db[x] = sg * __ldg(sb + x);
-          dk[x] = sg * __ldg(sk + x);
+          db[x] += flip(__ldg(sb + x), m);
+          dk[x] += flip(__ldg(sk + x), m);
         }
       }
     } else {
       for (int x = lane; x < width; x += 32) {
-        db[x] = sg * __ldg(sb + x);
-        dk[x] = sg * __ldg(sk + x);
+        db[x] += flip(__ldg(sb + x), m);
+        dk[x] += flip(__ldg(sk + x), m);
       }
-    }
-  }
-  // identity column: the CI coefficients themselves
-  for (int x = tid; x < width; x += nthreads) {
-    braT[P.n2 * Bp + x] = crow_bra[b0 + x];
-    ketT[P.n2 * Bp + x] = crow_ket[b0 + x];
-  }
-  __syncthreads();
-  for (int l = warp; l < P.nlink_b; l += NWARPS) {
-    const uint64_t* lb = P.link_b + static_cast<int64_t>(l) * P.nb + b0;
-    for (int x = lane; x < width; x += 32) {
-      int Jb, a, i; double sg;
-      unpack_link(__ldg(lb + x), Jb, a, i, sg);
-      braT[(a * n + i) * Bp + x] += sg * crow_bra[Jb];
-      ketT[(i * n + a) * Bp + x] += sg * crow_ket[Jb];
     }
   }
 }
@@ -266,59 +282,7 @@ __device__ __forceinline__ void pipe_build(const TrdmParams& P, const double* __
   }
   bar_sync_n(kBarBuild, nthreads);
   const int width = min(P.Bt, nb - b0);
-  const uint64_t* la = P.link_a + Ia * P.nlink_a;
-  const bool vec2 = ((nb & 1) == 0) && ((b0 & 1) == 0) && ((width & 1) == 0);
-  // alpha links: four links per warp pass, all records then all gathers in flight before the first store
-  for (int l0 = warp; l0 < P.nlink_a; l0 += 4 * kPipeBuild) {
-    uint64_t rec[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int l = l0 + j * kPipeBuild;
-      rec[j] = l < P.nlink_a ? __ldg(la + l) : ~0ull;
-    }
-    if (vec2) {
-      for (int x = 2 * lane; x < width; x += 64) {
-        double2 vb[4], vk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (rec[j] != ~0ull) {
-            const int64_t off = static_cast<int64_t>(rec[j] & 0xffffffffu) * P.nb + b0 + x;
-            vb[j] = __ldg(reinterpret_cast<const double2*>(cbra + off));
-            vk[j] = __ldg(reinterpret_cast<const double2*>(cket + off));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (rec[j] != ~0ull) {
-            int Ja, a, i; double sg;
-            unpack_link(rec[j], Ja, a, i, sg);
-            *reinterpret_cast<double2*>(braT + (a * n + i) * Bp + x) = make_double2(sg * vb[j].x, sg * vb[j].y);
-            *reinterpret_cast<double2*>(ketT + (i * n + a) * Bp + x) = make_double2(sg * vk[j].x, sg * vk[j].y);
-          }
-        }
-      }
-    } else {
-      for (int x = lane; x < width; x += 32) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (rec[j] != ~0ull) {
-            int Ja, a, i; double sg;
-            unpack_link(rec[j], Ja, a, i, sg);
-            const int64_t off = static_cast<int64_t>(Ja) * P.nb + b0 + x;
-            braT[(a * n + i) * Bp + x] = sg * __ldg(cbra + off);
-            ketT[(i * n + a) * Bp + x] = sg * __ldg(cket + off);
-          }
-        }
-      }
-    }
-  }
-  // identity column: the CI coefficients themselves
-  for (int x = tid; x < width; x += nthreads) {
-    braT[P.n2 * Bp + x] = crow_bra[b0 + x];
-    ketT[P.n2 * Bp + x] = crow_ket[b0 + x];
-  }
-  bar_sync_n(kBarBuild, nthreads);
-  // beta links: four link rows per warp pass, the lanes over the beta strings of the tile
+  // beta links (pure stores, see build_tiles): four link rows per warp pass, the lanes over the beta strings
   for (int l0 = warp; l0 < P.nlink_b; l0 += 4 * kPipeBuild) {
     for (int x = lane; x < width; x += 32) {
       uint64_t rec[4];
@@ -332,8 +296,70 @@ __device__ __forceinline__ void pipe_build(const TrdmParams& P, const double* __
         if (rec[j] != ~0ull) {
           int Jb, a, i; double sg;
           unpack_link(rec[j], Jb, a, i, sg);
-          braT[(a * n + i) * Bp + x] += sg * crow_bra[Jb];
-          ketT[(i * n + a) * Bp + x] += sg * crow_ket[Jb];
+          const unsigned long long m = link_sign_mask(rec[j]);
+          braT[(a * n + i) * Bp + x] = flip(crow_bra[Jb], m);
+          ketT[(i * n + a) * Bp + x] = flip(crow_ket[Jb], m);
+        }
+      }
+    }
+  }
+  // identity column: the CI coefficients themselves
+  for (int x = tid; x < width; x += nthreads) {
+    braT[P.n2 * Bp + x] = crow_bra[b0 + x];
+    ketT[P.n2 * Bp + x] = crow_ket[b0 + x];
+  }
+  bar_sync_n(kBarBuild, nthreads);
+  // alpha links (added to the rows): four links per warp pass, all records, then all gathers and row reads in
+  // flight before the first addition
+  const uint64_t* la = P.link_a + Ia * P.nlink_a;
+  const bool vec2 = ((nb & 1) == 0) && ((b0 & 1) == 0) && ((width & 1) == 0);
+  for (int l0 = warp; l0 < P.nlink_a; l0 += 4 * kPipeBuild) {
+    uint64_t rec[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = l0 + j * kPipeBuild;
+      rec[j] = l < P.nlink_a ? __ldg(la + l) : ~0ull;
+    }
+    if (vec2) {
+      for (int x = 2 * lane; x < width; x += 64) {
+        double2 vb[4], vk[4], tb[4], tk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rec[j] != ~0ull) {
+            int Ja, a, i; double sg;
+            unpack_link(rec[j], Ja, a, i, sg);
+            const int64_t off = static_cast<int64_t>(Ja) * P.nb + b0 + x;
+            vb[j] = __ldg(reinterpret_cast<const double2*>(cbra + off));
+            vk[j] = __ldg(reinterpret_cast<const double2*>(cket + off));
+            tb[j] = *reinterpret_cast<const double2*>(braT + (a * n + i) * Bp + x);
+            tk[j] = *reinterpret_cast<const double2*>(ketT + (i * n + a) * Bp + x);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rec[j] != ~0ull) {
+            int Ja, a, i; double sg;
+            unpack_link(rec[j], Ja, a, i, sg);
+            const unsigned long long m = link_sign_mask(rec[j]);
+            *reinterpret_cast<double2*>(braT + (a * n + i) * Bp + x) =
+                make_double2(tb[j].x + flip(vb[j].x, m), tb[j].y + flip(vb[j].y, m));
+            *reinterpret_cast<double2*>(ketT + (i * n + a) * Bp + x) =
+                make_double2(tk[j].x + flip(vk[j].x, m), tk[j].y + flip(vk[j].y, m));
+          }
+        }
+      }
+    } else {
+      for (int x = lane; x < width; x += 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rec[j] != ~0ull) {
+            int Ja, a, i; double sg;
+            unpack_link(rec[j], Ja, a, i, sg);
+            const unsigned long long m = link_sign_mask(rec[j]);
+            const int64_t off = static_cast<int64_t>(Ja) * P.nb + b0 + x;
+            braT[(a * n + i) * Bp + x] += flip(__ldg(cbra + off), m);
+            ketT[(i * n + a) * Bp + x] += flip(__ldg(cket + off), m);
+          }
         }
       }
     }
