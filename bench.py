@@ -853,7 +853,12 @@ def run_b200(args):
                          "issued_tflops": issued / (trdm_ms * 1e-3) / 1e12,
                          "peak": dgemm_tf, "unit": "TFLOP/s",
                          "frac": (trdm_alg_flops / (trdm_ms * 1e-3) / 1e12 / dgemm_tf) if dgemm_tf else None,
-                         "traffic": None}}
+                         "issued_frac": (issued / (trdm_ms * 1e-3) / 1e12 / dgemm_tf) if dgemm_tf else None,
+                         "kernel": "trdm_pipe_kernel (norb = 10, 11) / trdm_fused_kernel + trdm_finalize_kernel",
+                         # dram__bytes_read + dram__bytes_write of one trdm_pipe_kernel launch of 210 H10 pairs
+                         # (10.6 + 52.0 MB: the CI vectors once, the split-K partials of the alpha slices)
+                         "traffic": 62.6e6 * len(my_pairs) / 210.0 if (n == 10 and NELEC == (5, 5)) else None,
+                         "traffic_source": "profiles/r02_trdm_pipe_ncu_full.txt"}}
 
     if rank != 0:
         if world > 1:
