@@ -43,6 +43,8 @@ def test_hand_value(solver):
     (5, (3, 2)), (6, (3, 3)), (6, (1, 1)), (7, (3, 3)), (7, (4, 2)), (8, (4, 4)), (8, (2, 2)),
     (9, (3, 3)), (10, (2, 2)), (11, (2, 2)), (12, (2, 2)), (13, (2, 2)), (13, (1, 2)),
     (6, (0, 0)), (6, (6, 6)), (5, (5, 0)),
+    # producer / consumer kernel (norb = 10, 11): even and odd beta counts, na != nb, one- and two-step CTAs
+    (10, (2, 3)), (10, (3, 2)), (10, (0, 1)), (10, (1, 0)), (10, (10, 10)), (10, (1, 4)), (11, (1, 3)), (11, (3, 3)),
 ])
 def test_against_oracle(solver, norb, nelec):
     from oracle import cistring as ocs, trans_rdm as otr
