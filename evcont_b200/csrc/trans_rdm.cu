@@ -567,6 +567,14 @@ int plan_trdm(int norb, int64_t na, int64_t nb, int npairs, int sm_count, TrdmPl
     }
   }
   if (best < 0) return -2;
+  {
+    // development aid: EVC_TRDM_BT forces the tile width (must be 4 mod 8 and fit); the results do not depend on it
+    // (the k order is the order of the beta strings whatever the tile boundaries, the padding adds exact zeros)
+    static const int force_bt = [] { const char* e = getenv("EVC_TRDM_BT"); return e ? atoi(e) : 0; }();
+    if (force_bt >= 12 && force_bt % 8 == 4 &&
+        2 * static_cast<size_t>(pl->W) * force_bt * 8 + crow_bytes <= (want_occ == 2 ? budget : smem_cap - 1024))
+      best = force_bt;
+  }
   pl->Bt = best;
   pl->ntile = static_cast<int>((nb + best - 1) / best);
   pl->smem = 2 * static_cast<size_t>(pl->W) * best * 8 + crow_bytes;
