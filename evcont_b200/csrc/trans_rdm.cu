@@ -246,23 +246,24 @@ trdm_fused_kernel(const __grid_constant__ TrdmParams P) {
 
 // ---- producer / consumer form of the fused kernel (7 or 8 macro-block rows: norb = 10, 11) ------------------------
 // The fused kernel above alternates a t1 tile build (latency-bound gathers) and a DMMA phase in every warp, two
-// CTAs per SM filling each other's gaps: the DMMA pipe is busy 51 % of the time.  Here ONE 16-warp CTA per SM holds
-// two tile stages: warps 8..15 build stage (it + 1) while warps 0..7 multiply stage it.  The builders hold no
+// CTAs per SM filling each other's gaps: the DMMA pipe is busy 51 % of the time.  Here ONE CTA per SM (16 or 20 warps) holds
+// two tile stages: the 8 builder warps build stage (it + 1) while the NMMA (8 or 12) MMA warps multiply stage it.  The builders hold no
 // accumulators, so they keep four link records and their eight gathers in flight per lane.  Hand-over by named
 // barriers (bar.arrive by the side that is done, bar.sync by the side that waits; the PTX producer / consumer
 // pattern).  Same tiles, same k order and same alpha slices as the fused kernel => bit-identical results.
 __device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-constexpr int kPipeMma = 8, kPipeBuild = 8;                      // warps per role
+constexpr int kPipeBuild = 8;                                    // builder warps (the MMA warps: template NMMA)
 constexpr int kBarFull = 1, kBarEmpty = 3, kBarBuild = 5;        // named barriers: full[2], empty[2], builders
 
+template <int NMMA>
 __device__ __forceinline__ void pipe_build(const TrdmParams& P, const double* __restrict__ cbra,
                                            const double* __restrict__ cket, int64_t Ia, int b0,
                                            double* __restrict__ braT, double* __restrict__ ketT,
                                            double* __restrict__ crow_bra, double* __restrict__ crow_ket) {
   constexpr int nthreads = kPipeBuild * 32;
-  const int tid = threadIdx.x - kPipeMma * 32;
+  const int tid = threadIdx.x - NMMA * 32;
   const int warp = tid >> 5, lane = tid & 31;
   const int n = P.norb, Bp = P.Bt;
   const int nb = static_cast<int>(P.nb);
@@ -366,8 +367,8 @@ __device__ __forceinline__ void pipe_build(const TrdmParams& P, const double* __
   }
 }
 
-template <int MAXBLK>
-__global__ void __launch_bounds__((kPipeMma + kPipeBuild) * 32, 1)
+template <int NMMA, int MAXBLK>
+__global__ void __launch_bounds__((NMMA + kPipeBuild) * 32, 1)
 trdm_pipe_kernel(const __grid_constant__ TrdmParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Bp = P.Bt;
@@ -386,10 +387,10 @@ trdm_pipe_kernel(const __grid_constant__ TrdmParams P) {
   const int64_t ia_lo = P.na * split / P.nsplit;
   const int64_t ia_hi = P.na * (split + 1) / P.nsplit;
   const int nsteps = static_cast<int>(ia_hi - ia_lo) * P.ntile;
-  constexpr int kAll = (kPipeMma + kPipeBuild) * 32;
+  constexpr int kAll = (NMMA + kPipeBuild) * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp >= kPipeMma) {
+  if (warp >= NMMA) {
     // ---- builders ----
     int64_t Ia = ia_lo;
     int tile = 0;
@@ -397,7 +398,7 @@ trdm_pipe_kernel(const __grid_constant__ TrdmParams P) {
       const int s = it & 1;
       if (it >= 2) bar_sync_n(kBarEmpty + s, kAll);  // the MMA warps are done with this stage
       double* braT = stage0 + 2 * s * tile_elems;
-      pipe_build(P, cbra, cket, Ia, tile * P.Bt, braT, braT + tile_elems, crow_bra, crow_ket);
+      pipe_build<NMMA>(P, cbra, cket, Ia, tile * P.Bt, braT, braT + tile_elems, crow_bra, crow_ket);
       __threadfence_block();
       bar_arrive_n(kBarFull + s, kAll);
       if (++tile == P.ntile) { tile = 0; ++Ia; }
@@ -521,7 +522,7 @@ __global__ void stack_scatter_rows_kernel(int N, int norb, const double* __restr
 struct TrdmPlan {
   int W, nblk, T, nwarps, maxblk, Bt, ntile, nsplit, occupancy;
   size_t smem;
-  bool pipe;         // producer / consumer kernel (two tile stages, one CTA per SM)
+  int pipe;          // producer / consumer kernel (two tile stages, one CTA per SM): 0 off, else the MMA warps / 4
   size_t smem_pipe;
 };
 
@@ -589,9 +590,12 @@ int plan_trdm(int norb, int64_t na, int64_t nb, int npairs, int sm_count, TrdmPl
   if (s > 4096) s = 4096;
   pl->nsplit = static_cast<int>(s);
   // the producer / consumer kernel keeps the tile width and the alpha slices of the fused plan (same bits)
-  static const int use_pipe = [] { const char* e = getenv("EVC_TRDM_PIPE"); return e ? atoi(e) : 1; }();
+  // EVC_TRDM_PIPE: 0 fused kernel, 1 eight MMA warps, 2 (default) twelve: a warp issues one DMMA per ~17-20 clocks and
+  // stops for its fragment loads, so three warps per SM sub-partition keep the pipe fed where two just did
+  // (norb = 11: 7.17 -> 7.01 ms, H10 8.33 -> 8.31 ms: there the builders are the slower side)
+  static const int use_pipe = [] { const char* e = getenv("EVC_TRDM_PIPE"); return e ? atoi(e) : 2; }();
   pl->smem_pipe = 2 * (pl->smem - crow_bytes) + crow_bytes;
-  pl->pipe = use_pipe && pl->nwarps == 8 && pl->nblk >= 7 && pl->smem_pipe + 1024 <= smem_cap;
+  pl->pipe = (use_pipe && pl->nwarps == 8 && pl->nblk >= 7 && pl->smem_pipe + 1024 <= smem_cap) ? (use_pipe == 2 ? 3 : 2) : 0;
   return 0;
 }
 
@@ -612,12 +616,12 @@ void assign_blocks(const TrdmPlan& pl, TrdmParams* P) {
   }
 }
 
-template <int MAXBLK>
+template <int NMMA, int MAXBLK>
 int launch_pipe(const TrdmParams& P, const TrdmPlan& pl, int nitems, cudaStream_t stream) {
-  auto kern = trdm_pipe_kernel<MAXBLK>;
+  auto kern = trdm_pipe_kernel<NMMA, MAXBLK>;
   EVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(pl.smem_pipe)));
-  kern<<<nitems, (kPipeMma + kPipeBuild) * 32, pl.smem_pipe, stream>>>(P);
+  kern<<<nitems, (NMMA + kPipeBuild) * 32, pl.smem_pipe, stream>>>(P);
   EVC_CHECK_LAUNCH();
   return 0;
 }
@@ -678,17 +682,29 @@ int evc_trans_rdm12_batch_strided(evc_ctx* ctx, int norb, int64_t na, int64_t nb
   P.civecs = civecs; P.vec_stride = vec_stride; P.pairs = pairs; P.nsplit = pl.nsplit;
   P.link_a = link_a; P.nlink_a = nlink_a; P.link_b = link_b; P.nlink_b = nlink_b;
   P.Bt = pl.Bt; P.ntile = pl.ntile; P.partial = static_cast<double*>(workspace); P.T = pl.T;
-  assign_blocks(pl, &P);
   const int nitems = npairs * pl.nsplit;
   int rc = -1;
   if (pl.pipe && pl.smem_pipe <= ctx->smem_optin) {
-    switch (pl.maxblk) {
-      case 3: rc = launch_pipe<3>(P, pl, nitems, ctx->stream); break;
-      case 4: rc = launch_pipe<4>(P, pl, nitems, ctx->stream); break;
-      case 5: rc = launch_pipe<5>(P, pl, nitems, ctx->stream); break;
-      default: break;
+    TrdmPlan pp = pl;  // macro-blocks dealt to the MMA warps of the producer / consumer kernel
+    pp.nwarps = 4 * pl.pipe;
+    pp.maxblk = ((pl.T + 3) / 4 + pl.pipe - 1) / pl.pipe;
+    assign_blocks(pp, &P);
+    if (pl.pipe == 2) {
+      switch (pp.maxblk) {
+        case 3: rc = launch_pipe<8, 3>(P, pl, nitems, ctx->stream); break;
+        case 4: rc = launch_pipe<8, 4>(P, pl, nitems, ctx->stream); break;
+        case 5: rc = launch_pipe<8, 5>(P, pl, nitems, ctx->stream); break;
+        default: break;
+      }
+    } else {
+      switch (pp.maxblk) {
+        case 2: rc = launch_pipe<12, 2>(P, pl, nitems, ctx->stream); break;
+        case 3: rc = launch_pipe<12, 3>(P, pl, nitems, ctx->stream); break;
+        default: break;
+      }
     }
   }
+  if (rc == -1) assign_blocks(pl, &P);
   if (rc != -1) {
     // launched above
   } else if (pl.nwarps == 8) {
