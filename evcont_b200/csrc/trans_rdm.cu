@@ -153,6 +153,124 @@ __device__ __forceinline__ void build_tiles(const TrdmParams& P, const double* _
   }
 }
 
+// The same build with NL link records (and their gathers) in flight per warp: for the instances whose accumulators
+// leave the registers for it (at most three macro-blocks per warp).
+template <int NWARPS, int NL>
+__device__ __forceinline__ void build_tiles_nl(const TrdmParams& P, const double* __restrict__ cbra,
+                                            const double* __restrict__ cket, int64_t Ia, int b0,
+                                            double* __restrict__ braT, double* __restrict__ ketT,
+                                            double* __restrict__ crow_bra,
+                                            double* __restrict__ crow_ket) {
+  constexpr int nthreads = NWARPS * 32;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n = P.norb, Bp = P.Bt;
+  const int nb = static_cast<int>(P.nb);
+  {
+    // braT and ketT are contiguous: one vectorised zero fill
+    double2* t2 = reinterpret_cast<double2*>(braT);
+    const int tot = P.W * Bp;
+    for (int k = tid; k < tot; k += nthreads) t2[k] = make_double2(0.0, 0.0);
+    if (b0 == 0) {  // c[Ia, :] rows change only with Ia
+      const double* sb = cbra + Ia * P.nb;
+      const double* sk = cket + Ia * P.nb;
+      for (int k = tid; k < nb; k += nthreads) {
+        crow_bra[k] = __ldg(sb + k);
+        crow_ket[k] = __ldg(sk + k);
+      }
+    }
+  }
+  __syncthreads();
+  const int width = min(P.Bt, nb - b0);
+  // beta links first, as pure stores into the zeroed tiles (one link per (column, x)); the alpha links then ADD
+  // their rows with contiguous 16-byte accesses.  (beta as read-modify-write cost four scattered shared-memory
+  // accesses per element instead of two; tile = alpha + beta either way, one rounding.)
+  for (int l0 = warp; l0 < P.nlink_b; l0 += NL * NWARPS) {
+    for (int x = lane; x < width; x += 32) {
+      uint64_t rec[NL];
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const int l = l0 + j * NWARPS;
+        rec[j] = l < P.nlink_b ? __ldg(P.link_b + static_cast<int64_t>(l) * P.nb + b0 + x) : ~0ull;
+      }
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        if (rec[j] != ~0ull) {
+          int Jb, a, i; double sg;
+          unpack_link(rec[j], Jb, a, i, sg);
+          const unsigned long long m = link_sign_mask(rec[j]);
+          braT[(a * n + i) * Bp + x] = flip(crow_bra[Jb], m);
+          ketT[(i * n + a) * Bp + x] = flip(crow_ket[Jb], m);
+        }
+      }
+    }
+  }
+  // identity column: the CI coefficients themselves
+  for (int x = tid; x < width; x += nthreads) {
+    braT[P.n2 * Bp + x] = crow_bra[b0 + x];
+    ketT[P.n2 * Bp + x] = crow_ket[b0 + x];
+  }
+  __syncthreads();
+  const uint64_t* la = P.link_a + Ia * P.nlink_a;
+  const bool vec2 = ((nb & 1) == 0) && ((b0 & 1) == 0) && ((width & 1) == 0);
+  for (int l0 = warp; l0 < P.nlink_a; l0 += NL * NWARPS) {
+    uint64_t rec[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int l = l0 + j * NWARPS;
+      rec[j] = l < P.nlink_a ? __ldg(la + l) : ~0ull;
+    }
+    if (vec2) {
+      for (int x = 2 * lane; x < width; x += 64) {
+        double2 vb[NL], vk[NL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          if (rec[j] != ~0ull) {
+            const int64_t off = static_cast<int64_t>(rec[j] & 0xffffffffu) * P.nb + b0 + x;
+            vb[j] = __ldg(reinterpret_cast<const double2*>(cbra + off));
+            vk[j] = __ldg(reinterpret_cast<const double2*>(cket + off));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          if (rec[j] != ~0ull) {
+            int Ja, a, i; double sg;
+            unpack_link(rec[j], Ja, a, i, sg);
+            const unsigned long long m = link_sign_mask(rec[j]);
+            double2* db = reinterpret_cast<double2*>(braT + (a * n + i) * Bp + x);
+            double2* dk = reinterpret_cast<double2*>(ketT + (i * n + a) * Bp + x);
+            const double2 tb = *db, tk = *dk;
+            *db = make_double2(tb.x + flip(vb[j].x, m), tb.y + flip(vb[j].y, m));
+            *dk = make_double2(tk.x + flip(vk[j].x, m), tk.y + flip(vk[j].y, m));
+          }
+        }
+      }
+    } else {
+      for (int x = lane; x < width; x += 32) {
+        double vb[NL], vk[NL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          if (rec[j] != ~0ull) {
+            const int64_t off = static_cast<int64_t>(rec[j] & 0xffffffffu) * P.nb + b0 + x;
+            vb[j] = __ldg(cbra + off);
+            vk[j] = __ldg(cket + off);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          if (rec[j] != ~0ull) {
+            int Ja, a, i; double sg;
+            unpack_link(rec[j], Ja, a, i, sg);
+            const unsigned long long m = link_sign_mask(rec[j]);
+            braT[(a * n + i) * Bp + x] += flip(vb[j], m);
+            ketT[(i * n + a) * Bp + x] += flip(vk[j], m);
+          }
+        }
+      }
+    }
+  }
+}
+
 // DMMA phase of one tile: NB macro-blocks of this warp, straight-line (all fragment loads of a k-step ahead of its
 // DMMAs; a per-block `s < my_count` branch kept every block's loads next to its own DMMAs, their latency exposed).
 template <int NB, int MAXBLK>
@@ -224,7 +342,12 @@ trdm_fused_kernel(const __grid_constant__ TrdmParams P) {
     for (int tile = 0; tile < P.ntile; ++tile) {
       const int b0 = tile * P.Bt;
       __syncthreads();  // previous MMA phase done with the tiles
-      build_tiles<NWARPS>(P, cbra, cket, Ia, b0, braT, ketT, crow_bra, crow_ket);
+      // two link records in flight per warp where the registers allow (norb = 9: 2.16 -> 2.06 ms; with four or five
+      // macro-blocks per warp the second set spills and H2O sizes lose: those keep the one-link build)
+      if constexpr (MAXBLK <= 3 && MINCTA * NWARPS <= 16)
+        build_tiles_nl<NWARPS, 2>(P, cbra, cket, Ia, b0, braT, ketT, crow_bra, crow_ket);
+      else
+        build_tiles<NWARPS>(P, cbra, cket, Ia, b0, braT, ketT, crow_bra, crow_ket);
       __syncthreads();
       // a warp has MAXBLK or MAXBLK - 1 macro-blocks (fewer: its spare slots repeat block 0 and are never stored)
       if (my_count == MAXBLK) mma_tile<MAXBLK, MAXBLK>(acc, braT, ketT, xoff, yoff, P.Bt, Bp);
