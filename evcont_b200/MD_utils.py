@@ -107,9 +107,7 @@ def get_trajectory(init_mol, overlap, one_rdm, two_rdm, dt=10.0, steps=10, init_
         raise NotImplementedError("hermitian=False is not implemented on the device")
     from .md import DeviceNVE
     from .mol import MolLite
-    if not isinstance(init_mol, MolLite):
-        raise TypeError("get_trajectory integrates on the device and needs an evcont_b200.mol.MolLite "
-                        "(use get_scanner with pyscf.md for a pyscf Mole)")
+    init_mol = MolLite.from_mol(init_mol)  # a PySCF-like Mole with a named basis is re-expressed for the device
     veloc = None if init_veloc is None else np.asarray(init_veloc, dtype=np.float64)[None]
     nve = DeviceNVE(init_mol, one_rdm, two_rdm, overlap, init_mol.atom_coords()[None], veloc, dt=dt,
                     max_frames=steps)
@@ -216,10 +214,13 @@ def converge_EVCont_MD(EVCont_obj, init_mol, steps=100, dt=1, convergence_thresh
     in a row; otherwise add the frame chosen by ``data_addition`` ("farthest_point_ham", "farthest_point"
     or "energy")}.  A non-empty ``trn_times`` resumes a previous run from the files in ``workdir``.
 
-    ``init_mol`` is an :class:`evcont_b200.mol.MolLite`; one process (the reference's MPI rank 0 does
+    ``init_mol`` is an :class:`evcont_b200.mol.MolLite` (or a PySCF-like Mole with a named basis, converted by
+    ``MolLite.from_mol``); one process (the reference's MPI rank 0 does
     all of this work and broadcasts).  ``workdir`` and ``max_iterations`` (a cap on added training
     points, ``None`` = the reference's unbounded loop) are additions.  Returns the last trajectory.
     """
+    from .mol import MolLite
+    init_mol = MolLite.from_mol(init_mol)
     trn_times = list(trn_times)
     path = lambda name: os.path.join(workdir, name)
     if len(trn_times) < 1:

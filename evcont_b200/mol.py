@@ -120,6 +120,28 @@ class MolLite:
         self._cache = None
 
     # --- geometry --------------------------------------------------------------
+    @classmethod
+    def from_mol(cls, mol):
+        """``mol`` itself if it is a :class:`MolLite`, else a :class:`MolLite` with the geometry, basis NAME, charge and
+        spin of a PySCF-like molecule (``natm``, ``atom_symbol(i)``, ``atom_coords()`` in bohr, ``basis``): what
+        ``get_trajectory`` (evcont/MD_utils.py:60-125) is handed by the reference's scripts.  A basis given as a dict
+        of explicit shells cannot be mapped onto the device basis tables and raises ``TypeError``."""
+        if isinstance(mol, cls):
+            return mol
+        try:
+            natm = int(mol.natm)
+            symbols = [str(mol.atom_symbol(i)) for i in range(natm)]
+            coords = np.asarray(mol.atom_coords(), dtype=np.float64).reshape(natm, 3)
+            basis = mol.basis
+        except AttributeError as exc:
+            raise TypeError("expected an evcont_b200.mol.MolLite or a PySCF-like molecule with natm, atom_symbol(), "
+                            f"atom_coords() and basis ({exc})") from None
+        if not isinstance(basis, str):
+            raise TypeError("the device integral kernels need a NAMED basis (sto-6g, 6-31g); got " +
+                            type(basis).__name__)
+        return cls([(sym, tuple(map(float, c))) for sym, c in zip(symbols, coords)], basis=basis, unit="Bohr",
+                   charge=int(getattr(mol, "charge", 0)), spin=int(getattr(mol, "spin", 0)))
+
     def atom_coords(self, unit="Bohr"):
         c = self._coords.copy()
         return c if unit.lower().startswith(("b", "au")) else c * BOHR

@@ -36,3 +36,36 @@ def test_energy_table_round_trip(tmp_path):
     assert np.allclose(tab[:, 1], ep) and np.allclose(tab[:, 3], ep + ek) and np.allclose(tab[:, 0], t)
     np.savetxt(path, np.column_stack([t, ep, ek, ep + ek]))      # a table without the header reads the same
     assert np.allclose(read_md_energies(path)[:, 1], ep)
+
+
+class _PyscfLikeMole:
+    """The slice of ``pyscf.gto.Mole`` that the reference's scripts hand to ``get_trajectory``
+    (evcont/MD_utils.py:60-125): geometry in bohr, a named basis, charge and spin."""
+
+    def __init__(self, symbols, coords, basis, charge=0, spin=0):
+        self._s, self._c = list(symbols), np.asarray(coords, dtype=float)
+        self.natm, self.basis, self.charge, self.spin = len(self._s), basis, charge, spin
+
+    def atom_symbol(self, i):
+        return self._s[i]
+
+    def atom_coords(self):
+        return self._c.copy()
+
+
+def test_mollite_from_pyscf_like_mole():
+    from evcont_b200.mol import MolLite
+    co = np.array([[0.0, 0.0, 0.0], [1.8, 0.1, 0.0], [3.5, 0.0, -0.2], [5.4, 0.0, 0.0]])
+    ref = MolLite([("H", tuple(c)) for c in co], basis="sto-6g", unit="Bohr")
+    got = MolLite.from_mol(_PyscfLikeMole(["H"] * 4, co, "sto-6g"))
+    assert isinstance(got, MolLite) and got.natm == 4 and got.nelec == ref.nelec and got.basis == "sto-6g"
+    assert np.array_equal(got.atom_coords(), ref.atom_coords())
+    assert [got.atom_symbol(i) for i in range(4)] == ["H"] * 4
+    assert MolLite.from_mol(ref) is ref                                  # a MolLite passes through untouched
+    ion = MolLite.from_mol(_PyscfLikeMole(["H"] * 3, co[:3], "sto-6g", charge=1))
+    assert ion.charge == 1 and sum(ion.nelec) == 2
+    import pytest
+    with pytest.raises(TypeError):
+        MolLite.from_mol(_PyscfLikeMole(["H"] * 4, co, {"H": [[0, (1.0, 1.0)]]}))   # explicit shells: no device table
+    with pytest.raises(TypeError):
+        MolLite.from_mol(object())
