@@ -214,13 +214,11 @@ def converge_EVCont_MD(EVCont_obj, init_mol, steps=100, dt=1, convergence_thresh
     in a row; otherwise add the frame chosen by ``data_addition`` ("farthest_point_ham", "farthest_point"
     or "energy")}.  A non-empty ``trn_times`` resumes a previous run from the files in ``workdir``.
 
-    ``init_mol`` is an :class:`evcont_b200.mol.MolLite` (or a PySCF-like Mole with a named basis, converted by
-    ``MolLite.from_mol``); one process (the reference's MPI rank 0 does
+    ``init_mol`` is an :class:`evcont_b200.mol.MolLite` (``MolLite.from_mol`` makes one from a PySCF-like Mole with a
+    named basis); one process (the reference's MPI rank 0 does
     all of this work and broadcasts).  ``workdir`` and ``max_iterations`` (a cap on added training
     points, ``None`` = the reference's unbounded loop) are additions.  Returns the last trajectory.
     """
-    from .mol import MolLite
-    init_mol = MolLite.from_mol(init_mol)
     trn_times = list(trn_times)
     path = lambda name: os.path.join(workdir, name)
     if len(trn_times) < 1:
