@@ -119,3 +119,27 @@ def test_product_never_imports_oracle():
         if name.endswith(".py"):
             src = open(os.path.join(pkg, name)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), name
+
+
+def test_trans_rdm_workspace_plan_is_a_pure_function_of_the_sizes():
+    """The alpha-slice plan (host code, no GPU) fixes the summation order of every pair: it must depend on the sizes
+    and the SM count only -- not on which kernel form (fused / producer-consumer, ``EVC_TRDM_PIPE``) runs it.
+    H10 sizes on 148 SMs: 210 pairs x 9 alpha slices x 28 macro-blocks x 256 doubles."""
+    lib = _lib.lib()
+    out = C.c_size_t(0)
+    assert lib.evc_trans_rdm12_workspace_bytes(10, 252, 252, 210, 148, C.byref(out)) == 0
+    assert out.value == 210 * 9 * 28 * 256 * 8
+    h10 = out.value
+    import subprocess
+    import sys
+    code = ("import ctypes as C; from evcont_b200 import _lib; o = C.c_size_t(0); "
+            "assert _lib.lib().evc_trans_rdm12_workspace_bytes(10, 252, 252, 210, 148, C.byref(o)) == 0; print(o.value)")
+    for pipe in ("0", "1", "2"):
+        env = dict(os.environ, EVC_TRDM_PIPE=pipe, PYTHONPATH=ROOT)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT)
+        assert res.returncode == 0, res.stderr
+        assert int(res.stdout.strip()) == h10
+    # a share of the pairs planned for the whole build is smaller only by the pair count
+    assert lib.evc_trans_rdm12_workspace_bytes(13, 1287, 1287, 10, 148, C.byref(out)) == 0
+    assert out.value % (10 * 66 * 256 * 8) == 0
+    assert lib.evc_trans_rdm12_workspace_bytes(14, 10, 10, 1, 148, C.byref(out)) != 0   # norb > 13: refused
